@@ -1,0 +1,173 @@
+/*
+ * rhj.h -- C ABI of the B200-native radix hash join (librhj.so).
+ *
+ * Drop-in boundary for the reference's join path.  The reference has no FFI:
+ * its seam is one C++ member function and one POD page format,
+ *     void Result::multiRadixHashJoin(JobScheduler&, relation&, relation&)   (Result.h:30, Result.cpp:90-124)
+ * called from Query::run_joins (Query.cpp:185-186) and consumed by
+ * update_intermediate (intermediate.cpp:146-183).  Every entry point below
+ * cites the reference code it replaces.  Plain pointers and sizes only; no
+ * C++ or torch types cross this boundary.
+ *
+ * Conventions
+ *   - every function returns an rhj_status (0 = RHJ_OK); rhj_last_error(ctx)
+ *     gives the text of the last failure on that context.  There is NO CPU
+ *     fallback: without a usable sm_100 device rhj_create fails.
+ *   - `*_device` entry points take DEVICE pointers and a cudaStream_t passed as
+ *     void* (NULL = the context's own stream).  They enqueue on that stream and,
+ *     unless stated otherwise, synchronise it before returning so that host
+ *     out-parameters are valid.
+ *   - `*_host` entry points take HOST pointers, do their own H2D/D2H.
+ *   - a context is NOT thread-safe; the reference calls the join from up to
+ *     NUM_OF_THREADS=8 query threads (MainScheduler.cpp:6-14), so the host side
+ *     keeps one context per query thread (contexts are independent).
+ *   - rhj_tuple.key is the ROW ID and rhj_tuple.payload the JOIN VALUE, exactly
+ *     as in the reference (structs.h:33-36, structs.cpp:222-223).
+ */
+#ifndef RHJ_H
+#define RHJ_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RHJ_VERSION "0.1.0"
+
+/* layout-identical to `tuple` (structs.h:33-36) */
+typedef struct rhj_tuple { uint64_t key; uint64_t payload; } rhj_tuple;
+/* layout-identical to `key_tuple` (Result.h:9-12): always R's row id first
+ * (Result.cpp:66-69, JobScheduler.cpp:187-190) */
+typedef struct rhj_pair { uint64_t keyR; uint64_t keyS; } rhj_pair;
+
+typedef struct rhj_ctx rhj_ctx;
+
+typedef enum rhj_status {
+    RHJ_OK = 0,
+    RHJ_ERR_CUDA = 1,        /* a CUDA runtime call or kernel failed            */
+    RHJ_ERR_ARG = 2,         /* bad argument                                     */
+    RHJ_ERR_NOMEM = 3,       /* device or pinned-host allocation failed          */
+    RHJ_ERR_CAPACITY = 4,    /* output buffer too small; *count holds the need   */
+    RHJ_ERR_STATE = 5,       /* call sequence error (e.g. write before count)    */
+    RHJ_ERR_NO_DEVICE = 6    /* no CUDA device / not sm_100                       */
+} rhj_status;
+
+/* digit function of the stand-alone partition entry points */
+#define RHJ_DIGIT_RAW  0     /* (payload >> shift) & (2^bits-1): the reference's payload & 0xFF when shift=0,bits=8
+                                (JobScheduler.cpp:151,171) */
+#define RHJ_DIGIT_HASH 1     /* same bits taken from the 32-bit mixed hash the join itself partitions on */
+
+/* emitter selection for rhj_join_device */
+#define RHJ_EMIT_FUSED 0           /* one probe pass, block-level atomic reservation in the caller's buffer   */
+#define RHJ_EMIT_COUNT_THEN_WRITE 1 /* two probe passes: count -> prefix sum -> write at fixed offsets        */
+
+/* filter operators = the reference's `op` characters (Query.cpp:94,114,133) */
+#define RHJ_OP_GT '>'
+#define RHJ_OP_LT '<'
+#define RHJ_OP_EQ '='
+
+/* ---- context ------------------------------------------------------------------------------ */
+
+/* Creates a context on CUDA device `device` (one per query thread; replaces the per-thread
+ * JobScheduler of MainScheduler.cpp:6-14 on this path). */
+int rhj_create(int device, rhj_ctx **ctx);
+int rhj_destroy(rhj_ctx *ctx);
+const char *rhj_last_error(const rhj_ctx *ctx);
+const char *rhj_version(void);
+/* Pre-sizes the device workspace for joins of up to nR x nS tuples (optional; the workspace
+ * grows on demand, and growing is a cudaMalloc that benchmarks want outside the timed region). */
+int rhj_reserve(rhj_ctx *ctx, uint64_t nR, uint64_t nS);
+/* Bytes of device workspace currently held. */
+uint64_t rhj_workspace_bytes(const rhj_ctx *ctx);
+
+/* ---- the join: Result::multiRadixHashJoin (Result.cpp:90-124) -------------------------------- */
+
+/* Device-resident join.  dR[nR], dS[nS] are read-only device arrays; d_out receives up to
+ * `capacity` pairs, *count the number of matching pairs (valid even on RHJ_ERR_CAPACITY, in
+ * which case only the first `capacity` reservations were written).  Output is the full multiset
+ * of (rowidR,rowidS) with equal payloads; order unspecified, as in the reference.
+ * `emit` is RHJ_EMIT_FUSED or RHJ_EMIT_COUNT_THEN_WRITE. */
+int rhj_join_device(rhj_ctx *ctx, const rhj_tuple *dR, uint64_t nR, const rhj_tuple *dS, uint64_t nS,
+                    rhj_pair *d_out, uint64_t capacity, uint64_t *count, int emit, void *stream);
+
+/* Two-call form of the count-then-write emitter (replaces add_result/addAll paging,
+ * Result.cpp:21-35,78-84,111-121): the first call partitions both relations and counts, the
+ * second writes exactly *count pairs into a buffer the caller sized from it. */
+int rhj_join_count_device(rhj_ctx *ctx, const rhj_tuple *dR, uint64_t nR, const rhj_tuple *dS, uint64_t nS,
+                          uint64_t *count, void *stream);
+int rhj_join_write_device(rhj_ctx *ctx, rhj_pair *d_out, uint64_t capacity, void *stream);
+
+/* Host-resident join: what Result::multiRadixHashJoin does for the query threads.  R and S are
+ * host arrays (the caller's relation::tuples, structs.h:38-40).  *out is a pinned host array of
+ * *count pairs owned by the context and valid until the next call on it (NULL when *count == 0,
+ * matching head == nullptr, Result.cpp:16-18). */
+int rhj_join_host(rhj_ctx *ctx, const rhj_tuple *R, uint64_t nR, const rhj_tuple *S, uint64_t nS,
+                  const rhj_pair **out, uint64_t *count);
+
+/* Materialises pairs[count] as the reference's page list (Result.cpp:21-35): malloc'd 128 KiB
+ * pages [next*][8191 x key_tuple], newest page first; *head_size = pairs in the head page
+ * (Result.size), every other page is full.  The pages are free()'d by ~Result (Result.cpp:127-133).
+ * Returns the head page (NULL when count == 0). */
+void *rhj_pairs_to_pages(const rhj_pair *pairs, uint64_t count, uint64_t *head_size);
+
+/* ---- the steps, individually callable (parity tests compare each with the reference) -------- */
+
+/* HistogramJob::run + global sum (JobScheduler.cpp:149-155, structs.cpp:168-173):
+ * d_hist[2^bits] (u64) = number of tuples per digit. */
+int rhj_histogram_device(rhj_ctx *ctx, const rhj_tuple *d_in, uint64_t n, int bits, int shift, int digit_kind,
+                         uint64_t *d_hist, void *stream);
+
+/* hash_relation (structs.cpp:144-204): d_out[n] = d_in[n] grouped by digit (not stable -- the
+ * reference's consumers never depend on the order inside a bucket), d_offsets[2^bits+1] (u64) =
+ * exclusive prefix sum of the histogram. */
+int rhj_partition_device(rhj_ctx *ctx, const rhj_tuple *d_in, uint64_t n, int bits, int shift, int digit_kind,
+                         rhj_tuple *d_out, uint64_t *d_offsets, void *stream);
+
+/* ---- neighbours of the join on the query path ------------------------------------------------ */
+
+/* Query::run_filters predicate scans (Query.cpp:94-146).  d_rowids_in == NULL means "all rows
+ * 0..n_in-1" of the column (the initial set fill, Query.cpp:85-87); otherwise only those rows
+ * are tested.  Survivors keep their input order.  d_rowids_out may alias d_rowids_in. */
+int rhj_filter_u64_device(rhj_ctx *ctx, const uint64_t *d_col, const uint64_t *d_rowids_in, uint64_t n_in,
+                          int op, uint64_t constant, uint64_t *d_rowids_out, uint64_t *count, void *stream);
+
+/* relation::foo (structs.cpp:217-226): d_out[i] = {rowids[i], col[rowids[i]]}. */
+int rhj_gather_tuples_device(rhj_ctx *ctx, const uint64_t *d_col, const uint64_t *d_rowids, uint64_t n,
+                             rhj_tuple *d_out, void *stream);
+
+/* column_proj (Query.cpp:66-74): *sum = sum of col[rowids[i]] mod 2^64. */
+int rhj_gather_sum_u64_device(rhj_ctx *ctx, const uint64_t *d_col, const uint64_t *d_rowids, uint64_t n,
+                              uint64_t *sum, void *stream);
+
+/* Order-independent digest of a device pair list: *sum / *xr = sum / xor over pairs of
+ * mix64(keyR * 0x100000001b3 + keyS)  (same function as orc_pairs_digest). */
+int rhj_pairs_digest_device(rhj_ctx *ctx, const rhj_pair *d_pairs, uint64_t n, uint64_t *sum, uint64_t *xr,
+                            void *stream);
+
+/* ---- multi-GPU (no reference equivalent) --------------------------------------- */
+
+/* Groups d_in[n] by destination rank = top log2(world) bits of the join hash (world a power of
+ * two <= 256).  d_out[n] is grouped by rank, h_counts[world] (host) the per-rank tuple counts;
+ * the caller exchanges the groups (NCCL all-to-all) and joins what it receives with
+ * rhj_join_device -- tuples with equal payloads always land on the same rank. */
+int rhj_shuffle_partition_device(rhj_ctx *ctx, const rhj_tuple *d_in, uint64_t n, int world,
+                                 rhj_tuple *d_out, uint64_t *h_counts, void *stream);
+
+/* ---- introspection for benchmarks ------------------------------------------------------------ */
+
+typedef struct rhj_plan_info {
+    uint32_t bits_total, bits_pass1, bits_pass2; /* radix bits: total and per pass (0 = pass skipped) */
+    uint32_t build_is_S;                         /* 1 if S (the smaller side) is the build side       */
+    uint32_t n_partitions;                       /* 2^bits_total                                      */
+    uint32_t n_items;                            /* probe work items of the last join                 */
+    uint32_t kernel_launches;                    /* kernels launched by the last join call            */
+    uint32_t reserved;
+} rhj_plan_info;
+int rhj_last_plan(const rhj_ctx *ctx, rhj_plan_info *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RHJ_H */
