@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- radixHashJoin input tuples/s on B200 (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5          # our arm (CUDA, librhj.so)
+    python bench.py --impl reference --steps 5 --warmup 3   # the reference's CPU path (oracle/_ref)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...   # N > 1: one rank per GPU, NCCL
+
+A "step" is one complete radix hash join (histogram -> prefix sum -> partition scatter (x2) ->
+build/probe -> emit) of the workload; inputs are resident in HBM before the timed region, the
+result stays in HBM.  N = 1 runs BASELINE.json configs[1] (2^27 x 2^27 unique uniform u64 keys).
+N > 1 is weak scaling: every rank owns 2^27 + 2^27 tuples of a global 2^(27+log2 N) pair of relations;
+a step = radix-partition both local shards by destination rank, NCCL all-to-all over NVLink, local join.
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "radixhashjoin_input_tuples_per_s"
+UNIT = "tuples/s"
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sample SM clock + throttle reasons DURING the timed region (B200_PROFILING.md)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thr = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+
+    def _loop(self):
+        nv = self._nvml
+        names = {}
+        for n in ("HwSlowdown", "HwThermalSlowdown", "SwThermalSlowdown", "SwPowerCap", "HwPowerBrakeSlowdown"):
+            v = getattr(nv, "nvmlClocksThrottleReason" + n, None) or getattr(nv, "nvmlClocksEventReason" + n, None)
+            if v is not None:
+                names[v] = n
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, n in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self._nvml is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        s = sorted(self.samples)
+        snake = {"HwSlowdown": "hw_slowdown", "HwThermalSlowdown": "hw_thermal_slowdown",
+                 "SwThermalSlowdown": "sw_thermal_slowdown", "SwPowerCap": "sw_power_cap",
+                 "HwPowerBrakeSlowdown": "hw_power_brake_slowdown"}
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(snake[r] for r in self.reasons), "samples": len(s)}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference arm / cpu_baseline: the reference's own multiRadixHashJoin on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(log2n, steps, warmup):
+    """Times oracle/_ref (the unmodified reference, NUM_OF_THREADS pthread workers) -- or, if that
+    build is absent, the single-threaded C port -- on a 2^log2n x 2^log2n sample of the uniform
+    workload.  Returns (tuples_per_s, seconds_per_step, info)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import _oracle as O
+    from radixhashjoin_b200 import workloads as W
+    w = W.uniform_unique(log2n, "cpu")
+    R, S = W.to_numpy_tuples(w.R), W.to_numpy_tuples(w.S)
+    n_in = len(R) + len(S)
+    times = []
+    if O.have_ref():
+        kind, cores = "reference", O.libref().ref_num_threads()
+        for i in range(warmup + steps):
+            cnt, sec = O.reference_join(R, S, want_pairs=False)
+            assert cnt == len(S)
+            if i >= warmup:
+                times.append(sec)
+    else:
+        kind, cores = "port", 1
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            p = O.oracle_join(R, S)
+            sec = time.perf_counter() - t0
+            assert len(p) == len(S)
+            if i >= warmup:
+                times.append(sec)
+    sec = sum(times) / len(times)
+    info = {"kind": kind, "cores": cores, "host_cpus": os.cpu_count(),
+            "sample": f"uniform_unique 2^{log2n} x 2^{log2n} (same generator as the GPU workload), "
+                      f"{steps} timed run(s) of Result::multiRadixHashJoin alone, inputs in host RAM"}
+    return n_in / sec, sec, info
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    log2n = args.ref_log2n
+    val, sec, info = cpu_reference_run(log2n, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"uniform_unique_u64 2^{args.log2n} x 2^{args.log2n} per GPU "
+                                   f"(BASELINE.json configs[1]); each step a bounded 2^{log2n} x 2^{log2n} sample"},
+            "cpu_baseline": dict(info, value=val, unit=UNIT),
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from radixhashjoin_b200 import RadixHashJoin, EMIT_FUSED, EMIT_COUNT_THEN_WRITE
+    from radixhashjoin_b200 import workloads as W
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    emit = EMIT_FUSED if args.emit == "fused" else EMIT_COUNT_THEN_WRITE
+    eng = RadixHashJoin(local_rank)
+    log2n = args.log2n
+    n_local = 1 << log2n
+
+    # ---- inputs, resident in HBM before the timed region ----
+    if world == 1:
+        if args.workload == "uniform":
+            w = W.uniform_unique(log2n, dev)
+        elif args.workload == "zipf":
+            w = W.zipf_probe(log2n, dev)
+        elif args.workload == "fk":
+            w = W.foreign_key(args.fk_build_log2, log2n, dev)
+        else:
+            raise SystemExit("unknown workload")
+        R, S, expected = w.R, w.S, w.expected
+        wname = w.name
+    else:
+        assert args.workload == "uniform", "multi-GPU bench runs the uniform workload (config 5 shape)"
+        gbits = log2n + (world.bit_length() - 1)
+        assert (1 << (world.bit_length() - 1)) == world, "world size must be a power of two"
+        w = W.uniform_unique(log2n, dev, row_offset=rank * n_local, log2_global=gbits)
+        R, S = w.R, w.S
+        expected = None
+        wname = f"uniform_unique_global_2^{gbits}x2^{gbits}_sharded_over_{world}"
+    nR, nS = R.shape[0], S.shape[0]
+    n_in_local = nR + nS
+
+    if world == 1:
+        cap = nS if args.workload != "dup" else nS
+        out = torch.empty((cap, 2), dtype=torch.int64, device=dev)
+        eng.reserve(nR, nS)
+
+        def step():
+            return eng.join_device(R, S, out=out, emit=emit)
+    else:
+        slack = int(n_local * 1.05) + 4096
+        recvR = torch.empty((slack, 2), dtype=torch.int64, device=dev)
+        recvS = torch.empty((slack, 2), dtype=torch.int64, device=dev)
+        out = torch.empty((slack, 2), dtype=torch.int64, device=dev)
+        eng.reserve(slack, slack)
+        cnt_send = torch.empty(2 * world, dtype=torch.int64, device=dev)
+        cnt_recv = torch.empty(2 * world, dtype=torch.int64, device=dev)
+
+        def step():
+            # (K8) group both shards by destination rank (our kernels), exchange over NVLink (NCCL), join locally
+            gR, cR = eng.shuffle_partition(R, world)
+            gS, cS = eng.shuffle_partition(S, world)
+            cnt_send.copy_(torch.tensor([v for pair in zip(cR, cS) for v in pair], dtype=torch.int64))
+            dist.all_to_all_single(cnt_recv, cnt_send)
+            cr = cnt_recv.cpu().tolist()
+            rR, rS = cr[0::2], cr[1::2]
+            assert sum(rR) <= slack and sum(rS) <= slack
+            dist.all_to_all_single(recvR[:sum(rR)], gR, output_split_sizes=rR, input_split_sizes=cR)
+            dist.all_to_all_single(recvS[:sum(rS)], gS, output_split_sizes=rS, input_split_sizes=cS)
+            return eng.join_device(recvR[:sum(rR)], recvS[:sum(rS)], out=out, emit=emit)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up, then EXACTLY K timed steps between barrier + synchronize ----
+    for _ in range(max(args.warmup, 3)):
+        pairs, count = step()
+    sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    ev0.record()
+    for _ in range(args.steps):
+        pairs, count = step()
+    ev1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    plan = eng.last_plan()
+    launches_per_step = plan["kernel_launches"] * (1 if world == 1 else 1) + (0 if world == 1 else 6)
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = n_in_local * world / (ms_step * 1e-3)
+
+    # ---- verification of the timed configuration (outside the timed region) ----
+    dig = eng.pairs_digest(pairs)
+    if world == 1:
+        verified = tuple(dig) == tuple(expected)
+    else:
+        tot = torch.tensor([dig[0], dig[1] - (1 << 64) if dig[1] >= (1 << 63) else dig[1]], dtype=torch.int64, device=dev)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        xr = [None] * world
+        dist.all_gather_object(xr, dig[2])
+        x = 0
+        for v in xr:
+            x ^= v
+        verified = None
+        if rank == 0:
+            gbits = log2n + (world.bit_length() - 1)
+            exp = W.uniform_unique_global_digest(gbits, dev)
+            verified = (int(tot[0].item()), int(tot[1].item()) & ((1 << 64) - 1), x) == tuple(exp)
+    m_local = count
+
+    # ---- per-phase device times -> roofline of the dominant kernel (separate, untimed passes) ----
+    eng.set_profiling(True)
+    acc = {}
+    reps = 5
+    for _ in range(reps):
+        step()
+        torch.cuda.synchronize()
+        for k, v in eng.last_phase_ms().items():
+            acc[k] = acc.get(k, 0.0) + v / reps
+    eng.set_profiling(False)
+    n_join = (recvR.shape[0] if world > 1 else nR) + (recvS.shape[0] if world > 1 else nS)
+    if world > 1:
+        n_join = n_in_local  # ~ balanced: what this rank joins after the exchange
+    alg_bytes = {"hist1": 16 * n_join, "scatter1": 32 * n_join, "hist2": 16 * n_join, "scatter2": 32 * n_join,
+                 "join": 16 * n_join + 16 * m_local, "join_write": 16 * n_join + 16 * m_local}
+    dom = max((k for k in alg_bytes if acc.get(k, 0) > 0), key=lambda k: acc[k], default=None)
+    peak, peak_src = measured_hbm_peak()
+    roofline = None
+    if dom:
+        ach = alg_bytes[dom] / (acc[dom] * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": None, "peak_source": peak_src, "kernel_ms": acc[dom],
+                    "algorithmic_bytes_per_launch": alg_bytes[dom]}
+    b_alg_step = 96 * n_join + 16 * m_local     # canonical 2-pass plan
+    step_gbs = b_alg_step / (ms_step * 1e-3) / 1e9
+
+    # ---- end to end through the host entry point (pinned host buffers, H2D + D2H inside) ----
+    e2e = None
+    if world == 1 and not args.no_e2e:
+        hR = torch.empty((nR, 2), dtype=torch.int64).pin_memory()
+        hS = torch.empty((nS, 2), dtype=torch.int64).pin_memory()
+        hR.copy_(R)
+        hS.copy_(S)
+        torch.cuda.synchronize()
+        for _ in range(2):
+            view, cnt = eng.join_host_view(hR, hS)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        k = max(1, min(args.steps, args.e2e_steps))
+        for _ in range(k):
+            view, cnt = eng.join_host_view(hR, hS)
+            first = int(view["keyR"][0])  # the host reads the result
+        dt = (time.perf_counter() - t0) / k
+        e2e = {"value": n_in_local / dt, "unit": UNIT, "h2d_bytes_per_step": 16 * n_in_local,
+               "d2h_bytes_per_step": 16 * cnt, "ms_per_step": dt * 1e3, "steps": k,
+               "api": "rhj_join_host (count-then-write emitter, pinned host inputs, pinned host result)"}
+        del hR, hS
+    elif world > 1:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "note": "multi-GPU run keeps shards device-resident; e2e is reported at N=1"}
+
+    # ---- CPU baseline on this box's host cores (rank 0, N = 1 only, bounded sample) ----
+    cpu = None
+    if world == 1 and rank == 0 and not args.no_cpu:
+        del out
+        torch.cuda.empty_cache()
+        v, sec, info = cpu_reference_run(args.cpu_log2n, 1, 0)
+        cpu = dict(info, value=v, unit=UNIT, seconds=sec)
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                "config": {"workload": wname, "tuples_per_gpu": n_in_local, "tuple_bytes": 16,
+                           "matches_per_gpu": int(m_local), "emitter": args.emit,
+                           "cache": "inputs (2 x %.1f GiB per GPU) are far larger than the 126 MB L2; no flush needed"
+                                    % (nR * 16 / 2**30),
+                           "radix_bits": [plan["bits_pass1"], plan["bits_pass2"]],
+                           "parallelism": "1 GPU" if world == 1 else f"{world} ranks: rank-radix shuffle (NCCL all-to-all) + local join"},
+                "verified": verified, "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
+                "phase_ms": {k: round(v, 4) for k, v in acc.items() if v > 0},
+                "roofline": roofline,
+                "step_roofline": {"algorithmic_bytes": b_alg_step, "formula": "96*n + 16*m (SURVEY 8d)",
+                                  "achieved_GBps": step_gbs, "frac_of_measured_hbm": step_gbs / peak},
+                "e2e": e2e, "cpu_baseline": cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log2n", type=int, default=27, help="tuples per relation per GPU = 2^log2n")
+    ap.add_argument("--workload", default="uniform", choices=["uniform", "zipf", "fk"])
+    ap.add_argument("--fk-build-log2", type=int, default=24)
+    ap.add_argument("--emit", default="fused", choices=["fused", "count_then_write"])
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-log2n", type=int, default=26, help="cpu_baseline sample size (2^k x 2^k)")
+    ap.add_argument("--ref-log2n", type=int, default=24, help="--impl reference: sample per step")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("launch N > 1 with torchrun (one rank per GPU); see the module docstring")
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

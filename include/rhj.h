@@ -167,6 +167,23 @@ typedef struct rhj_plan_info {
 } rhj_plan_info;
 int rhj_last_plan(const rhj_ctx *ctx, rhj_plan_info *info);
 
+/* Per-phase device times of the last join call, measured with CUDA events recorded on the
+ * launching stream between the kernels (off by default; costs one event record per phase).
+ * ms[RHJ_NUM_PHASES], indexed by the RHJ_PHASE_* constants; phases that did not run are 0. */
+#define RHJ_PHASE_HIST1 0      /* (1) histogram, pass 1                 */
+#define RHJ_PHASE_SCAN1 1      /* (2) prefix sum, pass 1                */
+#define RHJ_PHASE_SCATTER1 2   /* (3) partition scatter, pass 1         */
+#define RHJ_PHASE_HIST2 3      /* (1) histogram, pass 2                 */
+#define RHJ_PHASE_SCAN2 4      /* (2) prefix sum, pass 2                */
+#define RHJ_PHASE_SCATTER2 5   /* (3) partition scatter, pass 2         */
+#define RHJ_PHASE_PLAN 6       /* work-item planning                    */
+#define RHJ_PHASE_JOIN 7       /* (4)+(5) build/probe + fused emit, or the count pass */
+#define RHJ_PHASE_SCAN_ITEMS 8 /* (5) prefix sum of per-item counts     */
+#define RHJ_PHASE_JOIN_WRITE 9 /* (4)+(5) write pass                    */
+#define RHJ_NUM_PHASES 10
+int rhj_set_profiling(rhj_ctx *ctx, int on);
+int rhj_last_phase_ms(rhj_ctx *ctx, float *ms);
+
 #ifdef __cplusplus
 }
 #endif

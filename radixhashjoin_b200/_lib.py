@@ -1,0 +1,67 @@
+"""Loader of librhj.so, the C ABI declared in include/rhj.h.
+
+The CUDA library is the product: there is no Python or CPU fallback.  If the shared object is
+missing, or no sm_100 device is usable, importing callers get a RuntimeError -- never a silent
+slow path.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librhj.so")
+
+c_u64 = ctypes.c_uint64
+c_u64p = ctypes.POINTER(ctypes.c_uint64)
+c_vp = ctypes.c_void_p
+
+
+class PlanInfo(ctypes.Structure):
+    """struct rhj_plan_info (include/rhj.h)."""
+    _fields_ = [("bits_total", ctypes.c_uint32), ("bits_pass1", ctypes.c_uint32), ("bits_pass2", ctypes.c_uint32),
+                ("build_is_S", ctypes.c_uint32), ("n_partitions", ctypes.c_uint32), ("n_items", ctypes.c_uint32),
+                ("kernel_launches", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+
+
+# name -> (restype, argtypes): every symbol include/rhj.h declares
+SIGNATURES = {
+    "rhj_version": (ctypes.c_char_p, []),
+    "rhj_create": (ctypes.c_int, [ctypes.c_int, ctypes.POINTER(c_vp)]),
+    "rhj_destroy": (ctypes.c_int, [c_vp]),
+    "rhj_last_error": (ctypes.c_char_p, [c_vp]),
+    "rhj_reserve": (ctypes.c_int, [c_vp, c_u64, c_u64]),
+    "rhj_workspace_bytes": (c_u64, [c_vp]),
+    "rhj_join_device": (ctypes.c_int, [c_vp, c_vp, c_u64, c_vp, c_u64, c_vp, c_u64, c_u64p, ctypes.c_int, c_vp]),
+    "rhj_join_count_device": (ctypes.c_int, [c_vp, c_vp, c_u64, c_vp, c_u64, c_u64p, c_vp]),
+    "rhj_join_write_device": (ctypes.c_int, [c_vp, c_vp, c_u64, c_vp]),
+    "rhj_join_host": (ctypes.c_int, [c_vp, c_vp, c_u64, c_vp, c_u64, ctypes.POINTER(c_vp), c_u64p]),
+    "rhj_pairs_to_pages": (c_vp, [c_vp, c_u64, c_u64p]),
+    "rhj_histogram_device": (ctypes.c_int, [c_vp, c_vp, c_u64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp]),
+    "rhj_partition_device": (ctypes.c_int, [c_vp, c_vp, c_u64, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_vp, c_vp, c_vp]),
+    "rhj_filter_u64_device": (ctypes.c_int, [c_vp, c_vp, c_vp, c_u64, ctypes.c_int, c_u64, c_vp, c_u64p, c_vp]),
+    "rhj_gather_tuples_device": (ctypes.c_int, [c_vp, c_vp, c_vp, c_u64, c_vp, c_vp]),
+    "rhj_gather_sum_u64_device": (ctypes.c_int, [c_vp, c_vp, c_vp, c_u64, c_u64p, c_vp]),
+    "rhj_pairs_digest_device": (ctypes.c_int, [c_vp, c_vp, c_u64, c_u64p, c_u64p, c_vp]),
+    "rhj_shuffle_partition_device": (ctypes.c_int, [c_vp, c_vp, c_u64, ctypes.c_int, c_vp, c_u64p, c_vp]),
+    "rhj_last_plan": (ctypes.c_int, [c_vp, ctypes.POINTER(PlanInfo)]),
+    "rhj_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "rhj_last_phase_ms": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_float)]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen librhj.so and bind every declared entry point (no GPU needed for this)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C radixhashjoin_b200/csrc` -- there is no CPU fallback")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib

@@ -26,23 +26,21 @@ struct __align__(16) Pair {
 
 constexpr u32 kEmpty = 0xFFFFFFFFu;
 
-// 32-bit mixed hash of the join value.  Partition id = TOP bits, table slot = LOW bits.
-// (The reference buckets on the raw low byte, JobScheduler.cpp:151; any function of the value
-// gives the same join result, and mixed bits keep low-entropy contest columns balanced.)
-__device__ __forceinline__ u32 hash32(u64 v) {
+// Mixed hash of the join value.  hash32 = low word: partition id = its TOP bits, table slot = its
+// LOW bits.  hash_hi32 = high word: destination rank of the multi-GPU shuffle (independent bits,
+// so a rank's local partitions stay balanced).  (The reference buckets on the raw low byte,
+// JobScheduler.cpp:151; any function of the value gives the same join result, and mixed bits
+// keep low-entropy contest columns balanced.)
+__device__ __forceinline__ u64 hash64(u64 v) {
     v ^= v >> 32;
     v *= 0xd6e8feb86659fd93ULL;
     v ^= v >> 32;
     v *= 0xd6e8feb86659fd93ULL;
     v ^= v >> 32;
-    return (u32) v;
+    return v;
 }
-
-template <bool HASHED>
-__device__ __forceinline__ u32 digit_of(u64 v, int shift, u32 mask) {
-    if (HASHED) return (hash32(v) >> shift) & mask;
-    return (u32) (v >> shift) & mask;
-}
+__device__ __forceinline__ u32 hash32(u64 v) { return (u32) hash64(v); }
+__device__ __forceinline__ u32 hash_hi32(u64 v) { return (u32) (hash64(v) >> 32); }
 
 // splitmix64 finalizer -- digest only (same function as orc_mix64)
 __device__ __forceinline__ u64 mix64(u64 x) {

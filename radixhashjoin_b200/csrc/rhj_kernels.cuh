@@ -1,0 +1,740 @@
+// rhj_kernels.cuh -- the sm_100a kernels of the radix hash join.
+//
+// north_star step            reference loop it replaces                       kernel here
+//  (1) histogram             HistogramJob::run, JobScheduler.cpp:149-155      k_hist
+//  (2) prefix sum            PartitionJob::run 163-169, Result.cpp:100-107    k_scan_digits, k_scan_parts
+//  (3) partition scatter     PartitionJob::run 170-174 + structs.cpp:183-194  k_scatter
+//  (4) per-bucket build/probe Result::join_buckets, Result.cpp:43-76           k_join
+//  (5) emitter               add_result/addAll, Result.cpp:21-35,78-84,111-121 k_join<COUNT|WRITE|FUSED>, k_scan_items
+//  filters / gathers         Query.cpp:94-146, structs.cpp:217-226, Query.cpp:66-74   k_filter_*, k_gather_*
+//
+// Data layout in HBM: relations stay 16-byte AoS tuples {rowid, value} end to end (the caller's
+// layout, structs.h:33-36); partitions are contiguous ranges described by u64 offset arrays;
+// results are 16-byte {rowidR,rowidS} pairs (Result.h:9-12) in one flat array.
+#pragma once
+#include "rhj_device.cuh"
+
+namespace rhj {
+
+// ---- tuning constants -------------------------------------------------------------------------
+constexpr int kPartThreads = 512;               // threads per partition CTA
+constexpr int kPartItems = 8;                   // tuples per thread
+constexpr int kTile = kPartThreads * kPartItems;  // 4096 tuples = 64 KiB staged per CTA
+constexpr int kMaxBitsPerPass = 9;
+constexpr int kMaxDigits = 1 << kMaxBitsPerPass;  // 512 digits per pass
+
+constexpr int kJoinThreads = 512;
+constexpr int kJoinItems = 4;                        // probe tuples per thread per round
+constexpr int kRound = kJoinThreads * kJoinItems;    // 2048 probe tuples per round
+constexpr u32 kBuildCap = 4096;                      // build tuples per shared-memory table (64 KiB)
+constexpr u32 kSlots = 8192;                         // open-addressing slots (u32 index), load <= 0.5 (32 KiB)
+constexpr u32 kProbeChunk = 16384;                   // probe tuples per work item
+constexpr u32 kTargetBuildPerPart = 2048;            // radix bits are chosen for this average
+
+enum DigitKind { kDigitRaw = 0, kDigitHash = 1, kDigitRank = 2 };
+
+template <int KIND>
+__device__ __forceinline__ u32 digit(u64 v, int shift, u32 mask) {
+    if (KIND == kDigitRaw) return (u32) (v >> shift) & mask;
+    if (KIND == kDigitHash) return (hash32(v) >> shift) & mask;
+    return (hash_hi32(v) >> shift) & mask;
+}
+
+// ---- (1)+(3): descriptors of a partition pass over up to two relations at once ---------------
+struct PartRel {
+    const Tup *in;
+    Tup *out;
+    u64 n;
+    u64 *hist;             // [nseg * ndig] digit counts (written by k_hist)
+    u64 *cursor;           // [nseg * ndig] running output cursors (consumed by k_scatter)
+    const u64 *seg_off;    // SEG: [nseg+1] segment boundaries inside `in` (pass-1 partitions)
+    const u32 *seg_tile0;  // SEG: [nseg+1] first tile of each segment
+    u32 nseg;
+    u32 ntiles;            // tiles of this relation (SEG: host-side upper bound)
+};
+struct PartArgs {
+    PartRel rel[2];
+    int shift;
+    u32 mask;
+    u32 ndig;
+};
+
+// Maps a relation-local tile index to its tuple range.  SEG tiles never straddle a segment.
+template <bool SEG>
+__device__ __forceinline__ bool tile_range(const PartRel &r, u32 lt, u32 &seg, u64 &beg, u64 &end) {
+    if (!SEG) {
+        seg = 0;
+        beg = (u64) lt * kTile;
+        end = min(beg + (u64) kTile, r.n);
+        return beg < r.n;
+    }
+    if (lt >= r.seg_tile0[r.nseg]) return false;
+    u32 lo = 0, hi = r.nseg;  // last seg with seg_tile0[seg] <= lt
+    while (hi - lo > 1) {
+        u32 mid = (lo + hi) >> 1;
+        if (r.seg_tile0[mid] <= lt) lo = mid; else hi = mid;
+    }
+    seg = lo;
+    beg = r.seg_off[lo] + (u64) (lt - r.seg_tile0[lo]) * kTile;
+    end = min(beg + (u64) kTile, r.seg_off[lo + 1]);
+    return true;
+}
+
+// (1) Histogram.  Each CTA owns a contiguous range of tiles, counts digits in shared memory
+// (one ATOMS per tuple; with AGG the lanes of a warp that hit the same counter are combined
+// first by match.any so a skewed digit costs one atomic per warp instead of 32 serialised ones)
+// and flushes to the global u64 counters only when its (relation, segment) changes.
+// Algorithmic bytes: 16 per tuple read.
+template <int KIND, bool SEG, bool AGG>
+__global__ void __launch_bounds__(kPartThreads) k_hist(PartArgs a) {
+    __shared__ u32 s_h[kMaxDigits];
+    const u32 tid = threadIdx.x;
+    const u32 total = a.rel[0].ntiles + a.rel[1].ntiles;
+    const u32 per = (total + gridDim.x - 1) / gridDim.x;
+    const u32 t0 = min(total, blockIdx.x * per), t1 = min(total, t0 + per);
+    for (u32 d = tid; d < a.ndig; d += kPartThreads) s_h[d] = 0;
+    __syncthreads();
+    int cur_rel = -1;
+    u32 cur_seg = 0;
+    for (u32 t = t0; t < t1; ++t) {
+        const int ri = t >= a.rel[0].ntiles;
+        const PartRel &r = a.rel[ri];
+        u32 seg;
+        u64 beg, end;
+        if (!tile_range<SEG>(r, t - (ri ? a.rel[0].ntiles : 0), seg, beg, end)) continue;
+        if (cur_rel >= 0 && (ri != cur_rel || seg != cur_seg)) {
+            __syncthreads();
+            u64 *h = a.rel[cur_rel].hist + (u64) cur_seg * a.ndig;
+            for (u32 d = tid; d < a.ndig; d += kPartThreads) {
+                u32 c = s_h[d];
+                if (c) { atomicAdd(h + d, (u64) c); s_h[d] = 0; }
+            }
+            __syncthreads();
+        }
+        cur_rel = ri;
+        cur_seg = seg;
+        Tup v[kPartItems];
+        bool ok[kPartItems];
+#pragma unroll
+        for (int j = 0; j < kPartItems; ++j) {
+            u64 idx = beg + (u64) j * kPartThreads + tid;
+            ok[j] = idx < end;
+            if (ok[j]) v[j] = ld_stream(r.in + idx);
+        }
+#pragma unroll
+        for (int j = 0; j < kPartItems; ++j) {
+            u32 d = ok[j] ? digit<KIND>(v[j].val, a.shift, a.mask) : kEmpty;
+            if (AGG) {
+                u32 peers = __match_any_sync(0xffffffffu, d);
+                if (ok[j] && lane_id() == (u32) (__ffs(peers) - 1)) atomicAdd(&s_h[d], (u32) __popc(peers));
+            } else {
+                if (ok[j]) atomicAdd(&s_h[d], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    if (cur_rel >= 0) {
+        u64 *h = a.rel[cur_rel].hist + (u64) cur_seg * a.ndig;
+        for (u32 d = tid; d < a.ndig; d += kPartThreads) {
+            u32 c = s_h[d];
+            if (c) atomicAdd(h + d, (u64) c);
+        }
+    }
+}
+
+// (2a) Exclusive prefix sum over the <=512 digit counters of one pass, one CTA per relation.
+// Writes offsets[ndig+1], the scatter cursors (= offsets) and, when a second pass follows, the
+// first-tile table of the pass-1 partitions.
+struct ScanDigitsArgs {
+    const u64 *hist[2];
+    u64 *off[2];
+    u64 *cursor[2];
+    u32 *tile0[2];  // may be null
+    u32 ndig;
+};
+__global__ void __launch_bounds__(kMaxDigits) k_scan_digits(ScanDigitsArgs a) {
+    __shared__ u64 s_w[32];
+    __shared__ u32 s_wt[32];
+    const int ri = blockIdx.x;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    u64 c = tid < a.ndig ? a.hist[ri][tid] : 0;
+    u32 tl = (u32) ((c + kTile - 1) / kTile);
+    u64 inc = warp_incl_scan64(c);
+    u32 tinc = warp_incl_scan(tl);
+    if (lane == 31) { s_w[warp] = inc; s_wt[warp] = tinc; }
+    __syncthreads();
+    if (warp == 0) {
+        u64 w = lane < (kMaxDigits / 32) ? s_w[lane] : 0;
+        u32 wt = lane < (kMaxDigits / 32) ? s_wt[lane] : 0;
+        u64 wi = warp_incl_scan64(w);
+        u32 wti = warp_incl_scan(wt);
+        s_w[lane] = wi - w;
+        s_wt[lane] = wti - wt;
+    }
+    __syncthreads();
+    u64 ex = inc - c + s_w[warp];
+    u32 tex = tinc - tl + s_wt[warp];
+    if (tid < a.ndig) {
+        a.off[ri][tid] = ex;
+        a.cursor[ri][tid] = ex;
+        if (a.tile0[ri]) a.tile0[ri][tid] = tex;
+        if (tid == a.ndig - 1) {
+            a.off[ri][a.ndig] = ex + c;
+            if (a.tile0[ri]) a.tile0[ri][a.ndig] = tex + tl;
+        }
+    }
+}
+
+// (2b) Exclusive prefix sum over the 2^bits_total final partition counters (up to 2^18), one CTA
+// per relation, each thread owning a contiguous slice.
+struct ScanPartsArgs {
+    const u64 *hist[2];
+    u64 *off[2];
+    u64 *cursor[2];
+    u32 nparts;
+};
+__global__ void __launch_bounds__(1024) k_scan_parts(ScanPartsArgs a) {
+    __shared__ u64 s_w[32];
+    const int ri = blockIdx.x;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 per = (a.nparts + 1023) / 1024;
+    const u32 p0 = min(a.nparts, tid * per), p1 = min(a.nparts, p0 + per);
+    u64 c = 0;
+    for (u32 p = p0; p < p1; ++p) c += a.hist[ri][p];
+    u64 inc = warp_incl_scan64(c);
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        u64 w = s_w[lane];
+        u64 wi = warp_incl_scan64(w);
+        s_w[lane] = wi - w;
+    }
+    __syncthreads();
+    u64 run = inc - c + s_w[warp];
+    for (u32 p = p0; p < p1; ++p) {
+        a.off[ri][p] = run;
+        a.cursor[ri][p] = run;
+        run += a.hist[ri][p];
+    }
+    if (p1 == a.nparts && p0 < p1) a.off[ri][a.nparts] = run;
+    if (a.nparts == 0 && tid == 0) a.off[ri][0] = 0;
+}
+
+// (3) Partition scatter with shared-memory staging (software write-combining).
+// One CTA = one tile of 4096 tuples:
+//   load 8 tuples/thread (coalesced 16-B loads) -> rank each inside its digit with one
+//   shared-memory atomic -> one global atomic per non-empty digit reserves that digit's run in
+//   the output -> tuples are placed in shared memory sorted by digit -> the sorted tile is
+//   written out so that every digit's run is one contiguous burst: either by all threads
+//   (consecutive threads -> consecutive 16-B slots, full 32-B sectors / 128-B lines inside a run)
+//   or, with BULK, by one TMA bulk store (cp.async.bulk shared->global) per run.
+// Algorithmic bytes: 16 read + 16 written per tuple.
+template <int KIND, bool SEG, bool BULK>
+__global__ void __launch_bounds__(kPartThreads, 2) k_scatter(PartArgs a) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    Tup *s_tup = reinterpret_cast<Tup *>(dyn_smem);
+    __shared__ u32 s_cnt[kMaxDigits];
+    __shared__ u32 s_off[kMaxDigits];
+    __shared__ u64 s_delta[kMaxDigits];  // global index of sorted slot i of digit d = s_delta[d] + i
+    __shared__ u32 s_w[32];
+
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ri = blockIdx.x >= a.rel[0].ntiles;
+    const PartRel &r = a.rel[ri];
+    u32 seg;
+    u64 beg, end;
+    if (!tile_range<SEG>(r, blockIdx.x - (ri ? a.rel[0].ntiles : 0), seg, beg, end)) return;
+    const u32 ntile = (u32) (end - beg);
+
+    for (u32 d = tid; d < a.ndig; d += kPartThreads) s_cnt[d] = 0;
+    Tup v[kPartItems];
+    u32 dr[kPartItems];  // digit << 16 | rank   (rank < 4096)
+#pragma unroll
+    for (int j = 0; j < kPartItems; ++j) {
+        u32 i = j * kPartThreads + tid;
+        if (i < ntile) v[j] = ld_stream(r.in + beg + i);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kPartItems; ++j) {
+        u32 i = j * kPartThreads + tid;
+        if (i < ntile) {
+            u32 d = digit<KIND>(v[j].val, a.shift, a.mask);
+            u32 rk = atomicAdd(&s_cnt[d], 1u);
+            dr[j] = (d << 16) | rk;
+        }
+    }
+    __syncthreads();
+    // reserve the runs (global atomic issued first so its latency overlaps the block scan)
+    u32 c = tid < a.ndig ? s_cnt[tid] : 0;
+    u64 g = 0;
+    if (c) g = atomicAdd(r.cursor + (u64) seg * a.ndig + tid, (u64) c);
+    u32 inc = warp_incl_scan(c);
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        u32 w = lane < (kPartThreads / 32) ? s_w[lane] : 0;
+        u32 wi = warp_incl_scan(w);
+        s_w[lane] = wi - w;
+    }
+    __syncthreads();
+    if (tid < a.ndig) {
+        u32 ex = inc - c + s_w[warp];
+        s_off[tid] = ex;
+        s_delta[tid] = g - ex;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < kPartItems; ++j) {
+        u32 i = j * kPartThreads + tid;
+        if (i < ntile) s_tup[s_off[dr[j] >> 16] + (dr[j] & 0xffffu)] = v[j];
+    }
+    if (BULK) {
+        fence_async_smem();
+        __syncthreads();
+        for (u32 d = tid; d < a.ndig; d += kPartThreads) {
+            u32 cd = s_cnt[d];
+            if (cd) bulk_s2g(r.out + s_delta[d] + s_off[d], s_tup + s_off[d], cd * (u32) sizeof(Tup));
+        }
+        bulk_commit();
+        bulk_wait_read0();
+    } else {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kPartItems; ++j) {
+            u32 i = j * kPartThreads + tid;
+            if (i < ntile) {
+                Tup t = s_tup[i];
+                u32 d = digit<KIND>(t.val, a.shift, a.mask);
+                st_stream(r.out + s_delta[d] + i, t);
+            }
+        }
+    }
+}
+
+// ---- (4)+(5): work planning ---------------------------------------------------------------------
+struct Item {
+    u32 part;
+    u32 chunk;
+};
+struct PlanArgs {
+    const u64 *offB;  // [nparts+1] build-side partition offsets
+    const u64 *offP;  // [nparts+1] probe-side partition offsets
+    u32 nparts;
+    Item *items;
+    u32 item_cap;
+    u32 *nitems;
+    u32 *err;
+};
+// One work item per (partition with both sides non-empty, chunk of <= kProbeChunk probe tuples):
+// a skewed probe partition is split over many CTAs that each rebuild the (small) table.
+__global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
+    __shared__ u32 s_w[32];
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 per = (a.nparts + 1023) / 1024;
+    const u32 p0 = min(a.nparts, tid * per), p1 = min(a.nparts, p0 + per);
+    u32 c = 0;
+    for (u32 p = p0; p < p1; ++p) {
+        u64 nb = a.offB[p + 1] - a.offB[p], np = a.offP[p + 1] - a.offP[p];
+        if (nb && np) c += (u32) ((np + kProbeChunk - 1) / kProbeChunk);
+    }
+    u32 inc = warp_incl_scan(c);
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        u32 w = s_w[lane];
+        u32 wi = warp_incl_scan(w);
+        s_w[lane] = wi - w;
+        if (lane == 31) {
+            *a.nitems = wi <= a.item_cap ? wi : 0;
+            if (wi > a.item_cap) *a.err = 1;
+        }
+    }
+    __syncthreads();
+    u32 at = inc - c + s_w[warp];
+    for (u32 p = p0; p < p1; ++p) {
+        u64 nb = a.offB[p + 1] - a.offB[p], np = a.offP[p + 1] - a.offP[p];
+        if (nb && np) {
+            u32 k = (u32) ((np + kProbeChunk - 1) / kProbeChunk);
+            for (u32 ch = 0; ch < k; ++ch)
+                if (at + ch < a.item_cap) a.items[at + ch] = Item{p, ch};
+            at += k;
+        }
+    }
+}
+
+__global__ void k_set_single_part(u64 *offB, u64 nB, u64 *offP, u64 nP) {
+    offB[0] = 0; offB[1] = nB;
+    offP[0] = 0; offP[1] = nP;
+}
+
+// (5) prefix sum of the per-item match counts -> per-item output offsets + total
+__global__ void __launch_bounds__(1024) k_scan_items(const u64 *cnt, const u32 *nitems, u64 *off, u64 *total) {
+    __shared__ u64 s_w[32];
+    const u32 n = *nitems;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 per = (n + 1023) / 1024;
+    const u32 i0 = min(n, tid * per), i1 = min(n, i0 + per);
+    u64 c = 0;
+    for (u32 i = i0; i < i1; ++i) c += cnt[i];
+    u64 inc = warp_incl_scan64(c);
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        u64 w = s_w[lane];
+        u64 wi = warp_incl_scan64(w);
+        s_w[lane] = wi - w;
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    u64 run = inc - c + s_w[warp];
+    for (u32 i = i0; i < i1; ++i) {
+        off[i] = run;
+        run += cnt[i];
+    }
+}
+
+// ---- (4)+(5): per-partition build / probe / emit ----------------------------------------------
+enum JoinMode { kJoinCount = 0, kJoinWrite = 1, kJoinFused = 2 };
+
+struct JoinArgs {
+    const Tup *build;    // partitioned build relation (the smaller input)
+    const Tup *probe;    // partitioned probe relation
+    const u64 *offB;
+    const u64 *offP;
+    const Item *items;
+    const u32 *nitems;
+    u32 *work_counter;   // dynamic item scheduler
+    u64 *item_cnt;       // COUNT: out; per-item match count
+    const u64 *item_off; // WRITE: per-item output offset
+    u64 *out_cursor;     // FUSED: global reservation cursor (ends as the total match count)
+    Pair *out;
+    u64 capacity;
+    int build_is_S;      // output is always (rowidR, rowidS): Result.cpp:66-69
+};
+
+__device__ __forceinline__ u32 slot_of(u64 v) { return hash32(v) & (kSlots - 1); }
+
+// Persistent CTAs pull work items (partition p, probe chunk c).  For each build chunk of
+// <= 4096 tuples of partition p:
+//   - one elected thread TMA-bulk-loads the chunk's tuples verbatim into shared memory
+//     (cp.async.bulk + mbarrier) while all threads clear the slot table;
+//   - build: every tuple claims a slot of the open-addressing table (u32 index into the staged
+//     tuples, linear probing, atomicCAS on shared memory; load factor <= 0.5).  A claim that
+//     walks past an equal value flags the chunk as "has duplicate keys";
+//   - probe: rounds of 2048 probe tuples (4 per thread, coalesced 16-B loads).  Unique-key
+//     chunks stop at the first hit; duplicate-key chunks count, then re-walk to write.
+//   - emit: matches of a round are ranked with ballots + one shared atomic per warp; one thread
+//     reserves the round's output range (FUSED: one global atomic per round; WRITE: running
+//     offset from the count pass) and lanes write 16-B pairs at consecutive positions.
+// Algorithmic bytes: 16 per input tuple read + 16 per result pair written.
+template <int MODE>
+__global__ void __launch_bounds__(kJoinThreads, 2) k_join(JoinArgs a) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    Tup *s_tup = reinterpret_cast<Tup *>(dyn_smem);
+    u32 *s_slot = reinterpret_cast<u32 *>(dyn_smem + (size_t) kBuildCap * sizeof(Tup));
+    __shared__ __align__(8) u64 s_bar;
+    __shared__ u32 s_item;
+    __shared__ u32 s_cnt[2];
+    __shared__ u64 s_base[2];
+    __shared__ u64 s_red[32];
+
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 lt_mask = lanemask_lt();
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        s_cnt[0] = 0;
+        s_cnt[1] = 0;
+    }
+    __syncthreads();
+    const u32 nitems = *a.nitems;
+    u32 phase = 0, rr = 0;
+
+    while (true) {
+        if (tid == 0) s_item = atomicAdd(a.work_counter, 1u);
+        __syncthreads();
+        const u32 item = s_item;
+        if (item >= nitems) break;
+        const Item it = a.items[item];
+        const u64 b0 = a.offB[it.part], b1 = a.offB[it.part + 1];
+        const u64 p0 = a.offP[it.part] + (u64) it.chunk * kProbeChunk;
+        const u64 p1 = min(a.offP[it.part + 1], p0 + (u64) kProbeChunk);
+        u64 my_count = 0;                                   // COUNT
+        u64 run_base = (MODE == kJoinWrite && tid == 0) ? a.item_off[item] : 0;  // WRITE (thread 0 only)
+
+        for (u64 bb = b0; bb < b1; bb += kBuildCap) {
+            const u32 nb = (u32) min((u64) kBuildCap, b1 - bb);
+            if (tid == 0) {
+                mbar_expect_tx(&s_bar, nb * (u32) sizeof(Tup));
+                bulk_g2s(s_tup, a.build + bb, nb * (u32) sizeof(Tup), &s_bar);
+            }
+            for (u32 i = tid; i < kSlots; i += kJoinThreads) s_slot[i] = kEmpty;
+            mbar_wait(&s_bar, phase);
+            phase ^= 1;
+            __syncthreads();
+            // build
+            int dup = 0;
+            for (u32 i = tid; i < nb; i += kJoinThreads) {
+                const u64 v = s_tup[i].val;
+                u32 h = slot_of(v);
+                while (true) {
+                    u32 old = atomicCAS(&s_slot[h], kEmpty, i);
+                    if (old == kEmpty) break;
+                    if (s_tup[old].val == v) dup = 1;
+                    h = (h + 1) & (kSlots - 1);
+                }
+            }
+            dup = __syncthreads_or(dup);
+
+            // probe
+            for (u64 q0 = p0; q0 < p1; q0 += kRound) {
+                Tup t[kJoinItems];
+                bool ok[kJoinItems];
+#pragma unroll
+                for (int j = 0; j < kJoinItems; ++j) {
+                    u64 idx = q0 + (u64) j * kJoinThreads + tid;
+                    ok[j] = idx < p1;
+                    if (ok[j]) t[j] = ld_stream(a.probe + idx);
+                }
+                if (!dup) {
+                    // unique build keys: at most one match per probe tuple
+                    u32 m[kJoinItems], ball[kJoinItems];
+                    u32 wtotal = 0;
+#pragma unroll
+                    for (int j = 0; j < kJoinItems; ++j) {
+                        m[j] = kEmpty;
+                        if (ok[j]) {
+                            u32 h = slot_of(t[j].val);
+                            u32 idx;
+                            while ((idx = s_slot[h]) != kEmpty) {
+                                if (s_tup[idx].val == t[j].val) { m[j] = idx; break; }
+                                h = (h + 1) & (kSlots - 1);
+                            }
+                        }
+                        ball[j] = __ballot_sync(0xffffffffu, m[j] != kEmpty);
+                        wtotal += __popc(ball[j]);
+                    }
+                    if (MODE == kJoinCount) {
+                        if (lane == 0) my_count += wtotal;
+                        continue;
+                    }
+                    u32 wbase = 0;
+                    if (lane == 0 && wtotal) wbase = atomicAdd(&s_cnt[rr], wtotal);
+                    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                    __syncthreads();
+                    if (tid == 0) {
+                        u32 c = s_cnt[rr];
+                        u64 base;
+                        if (MODE == kJoinFused) base = c ? atomicAdd(a.out_cursor, (u64) c) : 0;
+                        else { base = run_base; run_base += c; }
+                        s_base[rr] = base;
+                        s_cnt[rr ^ 1] = 0;
+                    }
+                    __syncthreads();
+                    u64 pos = s_base[rr] + wbase;
+#pragma unroll
+                    for (int j = 0; j < kJoinItems; ++j) {
+                        if (m[j] != kEmpty) {
+                            u64 at = pos + __popc(ball[j] & lt_mask);
+                            u64 bk = s_tup[m[j]].key;
+                            if (at < a.capacity) {
+                                if (a.build_is_S) st_stream(a.out + at, t[j].key, bk);
+                                else st_stream(a.out + at, bk, t[j].key);
+                            }
+                        }
+                        pos += __popc(ball[j]);
+                    }
+                    rr ^= 1;
+                } else {
+                    // duplicate build keys: count every match, reserve, then re-walk and write
+                    u32 cnt[kJoinItems];
+                    u32 mine = 0;
+#pragma unroll
+                    for (int j = 0; j < kJoinItems; ++j) {
+                        cnt[j] = 0;
+                        if (ok[j]) {
+                            u32 h = slot_of(t[j].val);
+                            u32 idx;
+                            while ((idx = s_slot[h]) != kEmpty) {
+                                if (s_tup[idx].val == t[j].val) cnt[j]++;
+                                h = (h + 1) & (kSlots - 1);
+                            }
+                        }
+                        mine += cnt[j];
+                    }
+                    if (MODE == kJoinCount) {
+                        my_count += mine;
+                        continue;
+                    }
+                    u32 incl = warp_incl_scan(mine);
+                    u32 wtotal = __shfl_sync(0xffffffffu, incl, 31);
+                    u32 wbase = 0;
+                    if (lane == 0 && wtotal) wbase = atomicAdd(&s_cnt[rr], wtotal);
+                    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                    __syncthreads();
+                    if (tid == 0) {
+                        u32 c = s_cnt[rr];
+                        u64 base;
+                        if (MODE == kJoinFused) base = c ? atomicAdd(a.out_cursor, (u64) c) : 0;
+                        else { base = run_base; run_base += c; }
+                        s_base[rr] = base;
+                        s_cnt[rr ^ 1] = 0;
+                    }
+                    __syncthreads();
+                    u64 at = s_base[rr] + wbase + (incl - mine);
+#pragma unroll
+                    for (int j = 0; j < kJoinItems; ++j) {
+                        if (cnt[j]) {
+                            u32 h = slot_of(t[j].val);
+                            u32 idx;
+                            while ((idx = s_slot[h]) != kEmpty) {
+                                if (s_tup[idx].val == t[j].val) {
+                                    u64 bk = s_tup[idx].key;
+                                    if (at < a.capacity) {
+                                        if (a.build_is_S) st_stream(a.out + at, t[j].key, bk);
+                                        else st_stream(a.out + at, bk, t[j].key);
+                                    }
+                                    ++at;
+                                }
+                                h = (h + 1) & (kSlots - 1);
+                            }
+                        }
+                    }
+                    rr ^= 1;
+                }
+            }
+            __syncthreads();  // everyone is done with this table before it is overwritten
+        }
+        if (MODE == kJoinCount) {
+            u64 w = warp_sum64(my_count);
+            if (lane == 0) s_red[warp] = w;
+            __syncthreads();
+            if (warp == 0) {
+                u64 x = lane < (kJoinThreads / 32) ? s_red[lane] : 0;
+                x = warp_sum64(x);
+                if (lane == 0) a.item_cnt[item] = x;
+            }
+        }
+    }
+}
+
+// ---- digest of a pair list (parity checks at sizes where sorting is too slow) ------------------
+__global__ void __launch_bounds__(256) k_pairs_digest(const Pair *p, u64 n, u64 *sum, u64 *xr) {
+    u64 s = 0, x = 0;
+    for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x) {
+        Pair q = p[i];
+        u64 h = mix64(q.r * 0x100000001b3ULL + q.s);
+        s += h;
+        x ^= h;
+    }
+    s = warp_sum64(s);
+    x = warp_xor64(x);
+    if (lane_id() == 0) {
+        atomicAdd(sum, s);
+        atomicXor(xr, x);
+    }
+}
+
+// ---- filters and gathers (Query.cpp:94-146, structs.cpp:217-226, Query.cpp:66-74) --------------
+constexpr int kFiltThreads = 256;
+constexpr int kFiltItems = 8;
+constexpr int kFiltTile = kFiltThreads * kFiltItems;
+
+__device__ __forceinline__ bool pred(u64 v, int op, u64 c) {
+    return op == '>' ? v > c : op == '<' ? v < c : v == c;
+}
+
+// pass 1: survivors per tile
+__global__ void __launch_bounds__(kFiltThreads) k_filter_count(const u64 *col, const u64 *rowids, u64 n, int op, u64 c,
+                                                               u32 *tile_cnt) {
+    __shared__ u32 s_c;
+    if (threadIdx.x == 0) s_c = 0;
+    __syncthreads();
+    u64 base = (u64) blockIdx.x * kFiltTile;
+    u32 mine = 0;
+#pragma unroll
+    for (int j = 0; j < kFiltItems; ++j) {
+        u64 i = base + (u64) threadIdx.x * kFiltItems + j;
+        if (i < n) {
+            u64 row = rowids ? rowids[i] : i;
+            mine += pred(col[row], op, c);
+        }
+    }
+    u32 w = (u32) warp_sum64(mine);
+    if (lane_id() == 0 && w) atomicAdd(&s_c, w);
+    __syncthreads();
+    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = s_c;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_tiles(const u32 *cnt, u32 n, u64 *off, u64 *total) {
+    __shared__ u64 s_w[32];
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 per = (n + 1023) / 1024;
+    const u32 i0 = min(n, tid * per), i1 = min(n, i0 + per);
+    u64 c = 0;
+    for (u32 i = i0; i < i1; ++i) c += cnt[i];
+    u64 inc = warp_incl_scan64(c);
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        u64 w = s_w[lane];
+        u64 wi = warp_incl_scan64(w);
+        s_w[lane] = wi - w;
+        if (lane == 31) *total = wi;
+    }
+    __syncthreads();
+    u64 run = inc - c + s_w[warp];
+    for (u32 i = i0; i < i1; ++i) {
+        off[i] = run;
+        run += cnt[i];
+    }
+}
+
+// pass 2: order-preserving compaction (thread t owns 8 consecutive rows -> ascending output)
+__global__ void __launch_bounds__(kFiltThreads) k_filter_write(const u64 *col, const u64 *rowids, u64 n, int op, u64 c,
+                                                               const u64 *tile_off, u64 *out) {
+    __shared__ u32 s_w[kFiltThreads / 32];
+    u64 base = (u64) blockIdx.x * kFiltTile;
+    u64 row[kFiltItems];
+    bool keep[kFiltItems];
+    u32 mine = 0;
+#pragma unroll
+    for (int j = 0; j < kFiltItems; ++j) {
+        u64 i = base + (u64) threadIdx.x * kFiltItems + j;
+        keep[j] = false;
+        if (i < n) {
+            row[j] = rowids ? rowids[i] : i;
+            keep[j] = pred(col[row[j]], op, c);
+        }
+        mine += keep[j];
+    }
+    u32 incl = warp_incl_scan(mine);
+    if (lane_id() == 31) s_w[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    u32 before = 0;
+    for (u32 w = 0; w < (threadIdx.x >> 5); ++w) before += s_w[w];
+    u64 at = tile_off[blockIdx.x] + before + (incl - mine);
+#pragma unroll
+    for (int j = 0; j < kFiltItems; ++j)
+        if (keep[j]) out[at++] = row[j];
+}
+
+__global__ void __launch_bounds__(256) k_gather_tuples(const u64 *col, const u64 *rowids, u64 n, Tup *out) {
+    for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x) {
+        u64 row = rowids[i];
+        Tup t;
+        t.key = row;
+        t.val = col[row];
+        out[i] = t;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_gather_sum(const u64 *col, const u64 *rowids, u64 n, u64 *sum) {
+    u64 s = 0;
+    for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x)
+        s += col[rowids[i]];
+    s = warp_sum64(s);
+    if (lane_id() == 0 && s) atomicAdd(sum, s);
+}
+
+}  // namespace rhj

@@ -1,0 +1,251 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI
+(include/rhj.h via radixhashjoin_b200.api), against the oracle on the same inputs.
+
+Bar: BIT-EXACT.  Integer work only -- the sorted multiset of (rowidR,rowidS) pairs must be
+identical to the oracle's (the reference leaves the order unspecified), histograms must be equal
+counter by counter, partitions equal as per-bucket multisets.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import _oracle as O
+import query_oracle as Q
+from radixhashjoin_b200 import (EMIT_COUNT_THEN_WRITE, EMIT_FUSED, DIGIT_HASH, DIGIT_RAW, PAIR_DTYPE, RhjError,
+                                Relation, Result)
+from radixhashjoin_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def to_dev(t):
+    """numpy TUPLE array -> (n,2) int64 CUDA tensor"""
+    a = np.ascontiguousarray(t).view(np.uint64).reshape(-1, 2).view(np.int64)
+    return torch.from_numpy(a.copy()).to(DEV)
+
+
+def pairs_np(p):
+    return p.cpu().numpy().view(np.uint64).reshape(-1, 2).view(PAIR_DTYPE).reshape(-1)
+
+
+def tuples_np(t):
+    return t.cpu().numpy().view(np.uint64).reshape(-1, 2).view(O.TUPLE).reshape(-1)
+
+
+def rand_rel(rng, n, dom, id_base=0):
+    return O.as_tuples(rng.permutation(n).astype(np.uint64) + np.uint64(id_base),
+                       rng.integers(0, dom, n, dtype=np.uint64))
+
+
+def check_join(engine, R, S, emit, expect=None):
+    if expect is None:
+        expect = O.oracle_join(R, S)
+    cap = max(len(expect), 1)
+    out, n = engine.join_device(to_dev(R), to_dev(S), capacity=cap, emit=emit)
+    assert n == len(expect)
+    got = pairs_np(out)
+    assert np.array_equal(O.sort_pairs(got), O.sort_pairs(expect))
+    return engine.last_plan()
+
+
+# ---- step (1): histogram == HistogramJob/global sum, on the reference's own bucket function -------
+@pytest.mark.parametrize("n", [0, 1, 511, 4096, 4097, 100000, 1 << 20])
+def test_histogram_equals_reference_histogram(engine, n):
+    rng = np.random.default_rng(n + 1)
+    T = rand_rel(rng, n, 1 << 40)
+    _, hist = O.oracle_partition(T, 256)                     # relation_info.histogram, structs.cpp:168-173
+    got = engine.histogram(to_dev(T), 8, 0, DIGIT_RAW).cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, hist)
+
+
+def test_histogram_skewed_digit(engine):
+    """every tuple in one bucket (warp-aggregated counters must not lose counts)"""
+    T = O.as_tuples(np.arange(100000, dtype=np.uint64), np.full(100000, 0x1234_5600, dtype=np.uint64))
+    got = engine.histogram(to_dev(T), 8, 0, DIGIT_RAW).cpu().numpy()
+    assert got[0] == 100000 and got.sum() == 100000
+
+
+# ---- steps (2)+(3): partition == hash_relation as per-bucket multisets ---------------------------
+@pytest.mark.parametrize("n,bits", [(0, 8), (1, 8), (4096, 8), (50000, 8), (1 << 20, 8), (300000, 9), (70000, 3)])
+def test_partition_equals_reference_partition(engine, n, bits):
+    rng = np.random.default_rng(n + bits)
+    T = rand_rel(rng, n, 1 << 30)
+    exp, hist = O.oracle_partition(T, 1 << bits)
+    out, off = engine.partition(to_dev(T), bits, 0, DIGIT_RAW)
+    off = off.cpu().numpy().view(np.uint64)
+    assert np.array_equal(off, np.concatenate([[0], np.cumsum(hist)]).astype(np.uint64))
+    got = tuples_np(out)
+    mask = np.uint64((1 << bits) - 1)
+    assert np.array_equal(got["payload"] & mask, exp["payload"] & mask)      # same bucket sequence
+    key = lambda a: np.lexsort((a["key"], a["payload"], a["payload"] & mask))
+    assert np.array_equal(got[key(got)], exp[key(exp)])                      # same multiset per bucket
+
+
+def test_partition_hash_digits_is_a_permutation(engine):
+    rng = np.random.default_rng(77)
+    T = rand_rel(rng, 200000, 1 << 50)
+    out, off = engine.partition(to_dev(T), 9, 23, DIGIT_HASH)
+    got = tuples_np(out)
+    assert int(off[-1]) == len(T)
+    assert np.array_equal(np.sort(got, order=["key", "payload"]), np.sort(T, order=["key", "payload"]))
+
+
+# ---- steps (4)+(5): the join ------------------------------------------------------------------------
+EDGE = [(0, 0, 10), (0, 9, 10), (9, 0, 10), (1, 1, 1), (2, 3, 1), (5, 4, 2), (100, 100, 1 << 40), (4096, 4096, 1 << 20),
+        (4097, 4097, 1 << 20), (4097, 100000, 3000), (43000, 43100, 500), (20000, 3, 7), (3, 20000, 7),
+        (300000, 200000, 1 << 18), (1 << 20, 1 << 20, 1 << 19)]
+
+
+@pytest.mark.parametrize("emit", [EMIT_FUSED, EMIT_COUNT_THEN_WRITE])
+@pytest.mark.parametrize("nR,nS,dom", EDGE)
+def test_join_equals_oracle(engine, nR, nS, dom, emit):
+    rng = np.random.default_rng(nR * 7919 + nS * 31 + dom % 1000)
+    R, S = rand_rel(rng, nR, dom), rand_rel(rng, nS, dom, 1 << 33)
+    check_join(engine, R, S, emit)
+
+
+@pytest.mark.parametrize("emit", [EMIT_FUSED, EMIT_COUNT_THEN_WRITE])
+def test_join_u64_extremes(engine, emit):
+    """values and row ids at the u64 limits; 0xFFFF.. must not collide with any sentinel"""
+    rng = np.random.default_rng(5)
+    vals = np.array([0, 1, 2**32, 2**63, 2**64 - 1, 2**64 - 256, 255, 256], dtype=np.uint64)
+    R = O.as_tuples(rng.integers(2**40, 2**64 - 1, 6000, dtype=np.uint64), vals[rng.integers(0, len(vals), 6000)])
+    S = O.as_tuples(rng.integers(2**40, 2**64 - 1, 5000, dtype=np.uint64), vals[rng.integers(0, len(vals), 5000)])
+    check_join(engine, R, S, emit)
+
+
+@pytest.mark.parametrize("emit", [EMIT_FUSED, EMIT_COUNT_THEN_WRITE])
+def test_join_build_overflow_single_key(engine, emit):
+    """one build key repeated 10000 times: no radix bit can split it -> multi-round table loads"""
+    R = O.as_tuples(np.arange(10000, dtype=np.uint64), np.full(10000, 7, dtype=np.uint64))
+    S = O.as_tuples(np.arange(300, dtype=np.uint64) + np.uint64(50000),
+                    np.array([7, 8, 9] * 100, dtype=np.uint64))
+    plan = check_join(engine, R, S, emit)
+    assert plan["build_is_S"] == 1
+    check_join(engine, S, R, emit)
+
+
+@pytest.mark.parametrize("emit", [EMIT_FUSED, EMIT_COUNT_THEN_WRITE])
+def test_join_two_pass_plan(engine, emit):
+    """large enough for two radix passes (bits_total > 9), duplicates on both sides"""
+    rng = np.random.default_rng(123)
+    n = 3 << 20
+    R, S = rand_rel(rng, n, n // 2), rand_rel(rng, n, n // 2, 1 << 40)
+    plan = check_join(engine, R, S, emit)
+    assert plan["bits_pass2"] > 0 and plan["bits_total"] == plan["bits_pass1"] + plan["bits_pass2"]
+
+
+def test_join_zipf_probe_skew(engine):
+    """Zipf probe keys: one partition holds ~1/20 of the probe side -> probe chunking across CTAs"""
+    w = W.zipf_probe(20)
+    R, S = W.to_numpy_tuples(w.R), W.to_numpy_tuples(w.S)
+    exp = O.oracle_join(R, S)
+    assert O.pairs_digest(exp) == tuple(w.expected)
+    for emit in (EMIT_FUSED, EMIT_COUNT_THEN_WRITE):
+        check_join(engine, R, S, emit, exp)
+
+
+def test_fused_emitter_reports_needed_capacity(engine):
+    rng = np.random.default_rng(8)
+    R, S = rand_rel(rng, 5000, 50), rand_rel(rng, 5000, 50)
+    exp = O.oracle_join(R, S)
+    with pytest.raises(RhjError) as ei:
+        engine.join_device(to_dev(R), to_dev(S), capacity=10, emit=EMIT_FUSED)
+    assert ei.value.code == 4 and ei.value.needed == len(exp)
+
+
+def test_count_then_write_two_calls(engine):
+    rng = np.random.default_rng(9)
+    R, S = rand_rel(rng, 60000, 900), rand_rel(rng, 50000, 900)
+    exp = O.oracle_join(R, S)
+    n = engine.join_count_device(to_dev(R), to_dev(S))
+    assert n == len(exp)
+    out = torch.empty((n, 2), dtype=torch.int64, device=DEV)
+    engine.join_write_device(out)
+    assert np.array_equal(O.sort_pairs(pairs_np(out)), O.sort_pairs(exp))
+
+
+def test_join_host_and_result_mirror(engine):
+    """host relations in, reference-shaped Result out (Result.h:19-38)"""
+    rng = np.random.default_rng(10)
+    R, S = rand_rel(rng, 30000, 2000), rand_rel(rng, 40000, 2000)
+    exp = O.oracle_join(R, S)
+    res = Result(engine).multiRadixHashJoin(Relation(R), Relation(S))
+    assert not res.isEmpty() and len(res.pairs) == len(exp)
+    walked = np.concatenate(list(res.pages()))
+    assert np.array_equal(O.sort_pairs(walked), O.sort_pairs(exp))
+    assert res.size == (len(exp) % 8191 or 8191)
+    empty = Result(engine).multiRadixHashJoin(Relation(R[:10]), Relation(O.as_tuples([1], [2**60])))
+    assert empty.isEmpty()
+
+
+# ---- full-size properties (sizes the oracle cannot finish quickly): closed-form digest ---------------
+@pytest.mark.parametrize("make", [lambda: W.uniform_unique(24, DEV), lambda: W.foreign_key(16, 25, DEV),
+                                  lambda: W.zipf_probe(24, DEV)], ids=["uniform24", "fk16x25", "zipf24"])
+@pytest.mark.parametrize("emit", [EMIT_FUSED, EMIT_COUNT_THEN_WRITE])
+def test_closed_form_digest_large(engine, make, emit):
+    w = make()
+    out, n = engine.join_device(w.R, w.S, capacity=w.expected[0], emit=emit)
+    assert (n,) + engine.pairs_digest(out)[1:] == tuple(w.expected)
+
+
+def test_baseline_config2_uniform_2p27(engine):
+    """BASELINE.json configs[1]: 2^27 x 2^27 unique uniform u64, 1:1 -- count and digest in closed form"""
+    w = W.uniform_unique(27, DEV)
+    out, n = engine.join_device(w.R, w.S, capacity=1 << 27, emit=EMIT_FUSED)
+    assert (n,) + engine.pairs_digest(out)[1:] == tuple(w.expected)
+    plan = engine.last_plan()
+    assert plan["bits_total"] == 16
+
+
+# ---- neighbours: filters, gathers, checksum -----------------------------------------------------------
+def test_filter_gather_sum_equal_oracle(engine):
+    rng = np.random.default_rng(11)
+    n = 100003
+    col = rng.integers(0, 1000, n, dtype=np.uint64)
+    dcol = torch.from_numpy(col.view(np.int64)).to(DEV)
+    out = np.empty(n, dtype=np.uint64)
+    for op in "><=":
+        k = O.liborc().orc_filter(col.ctypes.data, n, ord(op), 500, out.ctypes.data)
+        got = engine.filter(dcol, op, 500).cpu().numpy().view(np.uint64)
+        assert np.array_equal(got, out[:k])
+    # a second predicate over the survivors of the first (Query.cpp applies filters in sequence)
+    first = engine.filter(dcol, ">", 200)
+    second = engine.filter(dcol, "<", 400, rowids=first).cpu().numpy().view(np.uint64)
+    assert np.array_equal(second, np.nonzero((col > 200) & (col < 400))[0].astype(np.uint64))
+    rows = rng.integers(0, n, 70001, dtype=np.uint64)
+    drows = torch.from_numpy(rows.view(np.int64)).to(DEV)
+    t = tuples_np(engine.gather_tuples(dcol, drows))
+    assert np.array_equal(t["key"], rows) and np.array_equal(t["payload"], col[rows.astype(np.int64)])
+    assert engine.gather_sum(dcol, drows) == O.liborc().orc_column_sum(col.ctypes.data, rows.ctypes.data, len(rows))
+
+
+def test_shuffle_partition_keeps_equal_values_together(engine):
+    rng = np.random.default_rng(12)
+    T = rand_rel(rng, 100000, 5000)
+    out, counts = engine.shuffle_partition(to_dev(T), 8)
+    got = tuples_np(out)
+    assert sum(counts) == len(T)
+    assert np.array_equal(np.sort(got, order=["key", "payload"]), np.sort(T, order=["key", "payload"]))
+    owner = {}
+    at = 0
+    for r, c in enumerate(counts):
+        for v in np.unique(got["payload"][at:at + c]):
+            assert owner.setdefault(int(v), r) == r
+        at += c
+
+
+# ---- the reference's own golden vectors through the CUDA join ------------------------------------------
+def test_small_workload_golden_through_gpu_join(engine, small_dir, small_joins_golden):
+    """small.work driven exactly like Query::execute with every join done by librhj.so: all 50 lines of
+    small/small.result and all 94 per-join digests the unmodified reference logged."""
+    rels = Q.load_workload(small_dir)
+    queries = Q.parse_work(os.path.join(small_dir, "small.work"))
+    expected = open(os.path.join(small_dir, "small.result")).read().split("\n")
+    trace = []
+    lines = [Q.execute(q, rels, lambda R, S: engine.join_host(R, S), trace) for q in queries]
+    assert lines == expected[:50]
+    assert sorted(Q.join_trace_record(*t) for t in trace) == small_joins_golden
