@@ -8,7 +8,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librhj.so")
+LIB_PATH = os.environ.get("RHJ_LIB") or os.path.join(_HERE, "librhj.so")  # RHJ_LIB: tuning builds only
 
 c_u64 = ctypes.c_uint64
 c_u64p = ctypes.POINTER(ctypes.c_uint64)

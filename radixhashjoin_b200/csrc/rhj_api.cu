@@ -14,6 +14,7 @@
 
 #include "../../include/rhj.h"
 #include "rhj_kernels.cuh"
+#include "rhj_join_v1.cuh"
 
 using namespace rhj;
 
@@ -49,7 +50,8 @@ struct rhj_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     bool hist_agg = false;
-    bool scatter_bulk = false;
+    int join_v = 2;           // RHJ_JOIN_V: 2 pipelined kernel, 1 first kernel, 11 first kernel + early probe loads
+    int scatter_mode = 0;     // 0 staged per-thread stores, 1 TMA bulk stores, 2 direct (RHJ_SCATTER_MODE)
 
     DevBuf bufA, bufB;        // pass-1 / pass-2 partitioned tuples (build side first, then probe side)
     DevBuf zero;              // hist1 | hist2 | scalars   (memset to 0 per call)
@@ -157,7 +159,7 @@ cudaError_t set_smem(K k, size_t bytes) {
 }
 
 constexpr size_t kScatterSmem = (size_t) kTile * sizeof(Tup);
-constexpr size_t kJoinSmem = (size_t) kBuildCap * sizeof(Tup) + (size_t) kSlots * sizeof(u32);
+constexpr size_t kJoinSmem = kJoinSmemBytes;
 
 int launch_hist(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, bool seg) {
     u32 total = a.rel[0].ntiles + a.rel[1].ntiles;
@@ -178,20 +180,24 @@ int launch_hist(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, bool
     return RHJ_OK;
 }
 
-template <int K, bool S, bool B>
+template <int K, bool S, int W>
 cudaError_t launch_scatter_t(cudaStream_t st, const PartArgs &a, u32 grid) {
-    cudaError_t e = set_smem(k_scatter<K, S, B>, kScatterSmem);
+    const size_t smem = W == kWriteDirect ? 0 : kScatterSmem;
+    cudaError_t e = set_smem(k_scatter<K, S, W>, smem);
     if (e != cudaSuccess) return e;
-    k_scatter<K, S, B><<<grid, kPartThreads, kScatterSmem, st>>>(a);
+    k_scatter<K, S, W><<<grid, kPartThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
 int launch_scatter(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, bool seg) {
     u32 grid = a.rel[0].ntiles + a.rel[1].ntiles;
     if (!grid) return RHJ_OK;
-    bool bulk = ctx->scatter_bulk;
+    const int w = ctx->scatter_mode;
     cudaError_t e;
-#define SC(K, S) (bulk ? launch_scatter_t<K, S, true>(st, a, grid) : launch_scatter_t<K, S, false>(st, a, grid))
+#define SC(K, S)                                                                   \
+    (w == 1 ? launch_scatter_t<K, S, kWriteBulk>(st, a, grid)                      \
+            : w == 2 ? launch_scatter_t<K, S, kWriteDirect>(st, a, grid)           \
+                     : launch_scatter_t<K, S, kWriteStaged>(st, a, grid))
     if (kind == kDigitRaw) e = seg ? SC(kDigitRaw, true) : SC(kDigitRaw, false);
     else if (kind == kDigitHash) e = seg ? SC(kDigitHash, true) : SC(kDigitHash, false);
     else e = seg ? SC(kDigitRank, true) : SC(kDigitRank, false);
@@ -203,9 +209,17 @@ int launch_scatter(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, b
 
 template <int MODE>
 int launch_join(rhj_ctx *ctx, cudaStream_t st, const JoinArgs &a, u32 item_cap) {
-    CK(set_smem(k_join<MODE>, kJoinSmem));
     u32 grid = std::min<u32>(std::max<u32>(item_cap, 1), (u32) ctx->num_sms * 2);
-    k_join<MODE><<<grid, kJoinThreads, kJoinSmem, st>>>(a);
+    if (ctx->join_v == 1) {
+        CK(set_smem(k_join_v1<MODE, false>, kV1JoinSmemBytes));
+        k_join_v1<MODE, false><<<grid, kJoinThreads, kV1JoinSmemBytes, st>>>(a);
+    } else if (ctx->join_v == 11) {
+        CK(set_smem(k_join_v1<MODE, true>, kV1JoinSmemBytes));
+        k_join_v1<MODE, true><<<grid, kJoinThreads, kV1JoinSmemBytes, st>>>(a);
+    } else {
+        CK(set_smem(k_join<MODE>, kJoinSmem));
+        k_join<MODE><<<grid, kJoinThreads, kJoinSmem, st>>>(a);
+    }
     CK(cudaGetLastError());
     ctx->info.kernel_launches++;
     return RHJ_OK;
@@ -275,6 +289,8 @@ int partition_and_plan(rhj_ctx *ctx, cudaStream_t st, const Tup *dR, u64 nR, con
     const u64 ntot = pl.nB + pl.nP;
     const Tup *finB, *finP;
     const u64 *offB, *offP;
+    bool planned = false;
+    u32 item_cap = 0;
 
     if (pl.bits == 0) {
         finB = inB;
@@ -331,16 +347,28 @@ int partition_and_plan(rhj_ctx *ctx, cudaStream_t st, const Tup *dR, u64 nR, con
             mark(ctx, st, RHJ_PHASE_HIST2);
             if ((rc = launch_hist(ctx, st, b, kDigitHash, true))) return rc;
             mark(ctx, st, RHJ_PHASE_SCAN2);
-            ScanPartsArgs sp{};
+            // offsets of all 2^bits sub-partitions + the work-item list, one CTA per pass-1 partition
+            u64 cap64 = (u64) pl.nparts + pl.nP / kProbeChunk + 2;
+            if (cap64 > 0x7fffffffull) return fail(ctx, RHJ_ERR_ARG, "relation too large for the work-item table");
+            item_cap = (u32) cap64;
+            if ((rc = ensure(ctx, ctx->items, (size_t) item_cap * sizeof(Item)))) return rc;
+            ScanPlanArgs sp{};
             for (int i = 0; i < 2; ++i) {
-                sp.hist[i] = m.hist2[i];
-                sp.off[i] = m.off2[i];
-                sp.cursor[i] = m.cur2[i];
+                sp.hist2[i] = m.hist2[i];
+                sp.off1[i] = m.off1[i];
+                sp.off2[i] = m.off2[i];
+                sp.cursor2[i] = m.cur2[i];
             }
-            sp.nparts = pl.nparts;
-            k_scan_parts<<<2, 1024, 0, st>>>(sp);
+            sp.nseg = nseg;
+            sp.ndig = b.ndig;
+            sp.items = (Item *) ctx->items.p;
+            sp.item_cap = item_cap;
+            sp.nitems = (u32 *) (m.scalars + kScNItems);
+            sp.err = (u32 *) (m.scalars + kScErr);
+            k_scan_parts_plan<<<nseg, kMaxDigits, 0, st>>>(sp);
             CK(cudaGetLastError());
             ctx->info.kernel_launches++;
+            planned = true;
             // segment offsets inside A are relative to each relation's base: rel.in already points there
             mark(ctx, st, RHJ_PHASE_SCATTER2);
             if ((rc = launch_scatter(ctx, st, b, kDigitHash, true))) return rc;
@@ -351,23 +379,25 @@ int partition_and_plan(rhj_ctx *ctx, cudaStream_t st, const Tup *dR, u64 nR, con
         }
     }
 
-    // ---- plan: work items ----
-    mark(ctx, st, RHJ_PHASE_PLAN);
-    u64 cap64 = (u64) pl.nparts + pl.nP / kProbeChunk + 2;
-    if (cap64 > 0x7fffffffull) return fail(ctx, RHJ_ERR_ARG, "relation too large for the work-item table");
-    u32 item_cap = (u32) cap64;
-    if ((rc = ensure(ctx, ctx->items, (size_t) item_cap * sizeof(Item)))) return rc;
-    PlanArgs pa{};
-    pa.offB = offB;
-    pa.offP = offP;
-    pa.nparts = pl.nparts;
-    pa.items = (Item *) ctx->items.p;
-    pa.item_cap = item_cap;
-    pa.nitems = (u32 *) (m.scalars + kScNItems);
-    pa.err = (u32 *) (m.scalars + kScErr);
-    k_plan<<<1, 1024, 0, st>>>(pa);
-    CK(cudaGetLastError());
-    ctx->info.kernel_launches++;
+    // ---- plan: work items (two-pass plans were planned by k_scan_parts_plan) ----
+    if (!planned) {
+        mark(ctx, st, RHJ_PHASE_PLAN);
+        u64 cap64 = (u64) pl.nparts + pl.nP / kProbeChunk + 2;
+        if (cap64 > 0x7fffffffull) return fail(ctx, RHJ_ERR_ARG, "relation too large for the work-item table");
+        item_cap = (u32) cap64;
+        if ((rc = ensure(ctx, ctx->items, (size_t) item_cap * sizeof(Item)))) return rc;
+        PlanArgs pa{};
+        pa.offB = offB;
+        pa.offP = offP;
+        pa.nparts = pl.nparts;
+        pa.items = (Item *) ctx->items.p;
+        pa.item_cap = item_cap;
+        pa.nitems = (u32 *) (m.scalars + kScNItems);
+        pa.err = (u32 *) (m.scalars + kScErr);
+        k_plan<<<1, 1024, 0, st>>>(pa);
+        CK(cudaGetLastError());
+        ctx->info.kernel_launches++;
+    }
 
     ctx->cur.valid = true;
     ctx->cur.build = finB;
@@ -465,7 +495,8 @@ int rhj_create(int device, rhj_ctx **out) {
     ctx->num_sms = prop.multiProcessorCount;
     const char *e;
     if ((e = getenv("RHJ_HIST_AGG"))) ctx->hist_agg = atoi(e) != 0;
-    if ((e = getenv("RHJ_SCATTER_BULK"))) ctx->scatter_bulk = atoi(e) != 0;
+    if ((e = getenv("RHJ_SCATTER_MODE"))) ctx->scatter_mode = atoi(e);
+    if ((e = getenv("RHJ_JOIN_V"))) ctx->join_v = atoi(e);
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaHostAlloc((void **) &ctx->h_scalars, kScCount * sizeof(u64), cudaHostAllocDefault) != cudaSuccess) {

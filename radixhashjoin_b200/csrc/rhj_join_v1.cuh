@@ -1,0 +1,226 @@
+// rhj_join_v1.cuh -- the first (single-buffered, dynamically scheduled) join kernel, kept for A/B
+// measurements against rhj_join.cuh (RHJ_JOIN_V=1).  Same semantics; see rhj_join.cuh for the
+// description of the phases.  EARLY = issue the probe loads of round 0 before waiting for the TMA.
+#pragma once
+#include "rhj_join.cuh"
+
+namespace rhj {
+
+constexpr u32 kV1BuildCap = 4096;
+constexpr u32 kV1Slots = 8192;
+constexpr size_t kV1JoinSmemBytes = (size_t) kV1BuildCap * sizeof(Tup) + (size_t) kV1Slots * sizeof(u32);
+
+__device__ __forceinline__ u32 slot_of_v1(u64 v) { return hash32(v) & (kV1Slots - 1); }
+
+// Persistent CTAs pull work items (partition p, probe chunk c).  For each build chunk of
+// <= 4096 tuples of partition p:
+//   - one elected thread TMA-bulk-loads the chunk's tuples verbatim into shared memory
+//     (cp.async.bulk + mbarrier) while all threads clear the slot table;
+//   - build: every tuple claims a slot of the open-addressing table (u32 index into the staged
+//     tuples, linear probing, atomicCAS on shared memory; load factor <= 0.5).  A claim that
+//     walks past an equal value flags the chunk as "has duplicate keys";
+//   - probe: rounds of 2048 probe tuples (4 per thread, coalesced 16-B loads).  Unique-key
+//     chunks stop at the first hit; duplicate-key chunks count, then re-walk to write.
+//   - emit: matches of a round are ranked with ballots + one shared atomic per warp; one thread
+//     reserves the round's output range (FUSED: one global atomic per round; WRITE: running
+//     offset from the count pass) and lanes write 16-B pairs at consecutive positions.
+// Algorithmic bytes: 16 per input tuple read + 16 per result pair written.
+template <int MODE, bool EARLY>
+__global__ void __launch_bounds__(kJoinThreads, 2) k_join_v1(JoinArgs a) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    Tup *s_tup = reinterpret_cast<Tup *>(dyn_smem);
+    u32 *s_slot = reinterpret_cast<u32 *>(dyn_smem + (size_t) kV1BuildCap * sizeof(Tup));
+    __shared__ __align__(8) u64 s_bar;
+    __shared__ u32 s_item;
+    __shared__ u32 s_cnt[2];
+    __shared__ u64 s_base[2];
+    __shared__ u64 s_red[32];
+
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 lt_mask = lanemask_lt();
+    if (tid == 0) {
+        mbar_init(&s_bar, 1);
+        s_cnt[0] = 0;
+        s_cnt[1] = 0;
+    }
+    __syncthreads();
+    const u32 nitems = *a.nitems;
+    u32 phase = 0, rr = 0;
+
+    while (true) {
+        if (tid == 0) s_item = atomicAdd(a.work_counter, 1u);
+        __syncthreads();
+        const u32 item = s_item;
+        if (item >= nitems) break;
+        const Item it = a.items[item];
+        const u64 b0 = a.offB[it.part], b1 = a.offB[it.part + 1];
+        const u64 p0 = a.offP[it.part] + (u64) it.chunk * kProbeChunk;
+        const u64 p1 = min(a.offP[it.part + 1], p0 + (u64) kProbeChunk);
+        u64 my_count = 0;                                   // COUNT
+        u64 run_base = (MODE == kJoinWrite && tid == 0) ? a.item_off[item] : 0;  // WRITE (thread 0 only)
+
+        for (u64 bb = b0; bb < b1; bb += kV1BuildCap) {
+            const u32 nb = (u32) min((u64) kV1BuildCap, b1 - bb);
+            if (tid == 0) {
+                mbar_expect_tx(&s_bar, nb * (u32) sizeof(Tup));
+                bulk_g2s(s_tup, a.build + bb, nb * (u32) sizeof(Tup), &s_bar);
+            }
+            Tup t[kJoinItems];
+            if (EARLY) {
+#pragma unroll
+                for (int j = 0; j < kJoinItems; ++j) {
+                    u64 idx = p0 + (u64) j * kJoinThreads + tid;
+                    if (idx < p1) t[j] = ld_stream(a.probe + idx);
+                }
+            }
+            for (u32 i = tid; i < kV1Slots; i += kJoinThreads) s_slot[i] = kEmpty;
+            mbar_wait(&s_bar, phase);
+            phase ^= 1;
+            __syncthreads();
+            // build
+            int dup = 0;
+            for (u32 i = tid; i < nb; i += kJoinThreads) {
+                const u64 v = s_tup[i].val;
+                u32 h = slot_of_v1(v);
+                while (true) {
+                    u32 old = atomicCAS(&s_slot[h], kEmpty, i);
+                    if (old == kEmpty) break;
+                    if (s_tup[old].val == v) dup = 1;
+                    h = (h + 1) & (kV1Slots - 1);
+                }
+            }
+            dup = __syncthreads_or(dup);
+
+            // probe
+            for (u64 q0 = p0; q0 < p1; q0 += kRound) {
+                bool ok[kJoinItems];
+#pragma unroll
+                for (int j = 0; j < kJoinItems; ++j) {
+                    u64 idx = q0 + (u64) j * kJoinThreads + tid;
+                    ok[j] = idx < p1;
+                    if (ok[j] && !(EARLY && q0 == p0)) t[j] = ld_stream(a.probe + idx);
+                }
+                if (!dup) {
+                    // unique build keys: at most one match per probe tuple
+                    u32 m[kJoinItems], ball[kJoinItems];
+                    u32 wtotal = 0;
+#pragma unroll
+                    for (int j = 0; j < kJoinItems; ++j) {
+                        m[j] = kEmpty;
+                        if (ok[j]) {
+                            u32 h = slot_of_v1(t[j].val);
+                            u32 idx;
+                            while ((idx = s_slot[h]) != kEmpty) {
+                                if (s_tup[idx].val == t[j].val) { m[j] = idx; break; }
+                                h = (h + 1) & (kV1Slots - 1);
+                            }
+                        }
+                        ball[j] = __ballot_sync(0xffffffffu, m[j] != kEmpty);
+                        wtotal += __popc(ball[j]);
+                    }
+                    if (MODE == kJoinCount) {
+                        if (lane == 0) my_count += wtotal;
+                        continue;
+                    }
+                    u32 wbase = 0;
+                    if (lane == 0 && wtotal) wbase = atomicAdd(&s_cnt[rr], wtotal);
+                    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                    __syncthreads();
+                    if (tid == 0) {
+                        u32 c = s_cnt[rr];
+                        u64 base;
+                        if (MODE == kJoinFused) base = c ? atomicAdd(a.out_cursor, (u64) c) : 0;
+                        else { base = run_base; run_base += c; }
+                        s_base[rr] = base;
+                        s_cnt[rr ^ 1] = 0;
+                    }
+                    __syncthreads();
+                    u64 pos = s_base[rr] + wbase;
+#pragma unroll
+                    for (int j = 0; j < kJoinItems; ++j) {
+                        if (m[j] != kEmpty) {
+                            u64 at = pos + __popc(ball[j] & lt_mask);
+                            u64 bk = s_tup[m[j]].key;
+                            if (at < a.capacity) {
+                                if (a.build_is_S) st_stream(a.out + at, t[j].key, bk);
+                                else st_stream(a.out + at, bk, t[j].key);
+                            }
+                        }
+                        pos += __popc(ball[j]);
+                    }
+                    rr ^= 1;
+                } else {
+                    // duplicate build keys: count every match, reserve, then re-walk and write
+                    u32 cnt[kJoinItems];
+                    u32 mine = 0;
+#pragma unroll
+                    for (int j = 0; j < kJoinItems; ++j) {
+                        cnt[j] = 0;
+                        if (ok[j]) {
+                            u32 h = slot_of_v1(t[j].val);
+                            u32 idx;
+                            while ((idx = s_slot[h]) != kEmpty) {
+                                if (s_tup[idx].val == t[j].val) cnt[j]++;
+                                h = (h + 1) & (kV1Slots - 1);
+                            }
+                        }
+                        mine += cnt[j];
+                    }
+                    if (MODE == kJoinCount) {
+                        my_count += mine;
+                        continue;
+                    }
+                    u32 incl = warp_incl_scan(mine);
+                    u32 wtotal = __shfl_sync(0xffffffffu, incl, 31);
+                    u32 wbase = 0;
+                    if (lane == 0 && wtotal) wbase = atomicAdd(&s_cnt[rr], wtotal);
+                    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                    __syncthreads();
+                    if (tid == 0) {
+                        u32 c = s_cnt[rr];
+                        u64 base;
+                        if (MODE == kJoinFused) base = c ? atomicAdd(a.out_cursor, (u64) c) : 0;
+                        else { base = run_base; run_base += c; }
+                        s_base[rr] = base;
+                        s_cnt[rr ^ 1] = 0;
+                    }
+                    __syncthreads();
+                    u64 at = s_base[rr] + wbase + (incl - mine);
+#pragma unroll
+                    for (int j = 0; j < kJoinItems; ++j) {
+                        if (cnt[j]) {
+                            u32 h = slot_of_v1(t[j].val);
+                            u32 idx;
+                            while ((idx = s_slot[h]) != kEmpty) {
+                                if (s_tup[idx].val == t[j].val) {
+                                    u64 bk = s_tup[idx].key;
+                                    if (at < a.capacity) {
+                                        if (a.build_is_S) st_stream(a.out + at, t[j].key, bk);
+                                        else st_stream(a.out + at, bk, t[j].key);
+                                    }
+                                    ++at;
+                                }
+                                h = (h + 1) & (kV1Slots - 1);
+                            }
+                        }
+                    }
+                    rr ^= 1;
+                }
+            }
+            __syncthreads();  // everyone is done with this table before it is overwritten
+        }
+        if (MODE == kJoinCount) {
+            u64 w = warp_sum64(my_count);
+            if (lane == 0) s_red[warp] = w;
+            __syncthreads();
+            if (warp == 0) {
+                u64 x = lane < (kJoinThreads / 32) ? s_red[lane] : 0;
+                x = warp_sum64(x);
+                if (lane == 0) a.item_cnt[item] = x;
+            }
+        }
+    }
+}
+
+
+}  // namespace rhj

@@ -4,7 +4,7 @@
 //  (1) histogram             HistogramJob::run, JobScheduler.cpp:149-155      k_hist
 //  (2) prefix sum            PartitionJob::run 163-169, Result.cpp:100-107    k_scan_digits, k_scan_parts
 //  (3) partition scatter     PartitionJob::run 170-174 + structs.cpp:183-194  k_scatter
-//  (4) per-bucket build/probe Result::join_buckets, Result.cpp:43-76           k_join
+//  (4) per-bucket build/probe Result::join_buckets, Result.cpp:43-76           k_join            (rhj_join.cuh)
 //  (5) emitter               add_result/addAll, Result.cpp:21-35,78-84,111-121 k_join<COUNT|WRITE|FUSED>, k_scan_items
 //  filters / gathers         Query.cpp:94-146, structs.cpp:217-226, Query.cpp:66-74   k_filter_*, k_gather_*
 //
@@ -13,23 +13,25 @@
 // results are 16-byte {rowidR,rowidS} pairs (Result.h:9-12) in one flat array.
 #pragma once
 #include "rhj_device.cuh"
+#include "rhj_join.cuh"
 
 namespace rhj {
 
 // ---- tuning constants -------------------------------------------------------------------------
-constexpr int kPartThreads = 512;               // threads per partition CTA
-constexpr int kPartItems = 8;                   // tuples per thread
+#ifndef RHJ_PART_THREADS
+#define RHJ_PART_THREADS 512
+#endif
+#ifndef RHJ_PART_ITEMS
+#define RHJ_PART_ITEMS 8
+#endif
+#ifndef RHJ_PART_MINBLOCKS
+#define RHJ_PART_MINBLOCKS 2
+#endif
+constexpr int kPartThreads = RHJ_PART_THREADS;  // threads per partition CTA
+constexpr int kPartItems = RHJ_PART_ITEMS;      // tuples per thread
 constexpr int kTile = kPartThreads * kPartItems;  // 4096 tuples = 64 KiB staged per CTA
 constexpr int kMaxBitsPerPass = 9;
 constexpr int kMaxDigits = 1 << kMaxBitsPerPass;  // 512 digits per pass
-
-constexpr int kJoinThreads = 512;
-constexpr int kJoinItems = 4;                        // probe tuples per thread per round
-constexpr int kRound = kJoinThreads * kJoinItems;    // 2048 probe tuples per round
-constexpr u32 kBuildCap = 4096;                      // build tuples per shared-memory table (64 KiB)
-constexpr u32 kSlots = 8192;                         // open-addressing slots (u32 index), load <= 0.5 (32 KiB)
-constexpr u32 kProbeChunk = 16384;                   // probe tuples per work item
-constexpr u32 kTargetBuildPerPart = 2048;            // radix bits are chosen for this average
 
 enum DigitKind { kDigitRaw = 0, kDigitHash = 1, kDigitRank = 2 };
 
@@ -229,8 +231,9 @@ __global__ void __launch_bounds__(1024) k_scan_parts(ScanPartsArgs a) {
 //   (consecutive threads -> consecutive 16-B slots, full 32-B sectors / 128-B lines inside a run)
 //   or, with BULK, by one TMA bulk store (cp.async.bulk shared->global) per run.
 // Algorithmic bytes: 16 read + 16 written per tuple.
-template <int KIND, bool SEG, bool BULK>
-__global__ void __launch_bounds__(kPartThreads, 2) k_scatter(PartArgs a) {
+enum ScatterWrite { kWriteStaged = 0, kWriteBulk = 1, kWriteDirect = 2 };
+template <int KIND, bool SEG, int WMODE>
+__global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(PartArgs a) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     Tup *s_tup = reinterpret_cast<Tup *>(dyn_smem);
     __shared__ u32 s_cnt[kMaxDigits];
@@ -265,11 +268,21 @@ __global__ void __launch_bounds__(kPartThreads, 2) k_scatter(PartArgs a) {
         }
     }
     __syncthreads();
-    // reserve the runs (global atomic issued first so its latency overlaps the block scan)
-    u32 c = tid < a.ndig ? s_cnt[tid] : 0;
-    u64 g = 0;
-    if (c) g = atomicAdd(r.cursor + (u64) seg * a.ndig + tid, (u64) c);
-    u32 inc = warp_incl_scan(c);
+    // reserve the runs (global atomics issued first so their latency overlaps the block scan);
+    // thread t owns the kDigitsPerThread consecutive digits starting at t * kDigitsPerThread
+    constexpr int kDigitsPerThread = (kMaxDigits + kPartThreads - 1) / kPartThreads;
+    u32 c[kDigitsPerThread];
+    u64 g[kDigitsPerThread];
+    u32 csum = 0;
+#pragma unroll
+    for (int k = 0; k < kDigitsPerThread; ++k) {
+        u32 d = tid * kDigitsPerThread + k;
+        c[k] = d < a.ndig ? s_cnt[d] : 0;
+        g[k] = 0;
+        if (c[k]) g[k] = atomicAdd(r.cursor + (u64) seg * a.ndig + d, (u64) c[k]);
+        csum += c[k];
+    }
+    u32 inc = warp_incl_scan(csum);
     if (lane == 31) s_w[warp] = inc;
     __syncthreads();
     if (warp == 0) {
@@ -278,18 +291,36 @@ __global__ void __launch_bounds__(kPartThreads, 2) k_scatter(PartArgs a) {
         s_w[lane] = wi - w;
     }
     __syncthreads();
-    if (tid < a.ndig) {
-        u32 ex = inc - c + s_w[warp];
-        s_off[tid] = ex;
-        s_delta[tid] = g - ex;
+    {
+        u32 ex = inc - csum + s_w[warp];
+#pragma unroll
+        for (int k = 0; k < kDigitsPerThread; ++k) {
+            u32 d = tid * kDigitsPerThread + k;
+            if (d < a.ndig) {
+                s_off[d] = ex;
+                s_delta[d] = g[k] - ex;
+            }
+            ex += c[k];
+        }
     }
     __syncthreads();
+    if (WMODE == kWriteDirect) {
+        // no staging: every tuple goes straight to its slot; L2 merges the 16-B pieces of a run
+#pragma unroll
+        for (int j = 0; j < kPartItems; ++j) {
+            u32 i = j * kPartThreads + tid;
+            if (i < ntile) {
+                u32 d = dr[j] >> 16;
+                st_stream(r.out + s_delta[d] + s_off[d] + (dr[j] & 0xffffu), v[j]);
+            }
+        }
+    } else {
 #pragma unroll
     for (int j = 0; j < kPartItems; ++j) {
         u32 i = j * kPartThreads + tid;
         if (i < ntile) s_tup[s_off[dr[j] >> 16] + (dr[j] & 0xffffu)] = v[j];
     }
-    if (BULK) {
+    if (WMODE == kWriteBulk) {
         fence_async_smem();
         __syncthreads();
         for (u32 d = tid; d < a.ndig; d += kPartThreads) {
@@ -310,13 +341,10 @@ __global__ void __launch_bounds__(kPartThreads, 2) k_scatter(PartArgs a) {
             }
         }
     }
+    }
 }
 
 // ---- (4)+(5): work planning ---------------------------------------------------------------------
-struct Item {
-    u32 part;
-    u32 chunk;
-};
 struct PlanArgs {
     const u64 *offB;  // [nparts+1] build-side partition offsets
     const u64 *offP;  // [nparts+1] probe-side partition offsets
@@ -363,6 +391,70 @@ __global__ void __launch_bounds__(1024) k_plan(PlanArgs a) {
     }
 }
 
+// (2b')+(plan), two-pass plans: one CTA per pass-1 partition.  The 2^b2 sub-partition counters of
+// a pass-1 partition only need a LOCAL prefix sum on top of that partition's pass-1 offset, so the
+// 2^bits_total-entry scan and the work-item planning run fully in parallel: offsets + cursors for
+// both relations, then this partition's work items appended with one global atomic per CTA
+// (item order is irrelevant).
+struct ScanPlanArgs {
+    const u64 *hist2[2];   // [nseg * ndig] sub-partition counts (build, probe)
+    const u64 *off1[2];    // [nseg + 1] pass-1 offsets
+    u64 *off2[2];          // [nseg * ndig + 1]
+    u64 *cursor2[2];       // [nseg * ndig]
+    u32 nseg, ndig;
+    Item *items;
+    u32 item_cap;
+    u32 *nitems;
+    u32 *err;
+};
+__global__ void __launch_bounds__(kMaxDigits) k_scan_parts_plan(ScanPlanArgs a) {
+    __shared__ u64 s_w[32];
+    __shared__ u32 s_base;
+    const u32 seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 p = seg * a.ndig + tid;
+    u64 cnt[2];
+#pragma unroll
+    for (int ri = 0; ri < 2; ++ri) {
+        u64 c = tid < a.ndig ? a.hist2[ri][p] : 0;
+        cnt[ri] = c;
+        u64 inc = warp_incl_scan64(c);
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            u64 w = lane < (kMaxDigits / 32) ? s_w[lane] : 0;
+            u64 wi = warp_incl_scan64(w);
+            s_w[lane] = wi - w;
+        }
+        __syncthreads();
+        u64 off = a.off1[ri][seg] + inc - c + s_w[warp];
+        if (tid < a.ndig) {
+            a.off2[ri][p] = off;
+            a.cursor2[ri][p] = off;
+            if (seg == a.nseg - 1 && tid == a.ndig - 1) a.off2[ri][p + 1] = off + c;
+        }
+        __syncthreads();
+    }
+    // work items of this pass-1 partition
+    u32 k = (cnt[0] && cnt[1]) ? (u32) ((cnt[1] + kProbeChunk - 1) / kProbeChunk) : 0;
+    u32 inc = warp_incl_scan(k);
+    u32 *s_w32 = reinterpret_cast<u32 *>(s_w);
+    if (lane == 31) s_w32[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        u32 w = lane < (kMaxDigits / 32) ? s_w32[lane] : 0;
+        u32 wi = warp_incl_scan(w);
+        s_w32[lane] = wi - w;
+        u32 total = __shfl_sync(0xffffffffu, wi, 31);
+        if (lane == 0) s_base = total ? atomicAdd(a.nitems, total) : 0;
+    }
+    __syncthreads();
+    u32 at = s_base + inc - k + s_w32[warp];
+    for (u32 ch = 0; ch < k; ++ch) {
+        if (at + ch < a.item_cap) a.items[at + ch] = Item{p, ch};
+        else *a.err = 1;
+    }
+}
+
 __global__ void k_set_single_part(u64 *offB, u64 nB, u64 *offP, u64 nP) {
     offB[0] = 0; offB[1] = nB;
     offP[0] = 0; offP[1] = nP;
@@ -391,230 +483,6 @@ __global__ void __launch_bounds__(1024) k_scan_items(const u64 *cnt, const u32 *
     for (u32 i = i0; i < i1; ++i) {
         off[i] = run;
         run += cnt[i];
-    }
-}
-
-// ---- (4)+(5): per-partition build / probe / emit ----------------------------------------------
-enum JoinMode { kJoinCount = 0, kJoinWrite = 1, kJoinFused = 2 };
-
-struct JoinArgs {
-    const Tup *build;    // partitioned build relation (the smaller input)
-    const Tup *probe;    // partitioned probe relation
-    const u64 *offB;
-    const u64 *offP;
-    const Item *items;
-    const u32 *nitems;
-    u32 *work_counter;   // dynamic item scheduler
-    u64 *item_cnt;       // COUNT: out; per-item match count
-    const u64 *item_off; // WRITE: per-item output offset
-    u64 *out_cursor;     // FUSED: global reservation cursor (ends as the total match count)
-    Pair *out;
-    u64 capacity;
-    int build_is_S;      // output is always (rowidR, rowidS): Result.cpp:66-69
-};
-
-__device__ __forceinline__ u32 slot_of(u64 v) { return hash32(v) & (kSlots - 1); }
-
-// Persistent CTAs pull work items (partition p, probe chunk c).  For each build chunk of
-// <= 4096 tuples of partition p:
-//   - one elected thread TMA-bulk-loads the chunk's tuples verbatim into shared memory
-//     (cp.async.bulk + mbarrier) while all threads clear the slot table;
-//   - build: every tuple claims a slot of the open-addressing table (u32 index into the staged
-//     tuples, linear probing, atomicCAS on shared memory; load factor <= 0.5).  A claim that
-//     walks past an equal value flags the chunk as "has duplicate keys";
-//   - probe: rounds of 2048 probe tuples (4 per thread, coalesced 16-B loads).  Unique-key
-//     chunks stop at the first hit; duplicate-key chunks count, then re-walk to write.
-//   - emit: matches of a round are ranked with ballots + one shared atomic per warp; one thread
-//     reserves the round's output range (FUSED: one global atomic per round; WRITE: running
-//     offset from the count pass) and lanes write 16-B pairs at consecutive positions.
-// Algorithmic bytes: 16 per input tuple read + 16 per result pair written.
-template <int MODE>
-__global__ void __launch_bounds__(kJoinThreads, 2) k_join(JoinArgs a) {
-    extern __shared__ __align__(128) unsigned char dyn_smem[];
-    Tup *s_tup = reinterpret_cast<Tup *>(dyn_smem);
-    u32 *s_slot = reinterpret_cast<u32 *>(dyn_smem + (size_t) kBuildCap * sizeof(Tup));
-    __shared__ __align__(8) u64 s_bar;
-    __shared__ u32 s_item;
-    __shared__ u32 s_cnt[2];
-    __shared__ u64 s_base[2];
-    __shared__ u64 s_red[32];
-
-    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 lt_mask = lanemask_lt();
-    if (tid == 0) {
-        mbar_init(&s_bar, 1);
-        s_cnt[0] = 0;
-        s_cnt[1] = 0;
-    }
-    __syncthreads();
-    const u32 nitems = *a.nitems;
-    u32 phase = 0, rr = 0;
-
-    while (true) {
-        if (tid == 0) s_item = atomicAdd(a.work_counter, 1u);
-        __syncthreads();
-        const u32 item = s_item;
-        if (item >= nitems) break;
-        const Item it = a.items[item];
-        const u64 b0 = a.offB[it.part], b1 = a.offB[it.part + 1];
-        const u64 p0 = a.offP[it.part] + (u64) it.chunk * kProbeChunk;
-        const u64 p1 = min(a.offP[it.part + 1], p0 + (u64) kProbeChunk);
-        u64 my_count = 0;                                   // COUNT
-        u64 run_base = (MODE == kJoinWrite && tid == 0) ? a.item_off[item] : 0;  // WRITE (thread 0 only)
-
-        for (u64 bb = b0; bb < b1; bb += kBuildCap) {
-            const u32 nb = (u32) min((u64) kBuildCap, b1 - bb);
-            if (tid == 0) {
-                mbar_expect_tx(&s_bar, nb * (u32) sizeof(Tup));
-                bulk_g2s(s_tup, a.build + bb, nb * (u32) sizeof(Tup), &s_bar);
-            }
-            for (u32 i = tid; i < kSlots; i += kJoinThreads) s_slot[i] = kEmpty;
-            mbar_wait(&s_bar, phase);
-            phase ^= 1;
-            __syncthreads();
-            // build
-            int dup = 0;
-            for (u32 i = tid; i < nb; i += kJoinThreads) {
-                const u64 v = s_tup[i].val;
-                u32 h = slot_of(v);
-                while (true) {
-                    u32 old = atomicCAS(&s_slot[h], kEmpty, i);
-                    if (old == kEmpty) break;
-                    if (s_tup[old].val == v) dup = 1;
-                    h = (h + 1) & (kSlots - 1);
-                }
-            }
-            dup = __syncthreads_or(dup);
-
-            // probe
-            for (u64 q0 = p0; q0 < p1; q0 += kRound) {
-                Tup t[kJoinItems];
-                bool ok[kJoinItems];
-#pragma unroll
-                for (int j = 0; j < kJoinItems; ++j) {
-                    u64 idx = q0 + (u64) j * kJoinThreads + tid;
-                    ok[j] = idx < p1;
-                    if (ok[j]) t[j] = ld_stream(a.probe + idx);
-                }
-                if (!dup) {
-                    // unique build keys: at most one match per probe tuple
-                    u32 m[kJoinItems], ball[kJoinItems];
-                    u32 wtotal = 0;
-#pragma unroll
-                    for (int j = 0; j < kJoinItems; ++j) {
-                        m[j] = kEmpty;
-                        if (ok[j]) {
-                            u32 h = slot_of(t[j].val);
-                            u32 idx;
-                            while ((idx = s_slot[h]) != kEmpty) {
-                                if (s_tup[idx].val == t[j].val) { m[j] = idx; break; }
-                                h = (h + 1) & (kSlots - 1);
-                            }
-                        }
-                        ball[j] = __ballot_sync(0xffffffffu, m[j] != kEmpty);
-                        wtotal += __popc(ball[j]);
-                    }
-                    if (MODE == kJoinCount) {
-                        if (lane == 0) my_count += wtotal;
-                        continue;
-                    }
-                    u32 wbase = 0;
-                    if (lane == 0 && wtotal) wbase = atomicAdd(&s_cnt[rr], wtotal);
-                    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                    __syncthreads();
-                    if (tid == 0) {
-                        u32 c = s_cnt[rr];
-                        u64 base;
-                        if (MODE == kJoinFused) base = c ? atomicAdd(a.out_cursor, (u64) c) : 0;
-                        else { base = run_base; run_base += c; }
-                        s_base[rr] = base;
-                        s_cnt[rr ^ 1] = 0;
-                    }
-                    __syncthreads();
-                    u64 pos = s_base[rr] + wbase;
-#pragma unroll
-                    for (int j = 0; j < kJoinItems; ++j) {
-                        if (m[j] != kEmpty) {
-                            u64 at = pos + __popc(ball[j] & lt_mask);
-                            u64 bk = s_tup[m[j]].key;
-                            if (at < a.capacity) {
-                                if (a.build_is_S) st_stream(a.out + at, t[j].key, bk);
-                                else st_stream(a.out + at, bk, t[j].key);
-                            }
-                        }
-                        pos += __popc(ball[j]);
-                    }
-                    rr ^= 1;
-                } else {
-                    // duplicate build keys: count every match, reserve, then re-walk and write
-                    u32 cnt[kJoinItems];
-                    u32 mine = 0;
-#pragma unroll
-                    for (int j = 0; j < kJoinItems; ++j) {
-                        cnt[j] = 0;
-                        if (ok[j]) {
-                            u32 h = slot_of(t[j].val);
-                            u32 idx;
-                            while ((idx = s_slot[h]) != kEmpty) {
-                                if (s_tup[idx].val == t[j].val) cnt[j]++;
-                                h = (h + 1) & (kSlots - 1);
-                            }
-                        }
-                        mine += cnt[j];
-                    }
-                    if (MODE == kJoinCount) {
-                        my_count += mine;
-                        continue;
-                    }
-                    u32 incl = warp_incl_scan(mine);
-                    u32 wtotal = __shfl_sync(0xffffffffu, incl, 31);
-                    u32 wbase = 0;
-                    if (lane == 0 && wtotal) wbase = atomicAdd(&s_cnt[rr], wtotal);
-                    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-                    __syncthreads();
-                    if (tid == 0) {
-                        u32 c = s_cnt[rr];
-                        u64 base;
-                        if (MODE == kJoinFused) base = c ? atomicAdd(a.out_cursor, (u64) c) : 0;
-                        else { base = run_base; run_base += c; }
-                        s_base[rr] = base;
-                        s_cnt[rr ^ 1] = 0;
-                    }
-                    __syncthreads();
-                    u64 at = s_base[rr] + wbase + (incl - mine);
-#pragma unroll
-                    for (int j = 0; j < kJoinItems; ++j) {
-                        if (cnt[j]) {
-                            u32 h = slot_of(t[j].val);
-                            u32 idx;
-                            while ((idx = s_slot[h]) != kEmpty) {
-                                if (s_tup[idx].val == t[j].val) {
-                                    u64 bk = s_tup[idx].key;
-                                    if (at < a.capacity) {
-                                        if (a.build_is_S) st_stream(a.out + at, t[j].key, bk);
-                                        else st_stream(a.out + at, bk, t[j].key);
-                                    }
-                                    ++at;
-                                }
-                                h = (h + 1) & (kSlots - 1);
-                            }
-                        }
-                    }
-                    rr ^= 1;
-                }
-            }
-            __syncthreads();  // everyone is done with this table before it is overwritten
-        }
-        if (MODE == kJoinCount) {
-            u64 w = warp_sum64(my_count);
-            if (lane == 0) s_red[warp] = w;
-            __syncthreads();
-            if (warp == 0) {
-                u64 x = lane < (kJoinThreads / 32) ? s_red[lane] : 0;
-                x = warp_sum64(x);
-                if (lane == 0) a.item_cnt[item] = x;
-            }
-        }
     }
 }
 
