@@ -206,21 +206,14 @@ def run_b200(args, rank, world, local_rank):
         recvS = torch.empty((slack, 2), dtype=torch.int64, device=dev)
         out = torch.empty((slack, 2), dtype=torch.int64, device=dev)
         eng.reserve(slack, slack)
-        cnt_send = torch.empty(2 * world, dtype=torch.int64, device=dev)
-        cnt_recv = torch.empty(2 * world, dtype=torch.int64, device=dev)
+        from radixhashjoin_b200.distributed import ShardedJoin
+        sj = ShardedJoin(world, rank, lambda T: eng.shuffle_partition(T, world),
+                         lambda a, b: eng.join_device(a, b, out=out, emit=emit))
 
         def step():
             # (K8) group both shards by destination rank (our kernels), exchange over NVLink (NCCL), join locally
-            gR, cR = eng.shuffle_partition(R, world)
-            gS, cS = eng.shuffle_partition(S, world)
-            cnt_send.copy_(torch.tensor([v for pair in zip(cR, cS) for v in pair], dtype=torch.int64))
-            dist.all_to_all_single(cnt_recv, cnt_send)
-            cr = cnt_recv.cpu().tolist()
-            rR, rS = cr[0::2], cr[1::2]
-            assert sum(rR) <= slack and sum(rS) <= slack
-            dist.all_to_all_single(recvR[:sum(rR)], gR, output_split_sizes=rR, input_split_sizes=cR)
-            dist.all_to_all_single(recvS[:sum(rS)], gS, output_split_sizes=rS, input_split_sizes=cS)
-            return eng.join_device(recvR[:sum(rR)], recvS[:sum(rS)], out=out, emit=emit)
+            pairs, count, _ = sj.step(R, S, recvR, recvS)
+            return pairs, count
 
     def barrier():
         if world > 1:

@@ -14,7 +14,8 @@
  *     gives the text of the last failure on that context.  There is NO CPU
  *     fallback: without a usable sm_100 device rhj_create fails.
  *   - `*_device` entry points take DEVICE pointers and a cudaStream_t passed as
- *     void* (NULL = the context's own stream).  They enqueue on that stream and,
+ *     void* (NULL = CUDA's default stream, as in the runtime API).  They enqueue
+ *     on that stream -- after whatever the caller enqueued there before -- and,
  *     unless stated otherwise, synchronise it before returning so that host
  *     out-parameters are valid.
  *   - `*_host` entry points take HOST pointers, do their own H2D/D2H.

@@ -14,7 +14,6 @@
 
 #include "../../include/rhj.h"
 #include "rhj_kernels.cuh"
-#include "rhj_join_v1.cuh"
 
 using namespace rhj;
 
@@ -50,8 +49,7 @@ struct rhj_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     bool hist_agg = false;
-    int join_v = 2;           // RHJ_JOIN_V: 2 pipelined kernel, 1 first kernel, 11 first kernel + early probe loads
-    int scatter_mode = 0;     // 0 staged per-thread stores, 1 TMA bulk stores, 2 direct (RHJ_SCATTER_MODE)
+    int scatter_mode = 0;     // 0 staged per-thread stores, 1 TMA bulk stores (RHJ_SCATTER_MODE)
 
     DevBuf bufA, bufB;        // pass-1 / pass-2 partitioned tuples (build side first, then probe side)
     DevBuf zero;              // hist1 | hist2 | scalars   (memset to 0 per call)
@@ -182,7 +180,7 @@ int launch_hist(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, bool
 
 template <int K, bool S, int W>
 cudaError_t launch_scatter_t(cudaStream_t st, const PartArgs &a, u32 grid) {
-    const size_t smem = W == kWriteDirect ? 0 : kScatterSmem;
+    const size_t smem = kScatterSmem;
     cudaError_t e = set_smem(k_scatter<K, S, W>, smem);
     if (e != cudaSuccess) return e;
     k_scatter<K, S, W><<<grid, kPartThreads, smem, st>>>(a);
@@ -194,10 +192,7 @@ int launch_scatter(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, b
     if (!grid) return RHJ_OK;
     const int w = ctx->scatter_mode;
     cudaError_t e;
-#define SC(K, S)                                                                   \
-    (w == 1 ? launch_scatter_t<K, S, kWriteBulk>(st, a, grid)                      \
-            : w == 2 ? launch_scatter_t<K, S, kWriteDirect>(st, a, grid)           \
-                     : launch_scatter_t<K, S, kWriteStaged>(st, a, grid))
+#define SC(K, S) (w == 1 ? launch_scatter_t<K, S, kWriteBulk>(st, a, grid) : launch_scatter_t<K, S, kWriteStaged>(st, a, grid))
     if (kind == kDigitRaw) e = seg ? SC(kDigitRaw, true) : SC(kDigitRaw, false);
     else if (kind == kDigitHash) e = seg ? SC(kDigitHash, true) : SC(kDigitHash, false);
     else e = seg ? SC(kDigitRank, true) : SC(kDigitRank, false);
@@ -210,16 +205,8 @@ int launch_scatter(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, b
 template <int MODE>
 int launch_join(rhj_ctx *ctx, cudaStream_t st, const JoinArgs &a, u32 item_cap) {
     u32 grid = std::min<u32>(std::max<u32>(item_cap, 1), (u32) ctx->num_sms * 2);
-    if (ctx->join_v == 1) {
-        CK(set_smem(k_join_v1<MODE, false>, kV1JoinSmemBytes));
-        k_join_v1<MODE, false><<<grid, kJoinThreads, kV1JoinSmemBytes, st>>>(a);
-    } else if (ctx->join_v == 11) {
-        CK(set_smem(k_join_v1<MODE, true>, kV1JoinSmemBytes));
-        k_join_v1<MODE, true><<<grid, kJoinThreads, kV1JoinSmemBytes, st>>>(a);
-    } else {
-        CK(set_smem(k_join<MODE>, kJoinSmem));
-        k_join<MODE><<<grid, kJoinThreads, kJoinSmem, st>>>(a);
-    }
+    CK(set_smem(k_join<MODE>, kJoinSmem));
+    k_join<MODE><<<grid, kJoinThreads, kJoinSmem, st>>>(a);
     CK(cudaGetLastError());
     ctx->info.kernel_launches++;
     return RHJ_OK;
@@ -470,7 +457,9 @@ int write_phase(rhj_ctx *ctx, cudaStream_t st, Pair *d_out, u64 capacity) {
     return rc;
 }
 
-cudaStream_t pick(rhj_ctx *ctx, void *stream) { return stream ? (cudaStream_t) stream : ctx->stream; }
+// `stream` is the caller's cudaStream_t; NULL is CUDA's (legacy) default stream, exactly as in the
+// CUDA runtime API -- the caller's preceding work on that stream is what our kernels must follow.
+cudaStream_t pick(rhj_ctx *, void *stream) { return (cudaStream_t) stream; }
 
 }  // namespace
 
@@ -496,7 +485,6 @@ int rhj_create(int device, rhj_ctx **out) {
     const char *e;
     if ((e = getenv("RHJ_HIST_AGG"))) ctx->hist_agg = atoi(e) != 0;
     if ((e = getenv("RHJ_SCATTER_MODE"))) ctx->scatter_mode = atoi(e);
-    if ((e = getenv("RHJ_JOIN_V"))) ctx->join_v = atoi(e);
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaHostAlloc((void **) &ctx->h_scalars, kScCount * sizeof(u64), cudaHostAllocDefault) != cudaSuccess) {

@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(1024) k_scan_parts(ScanPartsArgs a) {
 //   (consecutive threads -> consecutive 16-B slots, full 32-B sectors / 128-B lines inside a run)
 //   or, with BULK, by one TMA bulk store (cp.async.bulk shared->global) per run.
 // Algorithmic bytes: 16 read + 16 written per tuple.
-enum ScatterWrite { kWriteStaged = 0, kWriteBulk = 1, kWriteDirect = 2 };
+enum ScatterWrite { kWriteStaged = 0, kWriteBulk = 1 };
 template <int KIND, bool SEG, int WMODE>
 __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(PartArgs a) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
@@ -304,17 +304,7 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
         }
     }
     __syncthreads();
-    if (WMODE == kWriteDirect) {
-        // no staging: every tuple goes straight to its slot; L2 merges the 16-B pieces of a run
-#pragma unroll
-        for (int j = 0; j < kPartItems; ++j) {
-            u32 i = j * kPartThreads + tid;
-            if (i < ntile) {
-                u32 d = dr[j] >> 16;
-                st_stream(r.out + s_delta[d] + s_off[d] + (dr[j] & 0xffffu), v[j]);
-            }
-        }
-    } else {
+    {
 #pragma unroll
     for (int j = 0; j < kPartItems; ++j) {
         u32 i = j * kPartThreads + tid;

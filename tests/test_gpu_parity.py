@@ -230,6 +230,9 @@ def test_shuffle_partition_keeps_equal_values_together(engine):
     got = tuples_np(out)
     assert sum(counts) == len(T)
     assert np.array_equal(np.sort(got, order=["key", "payload"]), np.sort(T, order=["key", "payload"]))
+    from radixhashjoin_b200.distributed import rank_of_values
+    # the numpy restatement used by the CPU (gloo) tests is the device's rank function
+    assert counts == np.bincount(rank_of_values(T["payload"], 8), minlength=8).tolist()
     owner = {}
     at = 0
     for r, c in enumerate(counts):
