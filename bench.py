@@ -136,6 +136,48 @@ def cpu_reference_run(log2n, steps, warmup):
     return n_in / sec, sec, info
 
 
+def small_work_wall(with_reference=False):
+    """BASELINE.json config 1 / metric part 2: wall time of `cat small.init small.work | ./join` for the
+    reference PROGRAM linked with our drop-in Result.cpp + intermediate.cpp + librhj.so
+    (radixhashjoin_b200/host/_build/join_b200_full, built in the dev container), output diffed
+    against small.result.  With --small-work-ref the unmodified reference program (oracle/_ref/join_ref)
+    is timed the same way (takes minutes)."""
+    import subprocess
+    import tarfile
+    import tempfile
+    host_bin = os.path.join(ROOT, "radixhashjoin_b200", "host", "_build", "join_b200_full")
+    if not os.path.exists(host_bin):
+        return {"unavailable": "radixhashjoin_b200/host/_build/join_b200_full not built (needs the reference sources)"}
+    golden = os.path.join(ROOT, "tests", "golden")
+    with tempfile.TemporaryDirectory() as d:
+        os.mkdir(os.path.join(d, "small"))
+        with tarfile.open(os.path.join(golden, "small_relations.tar.xz")) as tf:
+            tf.extractall(os.path.join(d, "small"))
+        data = open(os.path.join(golden, "small.init"), "rb").read() + open(os.path.join(golden, "small.work"), "rb").read()
+        expect = open(os.path.join(golden, "small.result"), "rb").read()
+
+        def run(binary, reps):
+            walls, same = [], True
+            for _ in range(reps):
+                t0 = time.perf_counter()
+                out = subprocess.run([binary], input=data, cwd=d, capture_output=True, timeout=1800)
+                walls.append(time.perf_counter() - t0)
+                same = same and out.returncode == 0 and out.stdout == expect
+            return walls, same
+
+        walls, same = run(host_bin, 3)
+        res = {"program": "reference join.cpp/Query.cpp/... + host/Result.cpp + host/intermediate.cpp + librhj.so",
+               "wall_s": min(walls), "wall_s_all": [round(w, 3) for w in walls], "output_identical_to_small_result": same,
+               "query_threads": 8}
+        ref_bin = os.path.join(ROOT, "oracle", "_ref", "join_ref")
+        if with_reference and os.path.exists(ref_bin):
+            rw, rsame = run(ref_bin, 1)
+            res["reference_wall_s"] = rw[0]
+            res["reference_output_identical"] = rsame
+            res["reference_build"] = "unmodified reference, g++ -Ofast -march=x86-64-v3 -funroll-loops -pthread"
+        return res
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -337,6 +379,8 @@ def run_b200(args, rank, world, local_rank):
                 "step_roofline": {"algorithmic_bytes": b_alg_step, "formula": "96*n + 16*m (SURVEY 8d)",
                                   "achieved_GBps": step_gbs, "frac_of_measured_hbm": step_gbs / peak},
                 "e2e": e2e, "cpu_baseline": cpu}
+        if world == 1 and not args.no_small_work:
+            line["small_work"] = small_work_wall(args.small_work_ref)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -355,6 +399,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-log2n", type=int, default=26, help="cpu_baseline sample size (2^k x 2^k)")
     ap.add_argument("--ref-log2n", type=int, default=24, help="--impl reference: sample per step")
+    ap.add_argument("--no-small-work", action="store_true")
+    ap.add_argument("--small-work-ref", action="store_true", help="also time the unmodified reference program (minutes)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

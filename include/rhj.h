@@ -147,6 +147,26 @@ int rhj_gather_sum_u64_device(rhj_ctx *ctx, const uint64_t *d_col, const uint64_
 int rhj_pairs_digest_device(rhj_ctx *ctx, const rhj_pair *d_pairs, uint64_t n, uint64_t *sum, uint64_t *xr,
                             void *stream);
 
+/* update_intermediate, case 2 (intermediate.cpp:52-66,108-125,162-170): one binding of the join is
+ * already in the intermediate (its row-id column is match_col[n_rows]); every result pair whose row
+ * id on that side equals match_col[e] yields a new row = old row e + the pair's other row id.  The
+ * reference scans all rows once per pair (99 % of the small.work wall time); here it is one join
+ * (index-keyed relations) + gathers.  match_on_S = 1 when the already-joined binding is the join's
+ * S side.  cols[n_cols] are the live columns of the old intermediate (n_rows each, HOST memory).
+ * out_cols[0..n_cols-1] = carried columns, out_cols[n_cols] = the new binding's column, each
+ * *out_rows long, in context-owned pinned HOST memory valid until the next call on the context.
+ * Row order differs from the reference; the multiset of rows is identical. */
+int rhj_intermediate_expand_host(rhj_ctx *ctx, const uint64_t *match_col, uint64_t n_rows, const rhj_pair *pairs,
+                                 uint64_t n_pairs, int match_on_S, const uint64_t *const *cols, uint32_t n_cols,
+                                 uint64_t **out_cols, uint64_t *out_rows);
+
+/* update_intermediate, case 3 (intermediate.cpp:72-87,130-138,171-180): both bindings are already in
+ * the intermediate; row e survives once per result pair equal to (col1[e], col2[e]).
+ * out_cols[0..n_cols-1] = the surviving rows of every carried column. */
+int rhj_intermediate_filter_host(rhj_ctx *ctx, const uint64_t *col1, const uint64_t *col2, uint64_t n_rows,
+                                 const rhj_pair *pairs, uint64_t n_pairs, const uint64_t *const *cols, uint32_t n_cols,
+                                 uint64_t **out_cols, uint64_t *out_rows);
+
 /* ---- multi-GPU (no reference equivalent) --------------------------------------- */
 
 /* Groups d_in[n] by destination rank = top log2(world) bits of the join hash (world a power of

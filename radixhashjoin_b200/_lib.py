@@ -41,6 +41,10 @@ SIGNATURES = {
     "rhj_gather_tuples_device": (ctypes.c_int, [c_vp, c_vp, c_vp, c_u64, c_vp, c_vp]),
     "rhj_gather_sum_u64_device": (ctypes.c_int, [c_vp, c_vp, c_vp, c_u64, c_u64p, c_vp]),
     "rhj_pairs_digest_device": (ctypes.c_int, [c_vp, c_vp, c_u64, c_u64p, c_u64p, c_vp]),
+    "rhj_intermediate_expand_host": (ctypes.c_int, [c_vp, c_vp, c_u64, c_vp, c_u64, ctypes.c_int, c_vp, ctypes.c_uint32,
+                                                    c_vp, c_u64p]),
+    "rhj_intermediate_filter_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_u64, c_vp, c_u64, c_vp, ctypes.c_uint32, c_vp,
+                                                    c_u64p]),
     "rhj_shuffle_partition_device": (ctypes.c_int, [c_vp, c_vp, c_u64, ctypes.c_int, c_vp, c_u64p, c_vp]),
     "rhj_last_plan": (ctypes.c_int, [c_vp, ctypes.POINTER(PlanInfo)]),
     "rhj_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),

@@ -232,6 +232,42 @@ class RadixHashJoin:
                                                      ctypes.byref(s), self._stream(stream)))
         return int(s.value)
 
+    def intermediate_expand_host(self, match_col, pairs, match_on_S, cols):
+        """update_intermediate case 2 (intermediate.cpp:108-125,162-170) as join + gather on the GPU.
+        match_col / cols: numpy u64 host columns of the old intermediate; pairs: PAIR_DTYPE join result.
+        Returns (carried columns, new binding's column) as numpy copies."""
+        match_col = np.ascontiguousarray(match_col, dtype=np.uint64)
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
+        cols = [np.ascontiguousarray(c, dtype=np.uint64) for c in cols]
+        ptrs = (ctypes.c_void_p * max(len(cols), 1))(*[c.ctypes.data for c in cols])
+        outs = (ctypes.c_void_p * (len(cols) + 1))()
+        rows = ctypes.c_uint64()
+        self._ck(self._lib.rhj_intermediate_expand_host(self._ctx, match_col.ctypes.data, len(match_col),
+                                                        pairs.ctypes.data, len(pairs), 1 if match_on_S else 0, ptrs,
+                                                        len(cols), outs, ctypes.byref(rows)))
+        m = int(rows.value)
+        take = lambda p: np.frombuffer((ctypes.c_uint64 * m).from_address(p), dtype=np.uint64).copy() if m else \
+            np.empty(0, dtype=np.uint64)
+        return [take(outs[i]) for i in range(len(cols))], take(outs[len(cols)])
+
+    def intermediate_filter_host(self, col1, col2, pairs, cols):
+        """update_intermediate case 3 (intermediate.cpp:130-138,171-180): rows whose (col1, col2) row-id
+        pair is in the join result.  Returns the surviving rows of every carried column."""
+        col1 = np.ascontiguousarray(col1, dtype=np.uint64)
+        col2 = np.ascontiguousarray(col2, dtype=np.uint64)
+        pairs = np.ascontiguousarray(pairs, dtype=PAIR_DTYPE)
+        cols = [np.ascontiguousarray(c, dtype=np.uint64) for c in cols]
+        ptrs = (ctypes.c_void_p * max(len(cols), 1))(*[c.ctypes.data for c in cols])
+        outs = (ctypes.c_void_p * max(len(cols), 1))()
+        rows = ctypes.c_uint64()
+        self._ck(self._lib.rhj_intermediate_filter_host(self._ctx, col1.ctypes.data, col2.ctypes.data, len(col1),
+                                                        pairs.ctypes.data, len(pairs), ptrs, len(cols), outs,
+                                                        ctypes.byref(rows)))
+        m = int(rows.value)
+        take = lambda p: np.frombuffer((ctypes.c_uint64 * m).from_address(p), dtype=np.uint64).copy() if m else \
+            np.empty(0, dtype=np.uint64)
+        return [take(outs[i]) for i in range(len(cols))]
+
     def pairs_digest(self, pairs, stream=None):
         """(count, sum, xor) of mix64(keyR*0x100000001b3 + keyS): order-independent multiset digest."""
         s, x = ctypes.c_uint64(), ctypes.c_uint64()

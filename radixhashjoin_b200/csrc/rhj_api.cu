@@ -6,124 +6,10 @@
 // launches on one CUDA stream.  No host synchronisation happens between the launches of one
 // join; sizes that depend on the data (partition sizes, work items, match counts) stay on the
 // device.  There is no CPU fallback anywhere in this file.
-#include <algorithm>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-
-#include "../../include/rhj.h"
+#include "rhj_ctx.cuh"
 #include "rhj_kernels.cuh"
 
-using namespace rhj;
-
-static_assert(sizeof(rhj_tuple) == sizeof(Tup), "tuple layout");
-static_assert(sizeof(rhj_pair) == sizeof(Pair), "pair layout");
-
 namespace {
-
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-};
-
-// indices into the zeroed scalar block (u64 units)
-enum Scalar {
-    kScWork0 = 0,   // work counter of the first join kernel
-    kScWork1 = 1,   // work counter of the second join kernel (write pass)
-    kScCursor = 2,  // FUSED output cursor / final count
-    kScNItems = 3,
-    kScTotal = 4,   // COUNT_THEN_WRITE total
-    kScErr = 5,
-    kScDigSum = 6,
-    kScDigXor = 7,
-    kScFilt = 8,
-    kScCount = 16
-};
-
-}  // namespace
-
-struct rhj_ctx {
-    int device = 0;
-    int num_sms = 148;
-    cudaStream_t stream = nullptr;
-    std::string err;
-    bool hist_agg = false;
-    int scatter_mode = 0;     // 0 staged per-thread stores, 1 TMA bulk stores (RHJ_SCATTER_MODE)
-
-    DevBuf bufA, bufB;        // pass-1 / pass-2 partitioned tuples (build side first, then probe side)
-    DevBuf zero;              // hist1 | hist2 | scalars   (memset to 0 per call)
-    DevBuf meta;              // offsets, cursors, tile tables
-    DevBuf items, item_cnt, item_off;
-    DevBuf filt_cnt, filt_off, filt_tmp;
-    DevBuf inR, inS, outP;    // device staging of the host entry point
-    void *h_out = nullptr;    // pinned host result of rhj_join_host
-    size_t h_out_cap = 0;
-    u64 *h_scalars = nullptr; // pinned, kScCount u64
-
-    // state left by the partition + plan phase for the emit phase
-    struct {
-        bool valid = false;
-        bool counted = false;
-        const Tup *build = nullptr, *probe = nullptr;
-        const u64 *offB = nullptr, *offP = nullptr;
-        u32 nparts = 0;
-        u32 item_cap = 0;
-        int build_is_S = 0;
-        u64 count = 0;
-    } cur;
-    rhj_plan_info info{};
-
-    // optional per-phase timing (rhj_set_profiling)
-    bool profiling = false;
-    static constexpr int kMaxMarks = 24;
-    cudaEvent_t ev[kMaxMarks] = {};
-    int mark_phase[kMaxMarks] = {};
-    int nmarks = 0;
-};
-
-namespace {
-
-int fail(rhj_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess) {
-    if (c) {
-        c->err = what;
-        if (e != cudaSuccess) {
-            c->err += ": ";
-            c->err += cudaGetErrorString(e);
-        }
-    }
-    return code;
-}
-
-#define CK(call)                                                           \
-    do {                                                                   \
-        cudaError_t e_ = (call);                                           \
-        if (e_ != cudaSuccess) return fail(ctx, RHJ_ERR_CUDA, #call, e_);  \
-    } while (0)
-
-int ensure(rhj_ctx *ctx, DevBuf &b, size_t bytes) {
-    if (bytes <= b.cap) return RHJ_OK;
-    CK(cudaSetDevice(ctx->device));
-    if (b.p) CK(cudaFree(b.p));
-    b.p = nullptr;
-    b.cap = 0;
-    size_t want = (bytes + 255) & ~(size_t) 255;
-    cudaError_t e = cudaMalloc(&b.p, want);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return fail(ctx, RHJ_ERR_NOMEM, "cudaMalloc workspace", e);
-    }
-    b.cap = want;
-    return RHJ_OK;
-}
-
-// Records "phase `phase` starts here" on the stream (profiling only); phase -1 closes the list.
-void mark(rhj_ctx *ctx, cudaStream_t st, int phase) {
-    if (!ctx->profiling || ctx->nmarks >= rhj_ctx::kMaxMarks) return;
-    if (!ctx->ev[ctx->nmarks]) cudaEventCreate(&ctx->ev[ctx->nmarks]);
-    cudaEventRecord(ctx->ev[ctx->nmarks], st);
-    ctx->mark_phase[ctx->nmarks++] = phase;
-}
 
 struct Plan {
     u64 nB, nP;
@@ -457,10 +343,6 @@ int write_phase(rhj_ctx *ctx, cudaStream_t st, Pair *d_out, u64 capacity) {
     return rc;
 }
 
-// `stream` is the caller's cudaStream_t; NULL is CUDA's (legacy) default stream, exactly as in the
-// CUDA runtime API -- the caller's preceding work on that stream is what our kernels must follow.
-cudaStream_t pick(rhj_ctx *, void *stream) { return (cudaStream_t) stream; }
-
 }  // namespace
 
 // =================================================================================================
@@ -499,11 +381,9 @@ int rhj_destroy(rhj_ctx *ctx) {
     if (!ctx) return RHJ_OK;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    DevBuf *bufs[] = {&ctx->bufA, &ctx->bufB, &ctx->zero, &ctx->meta, &ctx->items, &ctx->item_cnt, &ctx->item_off,
-                      &ctx->filt_cnt, &ctx->filt_off, &ctx->filt_tmp, &ctx->inR, &ctx->inS, &ctx->outP};
-    for (DevBuf *b : bufs)
-        if (b->p) cudaFree(b->p);
+    for_each_buf(ctx, [](DevBuf &b) { if (b.p) cudaFree(b.p); });
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->h_iu) cudaFreeHost(ctx->h_iu);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     for (cudaEvent_t e : ctx->ev)
         if (e) cudaEventDestroy(e);
@@ -516,10 +396,8 @@ const char *rhj_last_error(const rhj_ctx *ctx) { return ctx ? ctx->err.c_str() :
 
 uint64_t rhj_workspace_bytes(const rhj_ctx *ctx) {
     if (!ctx) return 0;
-    const DevBuf *bufs[] = {&ctx->bufA, &ctx->bufB, &ctx->zero, &ctx->meta, &ctx->items, &ctx->item_cnt,
-                            &ctx->item_off, &ctx->filt_cnt, &ctx->filt_off, &ctx->filt_tmp, &ctx->inR, &ctx->inS, &ctx->outP};
     uint64_t s = 0;
-    for (const DevBuf *b : bufs) s += b->cap;
+    for_each_buf(const_cast<rhj_ctx *>(ctx), [&s](DevBuf &b) { s += b.cap; });
     return s;
 }
 
@@ -656,19 +534,7 @@ int rhj_join_host(rhj_ctx *ctx, const rhj_tuple *R, uint64_t nR, const rhj_tuple
         return rc;
     if (n == 0) return RHJ_OK;
     if ((rc = ensure(ctx, ctx->outP, n * sizeof(Pair)))) return rc;
-    if (n * sizeof(Pair) > ctx->h_out_cap) {
-        if (ctx->h_out) cudaFreeHost(ctx->h_out);
-        ctx->h_out = nullptr;
-        ctx->h_out_cap = 0;
-        size_t want = n * sizeof(Pair);
-        want += want / 4;
-        cudaError_t e = cudaHostAlloc(&ctx->h_out, want, cudaHostAllocDefault);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            return fail(ctx, RHJ_ERR_NOMEM, "cudaHostAlloc result", e);
-        }
-        ctx->h_out_cap = want;
-    }
+    if ((rc = ensure_pinned(ctx, &ctx->h_out, &ctx->h_out_cap, n * sizeof(Pair)))) return rc;
     if ((rc = write_phase(ctx, st, (Pair *) ctx->outP.p, n))) return rc;
     CK(cudaMemcpyAsync(ctx->h_out, ctx->outP.p, n * sizeof(Pair), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -779,106 +645,6 @@ int rhj_shuffle_partition_device(rhj_ctx *ctx, const rhj_tuple *d_in, uint64_t n
     CK(cudaMemcpyAsync(off, ((u64 *) ctx->meta.p), (world + 1) * sizeof(u64), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     for (int r = 0; r < world; ++r) h_counts[r] = off[r + 1] - off[r];
-    return RHJ_OK;
-}
-
-// ---- filters / gathers ------------------------------------------------------------------------------
-
-int rhj_filter_u64_device(rhj_ctx *ctx, const uint64_t *d_col, const uint64_t *d_rowids_in, uint64_t n_in, int op,
-                          uint64_t constant, uint64_t *d_rowids_out, uint64_t *count, void *stream) {
-    if (!ctx || !count || (op != '>' && op != '<' && op != '=')) return RHJ_ERR_ARG;
-    *count = 0;
-    if (n_in == 0) return RHJ_OK;
-    if (!d_col || !d_rowids_out) return fail(ctx, RHJ_ERR_ARG, "null pointer");
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = pick(ctx, stream);
-    u64 ntile64 = (n_in + kFiltTile - 1) / kFiltTile;
-    if (ntile64 > 0x7fffffffull) return fail(ctx, RHJ_ERR_ARG, "column too large");
-    u32 ntile = (u32) ntile64;
-    int rc;
-    if ((rc = ensure(ctx, ctx->filt_cnt, (size_t) ntile * 4))) return rc;
-    if ((rc = ensure(ctx, ctx->filt_off, (size_t) ntile * 8 + 8))) return rc;
-    u64 *total = (u64 *) ctx->filt_off.p + ntile;
-    k_filter_count<<<ntile, kFiltThreads, 0, st>>>((const u64 *) d_col, (const u64 *) d_rowids_in, n_in, op, constant,
-                                                   (u32 *) ctx->filt_cnt.p);
-    k_scan_tiles<<<1, 1024, 0, st>>>((const u32 *) ctx->filt_cnt.p, ntile, (u64 *) ctx->filt_off.p, total);
-    // in-place compaction is safe tile by tile only if no tile writes ahead of an unread tile:
-    // output index <= input index always holds, but tiles run concurrently -> stage when aliased.
-    u64 *dst = (u64 *) d_rowids_out;
-    DevBuf &tmp = ctx->filt_tmp;
-    bool aliased = d_rowids_in && d_rowids_out == d_rowids_in;
-    if (aliased) {
-        if ((rc = ensure(ctx, tmp, n_in * 8))) return rc;
-        dst = (u64 *) tmp.p;
-    }
-    k_filter_write<<<ntile, kFiltThreads, 0, st>>>((const u64 *) d_col, (const u64 *) d_rowids_in, n_in, op, constant,
-                                                   (const u64 *) ctx->filt_off.p, dst);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(ctx->h_scalars, total, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    *count = ctx->h_scalars[0];
-    if (aliased && *count) {
-        CK(cudaMemcpyAsync(d_rowids_out, dst, *count * 8, cudaMemcpyDeviceToDevice, st));
-        CK(cudaStreamSynchronize(st));
-    }
-    return RHJ_OK;
-}
-
-int rhj_gather_tuples_device(rhj_ctx *ctx, const uint64_t *d_col, const uint64_t *d_rowids, uint64_t n,
-                             rhj_tuple *d_out, void *stream) {
-    if (!ctx) return RHJ_ERR_ARG;
-    if (n == 0) return RHJ_OK;
-    if (!d_col || !d_rowids || !d_out) return fail(ctx, RHJ_ERR_ARG, "null pointer");
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = pick(ctx, stream);
-    u32 grid = (u32) std::min<u64>((n + 255) / 256, (u64) ctx->num_sms * 16);
-    k_gather_tuples<<<grid, 256, 0, st>>>((const u64 *) d_col, (const u64 *) d_rowids, n, (Tup *) d_out);
-    CK(cudaGetLastError());
-    CK(cudaStreamSynchronize(st));
-    return RHJ_OK;
-}
-
-int rhj_gather_sum_u64_device(rhj_ctx *ctx, const uint64_t *d_col, const uint64_t *d_rowids, uint64_t n,
-                              uint64_t *sum, void *stream) {
-    if (!ctx || !sum) return RHJ_ERR_ARG;
-    *sum = 0;
-    if (n == 0) return RHJ_OK;
-    if (!d_col || !d_rowids) return fail(ctx, RHJ_ERR_ARG, "null pointer");
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = pick(ctx, stream);
-    int rc;
-    if ((rc = ensure(ctx, ctx->filt_off, 16))) return rc;
-    u64 *acc = (u64 *) ctx->filt_off.p;
-    CK(cudaMemsetAsync(acc, 0, 8, st));
-    u32 grid = (u32) std::min<u64>((n + 255) / 256, (u64) ctx->num_sms * 16);
-    k_gather_sum<<<grid, 256, 0, st>>>((const u64 *) d_col, (const u64 *) d_rowids, n, acc);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(ctx->h_scalars, acc, 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    *sum = ctx->h_scalars[0];
-    return RHJ_OK;
-}
-
-int rhj_pairs_digest_device(rhj_ctx *ctx, const rhj_pair *d_pairs, uint64_t n, uint64_t *sum, uint64_t *xr,
-                            void *stream) {
-    if (!ctx || !sum || !xr) return RHJ_ERR_ARG;
-    *sum = 0;
-    *xr = 0;
-    if (n == 0) return RHJ_OK;
-    if (!d_pairs) return fail(ctx, RHJ_ERR_ARG, "null pointer");
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = pick(ctx, stream);
-    int rc;
-    if ((rc = ensure(ctx, ctx->filt_off, 16))) return rc;
-    u64 *acc = (u64 *) ctx->filt_off.p;
-    CK(cudaMemsetAsync(acc, 0, 16, st));
-    u32 grid = (u32) std::min<u64>((n + 255) / 256, (u64) ctx->num_sms * 16);
-    k_pairs_digest<<<grid, 256, 0, st>>>((const Pair *) d_pairs, n, acc, acc + 1);
-    CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(ctx->h_scalars, acc, 16, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    *sum = ctx->h_scalars[0];
-    *xr = ctx->h_scalars[1];
     return RHJ_OK;
 }
 

@@ -1,0 +1,163 @@
+// rhj_ctx.cuh -- the context object behind `rhj_ctx*` and the helpers shared by the translation
+// units of librhj.so (rhj_api.cu: the join; rhj_query.cu: the join's neighbours on the query path).
+#pragma once
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/rhj.h"
+#include "rhj_device.cuh"
+
+using namespace rhj;
+
+static_assert(sizeof(rhj_tuple) == sizeof(Tup), "tuple layout");
+static_assert(sizeof(rhj_pair) == sizeof(Pair), "pair layout");
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+// indices into the zeroed scalar block (u64 units)
+enum Scalar {
+    kScWork0 = 0,   // work counter of the first join kernel
+    kScWork1 = 1,   // work counter of the second join kernel (write pass)
+    kScCursor = 2,  // FUSED output cursor / final count
+    kScNItems = 3,
+    kScTotal = 4,   // COUNT_THEN_WRITE total
+    kScErr = 5,
+    kScDigSum = 6,
+    kScDigXor = 7,
+    kScFilt = 8,
+    kScCount = 16
+};
+
+struct rhj_ctx {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    bool hist_agg = false;
+    int scatter_mode = 0;     // 0 staged per-thread stores, 1 TMA bulk stores (RHJ_SCATTER_MODE)
+
+    DevBuf bufA, bufB;        // pass-1 / pass-2 partitioned tuples (build side first, then probe side)
+    DevBuf zero;              // hist1 | hist2 | scalars   (memset to 0 per call)
+    DevBuf meta;              // offsets, cursors, tile tables
+    DevBuf items, item_cnt, item_off;
+    DevBuf filt_cnt, filt_off, filt_tmp;
+    DevBuf inR, inS, outP;    // device staging of the host entry point
+    DevBuf iu_col, iu_pairs, iu_A, iu_B, iu_ep, iu_out;  // update_intermediate staging (rhj_query.cu)
+    void *h_iu = nullptr;     // pinned host result columns of the intermediate update
+    size_t h_iu_cap = 0;
+    void *h_out = nullptr;    // pinned host result of rhj_join_host
+    size_t h_out_cap = 0;
+    u64 *h_scalars = nullptr; // pinned, kScCount u64
+
+    // state left by the partition + plan phase for the emit phase
+    struct {
+        bool valid = false;
+        bool counted = false;
+        const Tup *build = nullptr, *probe = nullptr;
+        const u64 *offB = nullptr, *offP = nullptr;
+        u32 nparts = 0;
+        u32 item_cap = 0;
+        int build_is_S = 0;
+        u64 count = 0;
+    } cur;
+    rhj_plan_info info{};
+
+    // optional per-phase timing (rhj_set_profiling)
+    bool profiling = false;
+    static constexpr int kMaxMarks = 24;
+    cudaEvent_t ev[kMaxMarks] = {};
+    int mark_phase[kMaxMarks] = {};
+    int nmarks = 0;
+};
+
+template <typename F>
+inline void for_each_buf(rhj_ctx *c, F f) {
+    DevBuf *bufs[] = {&c->bufA, &c->bufB, &c->zero, &c->meta, &c->items, &c->item_cnt, &c->item_off, &c->filt_cnt,
+                      &c->filt_off, &c->filt_tmp, &c->inR, &c->inS, &c->outP, &c->iu_col, &c->iu_pairs, &c->iu_A,
+                      &c->iu_B, &c->iu_ep, &c->iu_out};
+    for (DevBuf *b : bufs) f(*b);
+}
+
+inline int fail(rhj_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess) {
+    if (c) {
+        c->err = what;
+        if (e != cudaSuccess) {
+            c->err += ": ";
+            c->err += cudaGetErrorString(e);
+        }
+    }
+    return code;
+}
+
+#define CK(call)                                                           \
+    do {                                                                   \
+        cudaError_t e_ = (call);                                           \
+        if (e_ != cudaSuccess) return fail(ctx, RHJ_ERR_CUDA, #call, e_);  \
+    } while (0)
+
+// Grows a device buffer geometrically (never shrinks): the contest workload calls the join ~100
+// times per thread with varying sizes, and every cudaFree/cudaMalloc pair is a device-wide sync.
+inline int ensure(rhj_ctx *ctx, DevBuf &b, size_t bytes) {
+    if (bytes <= b.cap) return RHJ_OK;
+    CK(cudaSetDevice(ctx->device));
+    if (b.p) CK(cudaFree(b.p));
+    b.p = nullptr;
+    size_t want = std::max(bytes, std::min(2 * b.cap, b.cap + ((size_t) 1 << 30)));
+    want = std::max(want, (size_t) 1 << 16);
+    want = (want + 255) & ~(size_t) 255;
+    b.cap = 0;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess && want > bytes) {  // the slack did not fit: retry with the exact size
+        cudaGetLastError();
+        want = (bytes + 255) & ~(size_t) 255;
+        e = cudaMalloc(&b.p, want);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, RHJ_ERR_NOMEM, "cudaMalloc workspace", e);
+    }
+    b.cap = want;
+    return RHJ_OK;
+}
+
+// Same policy for the context-owned pinned host result blocks (pinning is slow: ~0.3 s / GiB).
+inline int ensure_pinned(rhj_ctx *ctx, void **p, size_t *cap, size_t bytes) {
+    if (bytes <= *cap) return RHJ_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    size_t want = std::max(bytes, std::min(2 * *cap, *cap + ((size_t) 1 << 30)));
+    want = std::max(want, (size_t) 1 << 20);
+    *cap = 0;
+    cudaError_t e = cudaHostAlloc(p, want, cudaHostAllocDefault);
+    if (e != cudaSuccess && want > bytes) {
+        cudaGetLastError();
+        want = bytes;
+        e = cudaHostAlloc(p, want, cudaHostAllocDefault);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, RHJ_ERR_NOMEM, "cudaHostAlloc result", e);
+    }
+    *cap = want;
+    return RHJ_OK;
+}
+
+inline void mark(rhj_ctx *ctx, cudaStream_t st, int phase) {
+    if (!ctx->profiling || ctx->nmarks >= rhj_ctx::kMaxMarks) return;
+    if (!ctx->ev[ctx->nmarks]) cudaEventCreate(&ctx->ev[ctx->nmarks]);
+    cudaEventRecord(ctx->ev[ctx->nmarks], st);
+    ctx->mark_phase[ctx->nmarks++] = phase;
+}
+
+
+// `stream` is the caller's cudaStream_t; NULL is CUDA's (legacy) default stream, exactly as in the
+// CUDA runtime API -- the caller's preceding work on that stream is what our kernels must follow.
+inline cudaStream_t pick(rhj_ctx *, void *stream) { return (cudaStream_t) stream; }
+
+

@@ -476,123 +476,4 @@ __global__ void __launch_bounds__(1024) k_scan_items(const u64 *cnt, const u32 *
     }
 }
 
-// ---- digest of a pair list (parity checks at sizes where sorting is too slow) ------------------
-__global__ void __launch_bounds__(256) k_pairs_digest(const Pair *p, u64 n, u64 *sum, u64 *xr) {
-    u64 s = 0, x = 0;
-    for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x) {
-        Pair q = p[i];
-        u64 h = mix64(q.r * 0x100000001b3ULL + q.s);
-        s += h;
-        x ^= h;
-    }
-    s = warp_sum64(s);
-    x = warp_xor64(x);
-    if (lane_id() == 0) {
-        atomicAdd(sum, s);
-        atomicXor(xr, x);
-    }
-}
-
-// ---- filters and gathers (Query.cpp:94-146, structs.cpp:217-226, Query.cpp:66-74) --------------
-constexpr int kFiltThreads = 256;
-constexpr int kFiltItems = 8;
-constexpr int kFiltTile = kFiltThreads * kFiltItems;
-
-__device__ __forceinline__ bool pred(u64 v, int op, u64 c) {
-    return op == '>' ? v > c : op == '<' ? v < c : v == c;
-}
-
-// pass 1: survivors per tile
-__global__ void __launch_bounds__(kFiltThreads) k_filter_count(const u64 *col, const u64 *rowids, u64 n, int op, u64 c,
-                                                               u32 *tile_cnt) {
-    __shared__ u32 s_c;
-    if (threadIdx.x == 0) s_c = 0;
-    __syncthreads();
-    u64 base = (u64) blockIdx.x * kFiltTile;
-    u32 mine = 0;
-#pragma unroll
-    for (int j = 0; j < kFiltItems; ++j) {
-        u64 i = base + (u64) threadIdx.x * kFiltItems + j;
-        if (i < n) {
-            u64 row = rowids ? rowids[i] : i;
-            mine += pred(col[row], op, c);
-        }
-    }
-    u32 w = (u32) warp_sum64(mine);
-    if (lane_id() == 0 && w) atomicAdd(&s_c, w);
-    __syncthreads();
-    if (threadIdx.x == 0) tile_cnt[blockIdx.x] = s_c;
-}
-
-__global__ void __launch_bounds__(1024) k_scan_tiles(const u32 *cnt, u32 n, u64 *off, u64 *total) {
-    __shared__ u64 s_w[32];
-    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 per = (n + 1023) / 1024;
-    const u32 i0 = min(n, tid * per), i1 = min(n, i0 + per);
-    u64 c = 0;
-    for (u32 i = i0; i < i1; ++i) c += cnt[i];
-    u64 inc = warp_incl_scan64(c);
-    if (lane == 31) s_w[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        u64 w = s_w[lane];
-        u64 wi = warp_incl_scan64(w);
-        s_w[lane] = wi - w;
-        if (lane == 31) *total = wi;
-    }
-    __syncthreads();
-    u64 run = inc - c + s_w[warp];
-    for (u32 i = i0; i < i1; ++i) {
-        off[i] = run;
-        run += cnt[i];
-    }
-}
-
-// pass 2: order-preserving compaction (thread t owns 8 consecutive rows -> ascending output)
-__global__ void __launch_bounds__(kFiltThreads) k_filter_write(const u64 *col, const u64 *rowids, u64 n, int op, u64 c,
-                                                               const u64 *tile_off, u64 *out) {
-    __shared__ u32 s_w[kFiltThreads / 32];
-    u64 base = (u64) blockIdx.x * kFiltTile;
-    u64 row[kFiltItems];
-    bool keep[kFiltItems];
-    u32 mine = 0;
-#pragma unroll
-    for (int j = 0; j < kFiltItems; ++j) {
-        u64 i = base + (u64) threadIdx.x * kFiltItems + j;
-        keep[j] = false;
-        if (i < n) {
-            row[j] = rowids ? rowids[i] : i;
-            keep[j] = pred(col[row[j]], op, c);
-        }
-        mine += keep[j];
-    }
-    u32 incl = warp_incl_scan(mine);
-    if (lane_id() == 31) s_w[threadIdx.x >> 5] = incl;
-    __syncthreads();
-    u32 before = 0;
-    for (u32 w = 0; w < (threadIdx.x >> 5); ++w) before += s_w[w];
-    u64 at = tile_off[blockIdx.x] + before + (incl - mine);
-#pragma unroll
-    for (int j = 0; j < kFiltItems; ++j)
-        if (keep[j]) out[at++] = row[j];
-}
-
-__global__ void __launch_bounds__(256) k_gather_tuples(const u64 *col, const u64 *rowids, u64 n, Tup *out) {
-    for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x) {
-        u64 row = rowids[i];
-        Tup t;
-        t.key = row;
-        t.val = col[row];
-        out[i] = t;
-    }
-}
-
-__global__ void __launch_bounds__(256) k_gather_sum(const u64 *col, const u64 *rowids, u64 n, u64 *sum) {
-    u64 s = 0;
-    for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (u64) gridDim.x * blockDim.x)
-        s += col[rowids[i]];
-    s = warp_sum64(s);
-    if (lane_id() == 0 && s) atomicAdd(sum, s);
-}
-
 }  // namespace rhj

@@ -19,35 +19,14 @@
 
 #include "Result.h"      // the reference's header (include path points at the reference tree)
 #include "rhj.h"
+#include "thread_ctx.h"
 
 #define BUCKET_SIZE (128 * 1024)   // Result.cpp:7
 
 static_assert(sizeof(tuple) == sizeof(rhj_tuple), "tuple must stay {u64 key; u64 payload}");
 static_assert(sizeof(key_tuple) == sizeof(rhj_pair), "key_tuple must stay {u64 keyR; u64 keyS}");
 
-namespace {
-
-// One GPU context per query thread: multiRadixHashJoin is entered concurrently from up to
-// NUM_OF_THREADS query threads (MainScheduler.cpp:6-14,23-26) and a context is not thread-safe.
-struct ThreadCtx {
-    rhj_ctx *ctx = nullptr;
-    ThreadCtx() {
-        const char *d = getenv("RHJ_DEVICE");
-        int rc = rhj_create(d ? atoi(d) : 0, &ctx);
-        if (rc != RHJ_OK) {
-            fprintf(stderr, "rhj_create failed (status %d): the CUDA join needs an sm_100 GPU; there is no CPU path\n", rc);
-            exit(EXIT_FAILURE);
-        }
-    }
-    ~ThreadCtx() { rhj_destroy(ctx); }
-};
-
-rhj_ctx *thread_ctx() {
-    static thread_local ThreadCtx t;
-    return t.ctx;
-}
-
-}  // namespace
+using rhj_host::thread_ctx;
 
 Result::Result() {
     capacity = (BUCKET_SIZE - sizeof(bucket_info)) / sizeof(tuple);
@@ -84,15 +63,13 @@ void Result::join_buckets(relation_info *, relation_info *, size_t, size_t, size
 }
 
 void Result::multiRadixHashJoin(JobScheduler &, relation &relR, relation &relS) {
+    rhj_host::Scope timer(0);
     rhj_ctx *ctx = thread_ctx();
     const rhj_pair *pairs = nullptr;
     uint64_t count = 0;
     int rc = rhj_join_host(ctx, (const rhj_tuple *) relR.tuples, relR.num_tuples, (const rhj_tuple *) relS.tuples,
                            relS.num_tuples, &pairs, &count);
-    if (rc != RHJ_OK) {
-        fprintf(stderr, "rhj_join_host failed (status %d): %s\n", rc, rhj_last_error(ctx));
-        exit(EXIT_FAILURE);
-    }
+    rhj_host::check(rc, "rhj_join_host");
     uint64_t head_size = capacity;
     head = (bucket_info *) rhj_pairs_to_pages(pairs, count, &head_size);
     size = head_size;

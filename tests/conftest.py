@@ -20,7 +20,8 @@ def pytest_configure(config):
 def small_dir(tmp_path_factory):
     """The contest `small` workload (14 binary relations + init/work/result), unpacked from the
     committed fixture tests/golden/small_relations.tar.xz."""
-    d = tmp_path_factory.mktemp("small")
+    d = tmp_path_factory.mktemp("work") / "small"      # the init file names ./small/rN
+    d.mkdir()
     with tarfile.open(os.path.join(GOLDEN, "small_relations.tar.xz")) as tf:
         tf.extractall(d)
     for name in ("small.init", "small.work", "small.result"):

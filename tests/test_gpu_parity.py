@@ -252,3 +252,113 @@ def test_small_workload_golden_through_gpu_join(engine, small_dir, small_joins_g
     lines = [Q.execute(q, rels, lambda R, S: engine.join_host(R, S), trace) for q in queries]
     assert lines == expected[:50]
     assert sorted(Q.join_trace_record(*t) for t in trace) == small_joins_golden
+
+
+# ---- update_intermediate on the GPU ----------------------------------------------------
+def _rows(cols):
+    """multiset of intermediate rows as a sorted 2-D array"""
+    a = np.stack(cols, axis=1) if len(cols) else np.empty((0, 0), dtype=np.uint64)
+    return a[np.lexsort(a.T[::-1])] if a.size else a
+
+
+@pytest.mark.parametrize("match_on_S", [0, 1])
+def test_intermediate_expand_equals_oracle(engine, match_on_S):
+    """case 2 (intermediate.cpp:108-125): N:M expansion of an existing intermediate by a join result"""
+    rng = np.random.default_rng(31 + match_on_S)
+    n_rows, n_pairs = 50000, 70000
+    inter = [rng.integers(0, 3000, n_rows, dtype=np.uint64), None, rng.integers(0, 10**6, n_rows, dtype=np.uint64), None]
+    pairs = np.empty(n_pairs, dtype=PAIR_DTYPE)
+    pairs["keyR"] = rng.integers(0, 3500, n_pairs, dtype=np.uint64)
+    pairs["keyS"] = rng.integers(0, 3500, n_pairs, dtype=np.uint64)
+    pairs = np.unique(pairs)
+    t1, t2 = (1, 0) if match_on_S else (0, 1)     # the binding already joined is table2 (S side) iff match_on_S
+    exp = Q.update_intermediate(inter, pairs, t1, t2)
+    carried, new = engine.intermediate_expand_host(inter[0], pairs, match_on_S, [inter[0], inter[2]])
+    got = _rows([carried[0], new, carried[1]])
+    assert len(new) == len(exp[0]) > n_rows
+    assert np.array_equal(got, _rows([exp[0], exp[1], exp[2]]))
+
+
+@pytest.mark.parametrize("wide", [False, True])
+def test_intermediate_filter_equals_oracle(engine, wide):
+    """case 3 (intermediate.cpp:130-138): keep rows whose (row id, row id) pair is in the join result;
+    wide = row ids >= 2^32 (composite-key fallback: match on the first id, verify the second)"""
+    rng = np.random.default_rng(41)
+    n_rows, n_pairs = 60000, 40000
+    base = np.uint64(2**40) if wide else np.uint64(0)
+    a = rng.integers(0, 300, n_rows, dtype=np.uint64) + base
+    b = rng.integers(0, 300, n_rows, dtype=np.uint64) + base
+    c = rng.integers(0, 10**9, n_rows, dtype=np.uint64)
+    pairs = np.empty(n_pairs, dtype=PAIR_DTYPE)
+    pairs["keyR"] = rng.integers(0, 300, n_pairs, dtype=np.uint64) + base
+    pairs["keyS"] = rng.integers(0, 300, n_pairs, dtype=np.uint64) + base
+    pairs = np.unique(pairs)
+    keep = np.isin(a.astype(object) * 2**64 + b.astype(object), pairs["keyR"].astype(object) * 2**64 + pairs["keyS"].astype(object)) \
+        if wide else np.isin((a << np.uint64(32)) | b, (pairs["keyR"] << np.uint64(32)) | pairs["keyS"])
+    got = engine.intermediate_filter_host(a, b, pairs, [a, b, c])
+    assert 0 < len(got[0]) == int(keep.sum())
+    assert np.array_equal(_rows(got), _rows([a[keep], b[keep], c[keep]]))
+
+
+def test_small_workload_with_gpu_intermediate(engine, small_dir):
+    """small.work with BOTH the join and update_intermediate on the GPU: all 50 checksum lines"""
+    rels = Q.load_workload(small_dir)
+    queries = Q.parse_work(os.path.join(small_dir, "small.work"))
+    expected = open(os.path.join(small_dir, "small.result")).read().split("\n")
+
+    def gpu_update(inter, pairs, t1, t2):
+        e1, e2 = inter[t1] is None, inter[t2] is None
+        if e1 and e2:
+            return Q.update_intermediate(inter, pairs, t1, t2)
+        live = [i for i, col in enumerate(inter) if col is not None]
+        new = [None] * len(inter)
+        if e1 or e2:
+            full, fresh = (t2, t1) if e1 else (t1, t2)
+            carried, col = engine.intermediate_expand_host(inter[full], pairs, 1 if e1 else 0, [inter[i] for i in live])
+            new[fresh] = col
+        else:
+            carried = engine.intermediate_filter_host(inter[t1], inter[t2], pairs, [inter[i] for i in live])
+        for i, colv in zip(live, carried):
+            new[i] = colv
+        return new
+
+    lines = [_execute_with(q, rels, engine, gpu_update) for q in queries]
+    assert lines == expected[:50]
+
+
+def _execute_with(q, rels, engine, update_fn):
+    filtered_out, filtered = Q.run_filters(q, rels)
+    inter = [None] * len(q.table)
+    if not filtered_out:
+        for (t1, c1, t2, c2) in q.join:
+            R = Q.create_relation(rels[q.table[t1]][c1], filtered[t1], inter[t1])
+            S = Q.create_relation(rels[q.table[t2]][c2], filtered[t2], inter[t2])
+            pairs = engine.join_host(R, S)
+            if len(pairs) == 0:
+                filtered_out = True
+                break
+            inter = update_fn(inter, pairs, t1, t2)
+    if filtered_out:
+        return " ".join("NULL" for _ in q.proj)
+    out = []
+    for (b, col) in q.proj:
+        rows = inter[b]
+        with np.errstate(over="ignore"):
+            out.append(0 if rows is None else int(np.add.reduce(rels[q.table[b]][col][rows.astype(np.int64)], dtype=np.uint64)))
+    return " ".join(str(v) for v in out)
+
+
+HOST_BIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "radixhashjoin_b200", "host", "_build")
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(HOST_BIN, "join_b200_full")),
+                    reason="drop-in binaries are built in the dev container (need the reference sources)")
+def test_reference_program_with_dropin_translation_units(small_dir):
+    """The reference PROGRAM itself (join.cpp, Query.cpp, ... unmodified) linked with our Result.cpp +
+    intermediate.cpp and librhj.so: `cat small.init small.work | ./join` == small.result."""
+    import subprocess
+    cwd = os.path.dirname(small_dir)
+    data = open(os.path.join(small_dir, "small.init"), "rb").read() + open(os.path.join(small_dir, "small.work"), "rb").read()
+    out = subprocess.run([os.path.join(HOST_BIN, "join_b200_full")], input=data, cwd=cwd, capture_output=True, timeout=600)
+    assert out.returncode == 0, out.stderr.decode()[-2000:]
+    assert out.stdout.decode() == open(os.path.join(small_dir, "small.result")).read()

@@ -4,7 +4,7 @@
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu ${BENCH_ARGS:-}"
+CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu --no-small-work ${BENCH_ARGS:-}"
 $CMD > gpurun_out/ncu_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_list.log 2>&1
 echo "launch list exit $?"

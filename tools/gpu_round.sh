@@ -18,13 +18,13 @@ cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ "${1:-}" != "quick" ]; then
   for v in "RHJ_HIST_AGG=1" "RHJ_SCATTER_BULK=1"; do
     echo "== bench $v"
-    env $v timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_$v.json 2> gpurun_out/bench_$v.err
+    env $v timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu --no-small-work > gpurun_out/bench_$v.json 2> gpurun_out/bench_$v.err
     cat gpurun_out/bench_$v.json; tail -3 gpurun_out/bench_$v.err
   done
   echo "== bench count_then_write"
-  timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu --emit count_then_write > gpurun_out/bench_ctw.json 2> gpurun_out/bench_ctw.err
+  timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu --no-small-work --emit count_then_write > gpurun_out/bench_ctw.json 2> gpurun_out/bench_ctw.err
   cat gpurun_out/bench_ctw.json
   echo "== bench 2^28"
-  timeout 600 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu --log2n 28 > gpurun_out/bench_28.json 2> gpurun_out/bench_28.err
+  timeout 600 python bench.py --steps 5 --warmup 3 --no-e2e --no-cpu --no-small-work --log2n 28 > gpurun_out/bench_28.json 2> gpurun_out/bench_28.err
   cat gpurun_out/bench_28.json; tail -3 gpurun_out/bench_28.err
 fi

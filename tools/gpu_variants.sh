@@ -8,7 +8,7 @@ echo "pytest exit $?" | tee -a gpurun_out/pytest.log
 tail -5 gpurun_out/pytest.log
 run() {  # name, env...
   name=$1; shift
-  env "$@" timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu ${BENCH_ARGS:-} > gpurun_out/v_$name.json 2> gpurun_out/v_$name.err
+  env "$@" timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu --no-small-work ${BENCH_ARGS:-} > gpurun_out/v_$name.json 2> gpurun_out/v_$name.err
   python - "$name" <<'PY'
 import json,sys
 n=sys.argv[1]
