@@ -248,14 +248,38 @@ def run_b200(args, rank, world, local_rank):
         recvS = torch.empty((slack, 2), dtype=torch.int64, device=dev)
         out = torch.empty((slack, 2), dtype=torch.int64, device=dev)
         eng.reserve(slack, slack)
-        from radixhashjoin_b200.distributed import ShardedJoin
-        sj = ShardedJoin(world, rank, lambda T: eng.shuffle_partition(T, world),
-                         lambda a, b: eng.join_device(a, b, out=out, emit=emit))
+        from radixhashjoin_b200.distributed import DmaShardedJoin, FusedShardedJoin, ShardedJoin
+        if args.shuffle == "dma":
+            # pass 1 partitions on (rank | sub-digit) into staging; the copy engines ship one chunk per peer
+            # while the SMs partition the other relation; pass 2 runs on the received (source, partition) pieces
+            dj = DmaShardedJoin(eng, world, rank, n_local * world, n_local * world, n_local, slack)
+            del recvR, recvS
 
-        def step():
-            # (K8) group both shards by destination rank (our kernels), exchange over NVLink (NCCL), join locally
-            pairs, count, _ = sj.step(R, S, recvR, recvS)
-            return pairs, count
+            def step():
+                pairs, count, _ = dj.step(R, S, out)
+                return pairs, count
+
+            def timeline():
+                marks = []
+                dj.step(R, S, out, marks)
+                torch.cuda.synchronize()
+                return dj.timeline(marks)
+        elif args.shuffle == "stores":
+            # pass 1 of the join IS the shuffle: runs are stored straight into the peers' receive buffers
+            fj = FusedShardedJoin(eng, world, rank, n_local * world, n_local * world, slack)
+            del recvR, recvS
+
+            def step():
+                pairs, count, _ = fj.step(R, S, out)
+                return pairs, count
+        else:
+            sj = ShardedJoin(world, rank, lambda T: eng.shuffle_partition(T, world),
+                             lambda a, b: eng.join_device(a, b, out=out, emit=emit))
+
+            def step():
+                # rank partition (our kernels) -> NCCL all-to-all -> local join
+                pairs, count, _ = sj.step(R, S, recvR, recvS)
+                return pairs, count
 
     def barrier():
         if world > 1:
@@ -277,7 +301,7 @@ def run_b200(args, rank, world, local_rank):
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
     plan = eng.last_plan()
-    launches_per_step = plan["kernel_launches"] * (1 if world == 1 else 1) + (0 if world == 1 else 6)
+    launches_per_step = plan["kernel_launches"] + (0 if world == 1 else (6 if args.shuffle == "nccl" else 0))
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -304,6 +328,9 @@ def run_b200(args, rank, world, local_rank):
             verified = (int(tot[0].item()), int(tot[1].item()) & ((1 << 64) - 1), x) == tuple(exp)
     m_local = count
 
+    shard_timeline = None
+    if world > 1 and args.shuffle == "dma":
+        shard_timeline = timeline()
     # ---- per-phase device times -> roofline of the dominant kernel (separate, untimed passes) ----
     eng.set_profiling(True)
     acc = {}
@@ -314,9 +341,7 @@ def run_b200(args, rank, world, local_rank):
         for k, v in eng.last_phase_ms().items():
             acc[k] = acc.get(k, 0.0) + v / reps
     eng.set_profiling(False)
-    n_join = (recvR.shape[0] if world > 1 else nR) + (recvS.shape[0] if world > 1 else nS)
-    if world > 1:
-        n_join = n_in_local  # ~ balanced: what this rank joins after the exchange
+    n_join = n_in_local  # at N > 1: ~ balanced, what this rank joins after the exchange
     alg_bytes = {"hist1": 16 * n_join, "scatter1": 32 * n_join, "hist2": 16 * n_join, "scatter2": 32 * n_join,
                  "join": 16 * n_join + 16 * m_local, "join_write": 16 * n_join + 16 * m_local}
     dom = max((k for k in alg_bytes if acc.get(k, 0) > 0), key=lambda k: acc[k], default=None)
@@ -372,13 +397,20 @@ def run_b200(args, rank, world, local_rank):
                            "cache": "inputs (2 x %.1f GiB per GPU) are far larger than the 126 MB L2; no flush needed"
                                     % (nR * 16 / 2**30),
                            "radix_bits": [plan["bits_pass1"], plan["bits_pass2"]],
-                           "parallelism": "1 GPU" if world == 1 else f"{world} ranks: rank-radix shuffle (NCCL all-to-all) + local join"},
+                           "parallelism": "1 GPU" if world == 1 else (
+                               f"{world} ranks: pass 1 partitions on (rank | sub-digit), copy engines ship one chunk per peer over "
+                               "NVLink overlapped with the other relation's passes, then local pass 2 + join" if args.shuffle == "dma" else
+                               f"{world} ranks: pass-1 scatter stores into peer receive buffers over NVLink (fused partition+shuffle), "
+                               "then local pass 2 + join" if args.shuffle == "stores" else
+                               f"{world} ranks: rank-radix partition + NCCL all-to-all + local join")},
                 "verified": verified, "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
                 "phase_ms": {k: round(v, 4) for k, v in acc.items() if v > 0},
                 "roofline": roofline,
                 "step_roofline": {"algorithmic_bytes": b_alg_step, "formula": "96*n + 16*m (SURVEY 8d)",
                                   "achieved_GBps": step_gbs, "frac_of_measured_hbm": step_gbs / peak},
                 "e2e": e2e, "cpu_baseline": cpu}
+        if shard_timeline:
+            line["shard_timeline_ms"] = shard_timeline
         if world == 1 and not args.no_small_work:
             line["small_work"] = small_work_wall(args.small_work_ref)
         print(json.dumps(line), flush=True)
@@ -399,6 +431,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-log2n", type=int, default=26, help="cpu_baseline sample size (2^k x 2^k)")
     ap.add_argument("--ref-log2n", type=int, default=24, help="--impl reference: sample per step")
+    ap.add_argument("--shuffle", default="dma", choices=["dma", "stores", "nccl"],
+                    help="multi-GPU exchange: pass-1 chunks shipped by the copy engines (default), pass-1 scatter storing "
+                         "straight into peer memory, or rank partition + NCCL all-to-all")
     ap.add_argument("--no-small-work", action="store_true")
     ap.add_argument("--small-work-ref", action="store_true", help="also time the unmodified reference program (minutes)")
     ap.add_argument("--no-e2e", action="store_true")

@@ -176,6 +176,51 @@ int rhj_intermediate_filter_host(rhj_ctx *ctx, const uint64_t *col1, const uint6
 int rhj_shuffle_partition_device(rhj_ctx *ctx, const rhj_tuple *d_in, uint64_t n, int world,
                                  rhj_tuple *d_out, uint64_t *h_counts, void *stream);
 
+/* Fused partition + shuffle: pass 1 of the join partitions on (destination rank | sub-digit) and
+ * its scatter stores every run directly into the destination rank's receive buffer through peer
+ * memory (NVLink / NVSwitch), so the exchange costs no extra pass over HBM and overlaps the
+ * scatter tile by tile.  Call sequence per join, on every rank, with the same plan:
+ *   rhj_shard_plan_make -> rhj_shard_histogram_device -> [all-gather the histograms] ->
+ *   rhj_shard_offsets_device -> [barrier: receive buffers free] -> rhj_shard_scatter_device ->
+ *   [barrier: all stores landed] -> rhj_shard_join_device.
+ * The two small collectives and the barriers are the caller's (torch.distributed / symmetric
+ * memory in radixhashjoin_b200/distributed.py). */
+typedef struct rhj_shard_plan {
+    uint32_t world, rank_bits;                       /* ranks (power of two <= 16), log2(world)        */
+    uint32_t bits_total, bits_pass1, bits_pass2;     /* local radix bits: total, fused pass, second pass */
+    uint32_t build_is_S;
+} rhj_shard_plan;
+int rhj_shard_plan_make(uint64_t nR_global, uint64_t nS_global, int world, rhj_shard_plan *plan);
+int rhj_shard_histogram_device(rhj_ctx *ctx, const rhj_shard_plan *plan, const rhj_tuple *dR, uint64_t nR,
+                               const rhj_tuple *dS, uint64_t nS, uint64_t *d_hist, void *stream);
+int rhj_shard_offsets_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int rank, const uint64_t *d_all_hist,
+                             uint64_t *recv_counts, void *stream);
+int rhj_shard_scatter_device(rhj_ctx *ctx, const rhj_shard_plan *plan, const rhj_tuple *dR, uint64_t nR,
+                             const rhj_tuple *dS, uint64_t nS, void *const *peer_R, void *const *peer_S, void *stream);
+int rhj_shard_join_device(rhj_ctx *ctx, const rhj_shard_plan *plan, const rhj_tuple *d_recvR, uint64_t nR_recv,
+                          const rhj_tuple *d_recvS, uint64_t nS_recv, rhj_pair *d_out, uint64_t capacity,
+                          uint64_t *count, void *stream);
+
+/* DMA-shipped variant of the sharded join (the default of bench.py at N > 1).  Pass 1 partitions each
+ * local shard on (destination rank | sub-digit) into a LOCAL staging buffer, so the data for one
+ * destination is one contiguous chunk that is already pass-1 partitioned; the caller ships the chunks
+ * with the copy engines (peer cudaMemcpyAsync over NVLink at full packet efficiency, no SM time) while
+ * the SMs partition the other relation; pass 2 consumes the received chunks as (source, partition)
+ * pieces.  Per relation (rel 0 = R, 1 = S), on every rank, same plan:
+ *   rhj_shardx_begin -> rhj_shardx_pass1_device(rel) -> [all-gather d_hist] -> rhj_shardx_layout_device(rel)
+ *   -> [barrier; peer copies of send_cnt[d] tuples from stage+send_off[d] to dest d's buffer+dst_off[d];
+ *      barrier] -> rhj_shardx_pass2_device(rel) ... -> rhj_shardx_join_device. */
+int rhj_shardx_begin(rhj_ctx *ctx, const rhj_shard_plan *plan, void *stream);
+int rhj_shardx_pass1_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int rel, const rhj_tuple *d_in, uint64_t n,
+                            rhj_tuple *d_stage, uint64_t *d_hist, void *stream);
+int rhj_shardx_layout_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int rank, int rel, const uint64_t *d_all_hist,
+                             uint64_t *send_off, uint64_t *send_cnt, uint64_t *dst_off, uint64_t *recv_total,
+                             void *stream);
+int rhj_shardx_pass2_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int rel, const rhj_tuple *d_recv, uint64_t n_recv,
+                            void *stream);
+int rhj_shardx_join_device(rhj_ctx *ctx, const rhj_shard_plan *plan, rhj_pair *d_out, uint64_t capacity, uint64_t *count,
+                           void *stream);
+
 /* ---- introspection for benchmarks ------------------------------------------------------------ */
 
 typedef struct rhj_plan_info {

@@ -22,6 +22,12 @@ class PlanInfo(ctypes.Structure):
                 ("kernel_launches", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
 
 
+class ShardPlan(ctypes.Structure):
+    """struct rhj_shard_plan (include/rhj.h)."""
+    _fields_ = [("world", ctypes.c_uint32), ("rank_bits", ctypes.c_uint32), ("bits_total", ctypes.c_uint32),
+                ("bits_pass1", ctypes.c_uint32), ("bits_pass2", ctypes.c_uint32), ("build_is_S", ctypes.c_uint32)]
+
+
 # name -> (restype, argtypes): every symbol include/rhj.h declares
 SIGNATURES = {
     "rhj_version": (ctypes.c_char_p, []),
@@ -46,6 +52,18 @@ SIGNATURES = {
     "rhj_intermediate_filter_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_u64, c_vp, c_u64, c_vp, ctypes.c_uint32, c_vp,
                                                     c_u64p]),
     "rhj_shuffle_partition_device": (ctypes.c_int, [c_vp, c_vp, c_u64, ctypes.c_int, c_vp, c_u64p, c_vp]),
+    "rhj_shard_plan_make": (ctypes.c_int, [c_u64, c_u64, ctypes.c_int, ctypes.POINTER(ShardPlan)]),
+    "rhj_shard_histogram_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), c_vp, c_u64, c_vp, c_u64, c_vp, c_vp]),
+    "rhj_shard_offsets_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, c_vp, c_u64p, c_vp]),
+    "rhj_shard_scatter_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), c_vp, c_u64, c_vp, c_u64, c_vp, c_vp, c_vp]),
+    "rhj_shard_join_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), c_vp, c_u64, c_vp, c_u64, c_vp, c_u64,
+                                             c_u64p, c_vp]),
+    "rhj_shardx_begin": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), c_vp]),
+    "rhj_shardx_pass1_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, c_vp, c_u64, c_vp, c_vp, c_vp]),
+    "rhj_shardx_layout_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, ctypes.c_int, c_vp, c_u64p,
+                                                c_u64p, c_u64p, c_u64p, c_vp]),
+    "rhj_shardx_pass2_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, c_vp, c_u64, c_vp]),
+    "rhj_shardx_join_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), c_vp, c_u64, c_u64p, c_vp]),
     "rhj_last_plan": (ctypes.c_int, [c_vp, ctypes.POINTER(PlanInfo)]),
     "rhj_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "rhj_last_phase_ms": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_float)]),

@@ -202,6 +202,84 @@ class RadixHashJoin:
                                                         self._stream(stream)))
         return out, [int(c) for c in counts]
 
+    # ---- multi-GPU: fused partition + shuffle (include/rhj.h, rhj_shard_*) ----------------------
+    def shard_plan(self, nR_global, nS_global, world):
+        plan = _lib.ShardPlan()
+        self._ck(self._lib.rhj_shard_plan_make(nR_global, nS_global, world, ctypes.byref(plan)))
+        return plan
+
+    def shard_histogram(self, plan, R, S, hist=None, stream=None):
+        """pass-1 histogram on (destination rank | sub-digit): int64 tensor [2, world << bits_pass1]"""
+        torch = _torch()
+        nR, nS = _check_rel(R), _check_rel(S)
+        if hist is None:
+            hist = torch.empty((2, plan.world << plan.bits_pass1), dtype=torch.int64, device=R.device)
+        self._ck(self._lib.rhj_shard_histogram_device(self._ctx, ctypes.byref(plan), _ptr(R), nR, _ptr(S), nS, _ptr(hist),
+                                                      self._stream(stream)))
+        return hist
+
+    def shard_offsets(self, plan, rank, all_hist, stream=None):
+        """write cursors + receive layout from the all-gathered histograms; returns (nR_recv, nS_recv)"""
+        recv = (ctypes.c_uint64 * 2)()
+        self._ck(self._lib.rhj_shard_offsets_device(self._ctx, ctypes.byref(plan), rank, _ptr(all_hist), recv,
+                                                    self._stream(stream)))
+        return int(recv[0]), int(recv[1])
+
+    def shard_scatter(self, plan, R, S, peer_ptrs_R, peer_ptrs_S, stream=None):
+        """the fused pass: scatter both shards straight into the destination ranks' receive buffers"""
+        nR, nS = _check_rel(R), _check_rel(S)
+        pr = (ctypes.c_void_p * plan.world)(*peer_ptrs_R)
+        ps = (ctypes.c_void_p * plan.world)(*peer_ptrs_S)
+        self._ck(self._lib.rhj_shard_scatter_device(self._ctx, ctypes.byref(plan), _ptr(R), nR, _ptr(S), nS, pr, ps,
+                                                    self._stream(stream)))
+
+    def shard_join(self, plan, recvR, recvS, out, stream=None):
+        """second radix pass + build/probe + fused emit on what this rank received"""
+        nR, nS = _check_rel(recvR), _check_rel(recvS)
+        cnt = ctypes.c_uint64()
+        rc = self._lib.rhj_shard_join_device(self._ctx, ctypes.byref(plan), _ptr(recvR), nR, _ptr(recvS), nS, _ptr(out),
+                                             out.shape[0], ctypes.byref(cnt), self._stream(stream))
+        if rc == 4:
+            e = RhjError(rc, self._lib.rhj_last_error(self._ctx).decode())
+            e.needed = int(cnt.value)
+            raise e
+        self._ck(rc)
+        return out[:cnt.value], int(cnt.value)
+
+    # ---- multi-GPU: DMA-shipped sharded join (include/rhj.h, rhj_shardx_*) ------------------------
+    def shardx_begin(self, plan, stream=None):
+        self._ck(self._lib.rhj_shardx_begin(self._ctx, ctypes.byref(plan), self._stream(stream)))
+
+    def shardx_pass1(self, plan, rel, T, stage, hist, stream=None):
+        """pass 1 of relation rel into the local staging tensor (ordered by destination rank, partition)"""
+        n = _check_rel(T)
+        self._ck(self._lib.rhj_shardx_pass1_device(self._ctx, ctypes.byref(plan), rel, _ptr(T), n, _ptr(stage), _ptr(hist),
+                                                   self._stream(stream)))
+
+    def shardx_layout(self, plan, rank, rel, all_hist, stream=None):
+        """(send_off[d], send_cnt[d], dst_off[d], recv_total) from the all-gathered histograms"""
+        W = plan.world
+        so, sc, do = (ctypes.c_uint64 * W)(), (ctypes.c_uint64 * W)(), (ctypes.c_uint64 * W)()
+        tot = ctypes.c_uint64()
+        self._ck(self._lib.rhj_shardx_layout_device(self._ctx, ctypes.byref(plan), rank, rel, _ptr(all_hist), so, sc, do,
+                                                    ctypes.byref(tot), self._stream(stream)))
+        return [int(v) for v in so], [int(v) for v in sc], [int(v) for v in do], int(tot.value)
+
+    def shardx_pass2(self, plan, rel, recv, stream=None):
+        n = _check_rel(recv)
+        self._ck(self._lib.rhj_shardx_pass2_device(self._ctx, ctypes.byref(plan), rel, _ptr(recv), n, self._stream(stream)))
+
+    def shardx_join(self, plan, out, stream=None):
+        cnt = ctypes.c_uint64()
+        rc = self._lib.rhj_shardx_join_device(self._ctx, ctypes.byref(plan), _ptr(out), out.shape[0], ctypes.byref(cnt),
+                                              self._stream(stream))
+        if rc == 4:
+            e = RhjError(rc, self._lib.rhj_last_error(self._ctx).decode())
+            e.needed = int(cnt.value)
+            raise e
+        self._ck(rc)
+        return out[:cnt.value], int(cnt.value)
+
     # ---- neighbours on the query path ----------------------------------------------------------
     def filter(self, col, op, constant, rowids=None, stream=None):
         """Query::run_filters predicate (Query.cpp:94-146): surviving row ids, input order kept."""

@@ -25,10 +25,10 @@ Plan make_plan(u64 nR, u64 nS) {
     p.nP = p.build_is_S ? nR : nS;
     int bits = 0;
     if (p.nB > kBuildCap) {
-        while (bits < 2 * kMaxBitsPerPass && (p.nB >> bits) > kTargetBuildPerPart) ++bits;
+        while (bits < 2 * kPlanBitsPerPass && (p.nB >> bits) > kTargetBuildPerPart) ++bits;
     }
     p.bits = bits;
-    p.b1 = bits <= kMaxBitsPerPass ? bits : (bits + 1) / 2;
+    p.b1 = bits <= kPlanBitsPerPass ? bits : (bits + 1) / 2;
     p.b2 = bits - p.b1;
     p.nparts = 1u << bits;
     return p;
@@ -57,6 +57,7 @@ int launch_hist(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, bool
     } while (0)
     if (kind == kDigitRaw) { if (seg) HIST(kDigitRaw, true); else HIST(kDigitRaw, false); }
     else if (kind == kDigitHash) { if (seg) HIST(kDigitHash, true); else HIST(kDigitHash, false); }
+    else if (kind == kDigitShard) HIST(kDigitShard, false);
     else { if (seg) HIST(kDigitRank, true); else HIST(kDigitRank, false); }
 #undef HIST
     CK(cudaGetLastError());
@@ -76,11 +77,12 @@ cudaError_t launch_scatter_t(cudaStream_t st, const PartArgs &a, u32 grid) {
 int launch_scatter(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, bool seg) {
     u32 grid = a.rel[0].ntiles + a.rel[1].ntiles;
     if (!grid) return RHJ_OK;
-    const int w = ctx->scatter_mode;
+    const int w = kind == kDigitShard ? ctx->shard_scatter_mode : ctx->scatter_mode;
     cudaError_t e;
 #define SC(K, S) (w == 1 ? launch_scatter_t<K, S, kWriteBulk>(st, a, grid) : launch_scatter_t<K, S, kWriteStaged>(st, a, grid))
     if (kind == kDigitRaw) e = seg ? SC(kDigitRaw, true) : SC(kDigitRaw, false);
     else if (kind == kDigitHash) e = seg ? SC(kDigitHash, true) : SC(kDigitHash, false);
+    else if (kind == kDigitShard) e = SC(kDigitShard, false);
     else e = seg ? SC(kDigitRank, true) : SC(kDigitRank, false);
 #undef SC
     CK(e);
@@ -138,6 +140,97 @@ u64 *scalars_of(rhj_ctx *ctx, u32 nparts) {
     return (u64 *) ctx->zero.p + 2 * (size_t) kMaxDigits + 2 * (size_t) nparts;
 }
 
+// Second radix pass (if the plan has one) over pass-1-partitioned relations inX[0] (build) and
+// inX[1] (probe) whose pass-1 offsets / first-tile tables are off1X / tile0X, then the work-item
+// plan.  Leaves ctx->cur describing the final partitions.  Enqueues only; no host sync.
+int second_pass_and_plan(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Meta &m, const Tup *const inX[2],
+                         const u64 *const off1X[2], const u32 *const tile0X[2]) {
+    int rc;
+    const Tup *finB, *finP;
+    const u64 *offB, *offP;
+    bool planned = false;
+    u32 item_cap = 0;
+    if (pl.b2 == 0) {
+        finB = inX[0];
+        finP = inX[1];
+        offB = off1X[0];
+        offP = off1X[1];
+    } else {
+        // ---- pass 2: next b2 bits, inside every pass-1 partition ----
+        if ((rc = ensure(ctx, ctx->bufB, (pl.nB + pl.nP) * sizeof(Tup)))) return rc;
+        Tup *B = (Tup *) ctx->bufB.p;
+        PartArgs b{};
+        b.shift = 32 - pl.bits;
+        b.mask = (1u << pl.b2) - 1;
+        b.ndig = 1u << pl.b2;
+        const u32 nseg = 1u << pl.b1;
+        b.rel[0] = PartRel{inX[0], B, pl.nB, m.hist2[0], m.cur2[0], off1X[0], tile0X[0], nseg, tiles_of(pl.nB) + nseg};
+        b.rel[1] = PartRel{inX[1], B + pl.nB, pl.nP, m.hist2[1], m.cur2[1], off1X[1], tile0X[1], nseg,
+                           tiles_of(pl.nP) + nseg};
+        mark(ctx, st, RHJ_PHASE_HIST2);
+        if ((rc = launch_hist(ctx, st, b, kDigitHash, true))) return rc;
+        mark(ctx, st, RHJ_PHASE_SCAN2);
+        // offsets of all 2^bits sub-partitions + the work-item list, one CTA per pass-1 partition
+        u64 cap64 = (u64) pl.nparts + pl.nP / kProbeChunk + 2;
+        if (cap64 > 0x7fffffffull) return fail(ctx, RHJ_ERR_ARG, "relation too large for the work-item table");
+        item_cap = (u32) cap64;
+        if ((rc = ensure(ctx, ctx->items, (size_t) item_cap * sizeof(Item)))) return rc;
+        ScanPlanArgs sp{};
+        for (int i = 0; i < 2; ++i) {
+            sp.hist2[i] = m.hist2[i];
+            sp.off1[i] = off1X[i];
+            sp.off2[i] = m.off2[i];
+            sp.cursor2[i] = m.cur2[i];
+        }
+        sp.nseg = nseg;
+        sp.ndig = b.ndig;
+        sp.items = (Item *) ctx->items.p;
+        sp.item_cap = item_cap;
+        sp.nitems = (u32 *) (m.scalars + kScNItems);
+        sp.err = (u32 *) (m.scalars + kScErr);
+        k_scan_parts_plan<<<nseg, kMaxDigits, 0, st>>>(sp);
+        CK(cudaGetLastError());
+        ctx->info.kernel_launches++;
+        planned = true;
+        mark(ctx, st, RHJ_PHASE_SCATTER2);
+        if ((rc = launch_scatter(ctx, st, b, kDigitHash, true))) return rc;
+        finB = B;
+        finP = B + pl.nB;
+        offB = m.off2[0];
+        offP = m.off2[1];
+    }
+
+    // ---- plan: work items (two-pass plans were planned by k_scan_parts_plan) ----
+    if (!planned) {
+        mark(ctx, st, RHJ_PHASE_PLAN);
+        u64 cap64 = (u64) pl.nparts + pl.nP / kProbeChunk + 2;
+        if (cap64 > 0x7fffffffull) return fail(ctx, RHJ_ERR_ARG, "relation too large for the work-item table");
+        item_cap = (u32) cap64;
+        if ((rc = ensure(ctx, ctx->items, (size_t) item_cap * sizeof(Item)))) return rc;
+        PlanArgs pa{};
+        pa.offB = offB;
+        pa.offP = offP;
+        pa.nparts = pl.nparts;
+        pa.items = (Item *) ctx->items.p;
+        pa.item_cap = item_cap;
+        pa.nitems = (u32 *) (m.scalars + kScNItems);
+        pa.err = (u32 *) (m.scalars + kScErr);
+        k_plan<<<1, 1024, 0, st>>>(pa);
+        CK(cudaGetLastError());
+        ctx->info.kernel_launches++;
+    }
+
+    ctx->cur.valid = true;
+    ctx->cur.build = finB;
+    ctx->cur.probe = finP;
+    ctx->cur.offB = offB;
+    ctx->cur.offP = offP;
+    ctx->cur.nparts = pl.nparts;
+    ctx->cur.item_cap = item_cap;
+    ctx->cur.build_is_S = pl.build_is_S;
+    return RHJ_OK;
+}
+
 // Partition both relations on `bits` hash bits (one or two passes) and build the work-item list.
 // Leaves ctx->cur describing the partitioned relations.  Enqueues only; no host sync.
 int partition_and_plan(rhj_ctx *ctx, cudaStream_t st, const Tup *dR, u64 nR, const Tup *dS, u64 nS) {
@@ -160,10 +253,8 @@ int partition_and_plan(rhj_ctx *ctx, cudaStream_t st, const Tup *dR, u64 nR, con
     CK(cudaMemsetAsync(ctx->zero.p, 0, m.zero_bytes, st));
 
     const u64 ntot = pl.nB + pl.nP;
-    const Tup *finB, *finP;
-    const u64 *offB, *offP;
-    bool planned = false;
-    u32 item_cap = 0;
+    const Tup *finB = nullptr, *finP = nullptr;
+    const u64 *offB = nullptr, *offP = nullptr;
 
     if (pl.bits == 0) {
         finB = inB;
@@ -200,87 +291,15 @@ int partition_and_plan(rhj_ctx *ctx, cudaStream_t st, const Tup *dR, u64 nR, con
         mark(ctx, st, RHJ_PHASE_SCATTER1);
         if ((rc = launch_scatter(ctx, st, a, kDigitHash, false))) return rc;
 
-        if (pl.b2 == 0) {
-            finB = A;
-            finP = A + pl.nB;
-            offB = m.off1[0];
-            offP = m.off1[1];
-        } else {
-            // ---- pass 2: next b2 bits, inside every pass-1 partition ----
-            if ((rc = ensure(ctx, ctx->bufB, ntot * sizeof(Tup)))) return rc;
-            Tup *B = (Tup *) ctx->bufB.p;
-            PartArgs b{};
-            b.shift = 32 - pl.bits;
-            b.mask = (1u << pl.b2) - 1;
-            b.ndig = 1u << pl.b2;
-            const u32 nseg = 1u << pl.b1;
-            b.rel[0] = PartRel{A, B, pl.nB, m.hist2[0], m.cur2[0], m.off1[0], m.tile0[0], nseg, tiles_of(pl.nB) + nseg};
-            b.rel[1] = PartRel{A + pl.nB, B + pl.nB, pl.nP, m.hist2[1], m.cur2[1], m.off1[1], m.tile0[1], nseg,
-                               tiles_of(pl.nP) + nseg};
-            mark(ctx, st, RHJ_PHASE_HIST2);
-            if ((rc = launch_hist(ctx, st, b, kDigitHash, true))) return rc;
-            mark(ctx, st, RHJ_PHASE_SCAN2);
-            // offsets of all 2^bits sub-partitions + the work-item list, one CTA per pass-1 partition
-            u64 cap64 = (u64) pl.nparts + pl.nP / kProbeChunk + 2;
-            if (cap64 > 0x7fffffffull) return fail(ctx, RHJ_ERR_ARG, "relation too large for the work-item table");
-            item_cap = (u32) cap64;
-            if ((rc = ensure(ctx, ctx->items, (size_t) item_cap * sizeof(Item)))) return rc;
-            ScanPlanArgs sp{};
-            for (int i = 0; i < 2; ++i) {
-                sp.hist2[i] = m.hist2[i];
-                sp.off1[i] = m.off1[i];
-                sp.off2[i] = m.off2[i];
-                sp.cursor2[i] = m.cur2[i];
-            }
-            sp.nseg = nseg;
-            sp.ndig = b.ndig;
-            sp.items = (Item *) ctx->items.p;
-            sp.item_cap = item_cap;
-            sp.nitems = (u32 *) (m.scalars + kScNItems);
-            sp.err = (u32 *) (m.scalars + kScErr);
-            k_scan_parts_plan<<<nseg, kMaxDigits, 0, st>>>(sp);
-            CK(cudaGetLastError());
-            ctx->info.kernel_launches++;
-            planned = true;
-            // segment offsets inside A are relative to each relation's base: rel.in already points there
-            mark(ctx, st, RHJ_PHASE_SCATTER2);
-            if ((rc = launch_scatter(ctx, st, b, kDigitHash, true))) return rc;
-            finB = B;
-            finP = B + pl.nB;
-            offB = m.off2[0];
-            offP = m.off2[1];
-        }
+        const Tup *inX[2] = {A, A + pl.nB};
+        const u64 *off1X[2] = {m.off1[0], m.off1[1]};
+        const u32 *tile0X[2] = {m.tile0[0], m.tile0[1]};
+        return second_pass_and_plan(ctx, st, pl, m, inX, off1X, tile0X);
     }
-
-    // ---- plan: work items (two-pass plans were planned by k_scan_parts_plan) ----
-    if (!planned) {
-        mark(ctx, st, RHJ_PHASE_PLAN);
-        u64 cap64 = (u64) pl.nparts + pl.nP / kProbeChunk + 2;
-        if (cap64 > 0x7fffffffull) return fail(ctx, RHJ_ERR_ARG, "relation too large for the work-item table");
-        item_cap = (u32) cap64;
-        if ((rc = ensure(ctx, ctx->items, (size_t) item_cap * sizeof(Item)))) return rc;
-        PlanArgs pa{};
-        pa.offB = offB;
-        pa.offP = offP;
-        pa.nparts = pl.nparts;
-        pa.items = (Item *) ctx->items.p;
-        pa.item_cap = item_cap;
-        pa.nitems = (u32 *) (m.scalars + kScNItems);
-        pa.err = (u32 *) (m.scalars + kScErr);
-        k_plan<<<1, 1024, 0, st>>>(pa);
-        CK(cudaGetLastError());
-        ctx->info.kernel_launches++;
-    }
-
-    ctx->cur.valid = true;
-    ctx->cur.build = finB;
-    ctx->cur.probe = finP;
-    ctx->cur.offB = offB;
-    ctx->cur.offP = offP;
-    ctx->cur.nparts = pl.nparts;
-    ctx->cur.item_cap = item_cap;
-    ctx->cur.build_is_S = pl.build_is_S;
-    return RHJ_OK;
+    const Tup *inX[2] = {finB, finP};
+    const u64 *off1X[2] = {offB, offP};
+    const u32 *tile0X[2] = {nullptr, nullptr};
+    return second_pass_and_plan(ctx, st, pl, m, inX, off1X, tile0X);
 }
 
 JoinArgs join_args(rhj_ctx *ctx, int work_slot) {
@@ -367,6 +386,7 @@ int rhj_create(int device, rhj_ctx **out) {
     const char *e;
     if ((e = getenv("RHJ_HIST_AGG"))) ctx->hist_agg = atoi(e) != 0;
     if ((e = getenv("RHJ_SCATTER_MODE"))) ctx->scatter_mode = atoi(e);
+    if ((e = getenv("RHJ_SHARD_SCATTER_MODE"))) ctx->shard_scatter_mode = atoi(e);
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaHostAlloc((void **) &ctx->h_scalars, kScCount * sizeof(u64), cudaHostAllocDefault) != cudaSuccess) {
@@ -566,7 +586,7 @@ void *rhj_pairs_to_pages(const rhj_pair *pairs, uint64_t count, uint64_t *head_s
 
 int rhj_histogram_device(rhj_ctx *ctx, const rhj_tuple *d_in, uint64_t n, int bits, int shift, int digit_kind,
                          uint64_t *d_hist, void *stream) {
-    if (!ctx || !d_hist || bits < 0 || bits > kMaxBitsPerPass || shift < 0 || shift > 63) return RHJ_ERR_ARG;
+    if (!ctx || !d_hist || bits < 0 || bits > kPlanBitsPerPass || shift < 0 || shift > 63) return RHJ_ERR_ARG;
     if (digit_kind != RHJ_DIGIT_RAW && digit_kind != RHJ_DIGIT_HASH) return RHJ_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = pick(ctx, stream);
@@ -615,7 +635,7 @@ static int partition_one(rhj_ctx *ctx, cudaStream_t st, const Tup *in, u64 n, in
 
 int rhj_partition_device(rhj_ctx *ctx, const rhj_tuple *d_in, uint64_t n, int bits, int shift, int digit_kind,
                          rhj_tuple *d_out, uint64_t *d_offsets, void *stream) {
-    if (!ctx || bits < 0 || bits > kMaxBitsPerPass || shift < 0 || shift > 63) return RHJ_ERR_ARG;
+    if (!ctx || bits < 0 || bits > kPlanBitsPerPass || shift < 0 || shift > 63) return RHJ_ERR_ARG;
     if (digit_kind != RHJ_DIGIT_RAW && digit_kind != RHJ_DIGIT_HASH) return RHJ_ERR_ARG;
     if (n && (!d_in || !d_out)) return fail(ctx, RHJ_ERR_ARG, "null pointer");
     CK(cudaSetDevice(ctx->device));
@@ -645,6 +665,397 @@ int rhj_shuffle_partition_device(rhj_ctx *ctx, const rhj_tuple *d_in, uint64_t n
     CK(cudaMemcpyAsync(off, ((u64 *) ctx->meta.p), (world + 1) * sizeof(u64), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     for (int r = 0; r < world; ++r) h_counts[r] = off[r + 1] - off[r];
+    return RHJ_OK;
+}
+
+// ---- multi-GPU: fused partition + shuffle over peer memory ---------------------------
+
+int rhj_shard_plan_make(uint64_t nR_global, uint64_t nS_global, int world, rhj_shard_plan *plan) {
+    if (!plan || world < 1 || world > kMaxPeers || (world & (world - 1))) return RHJ_ERR_ARG;
+    int rb = 0;
+    while ((1 << rb) < world) ++rb;
+    const u64 nB = (std::min(nR_global, nS_global) + world - 1) / world;  // expected build tuples per rank
+    int bits = 0;
+    if (nB > kBuildCap)
+        while (bits < 2 * kPlanBitsPerPass && (nB >> bits) > kTargetBuildPerPart) ++bits;
+    int b1 = std::min(kMaxBitsPerPass - rb, (bits + 1) / 2);  // balanced: the received data always gets a second pass
+    if (const char *e = getenv("RHJ_SHARD_SUBBITS")) b1 = std::max(0, std::min(std::min(atoi(e), bits), kMaxBitsPerPass - rb));
+    if (bits - b1 > kMaxBitsPerPass) bits = b1 + kMaxBitsPerPass;
+    plan->world = world;
+    plan->rank_bits = rb;
+    plan->bits_total = bits;
+    plan->bits_pass1 = b1;
+    plan->bits_pass2 = bits - b1;
+    plan->build_is_S = nS_global < nR_global;
+    return RHJ_OK;
+}
+
+static PartArgs shard_args(const rhj_shard_plan *sp) {
+    PartArgs a{};
+    a.rank_bits = sp->rank_bits;
+    a.sub_bits = sp->bits_pass1;
+    a.ndig = (u32) sp->world << sp->bits_pass1;
+    a.mask = a.ndig - 1;
+    a.shift = 0;
+    return a;
+}
+
+// Step 1: pass-1 histogram on the digit (destination rank | sub-digit) of both local shards.
+// d_hist[2][world << bits_pass1] (u64; [0] = R, [1] = S).  Enqueues only.
+int rhj_shard_histogram_device(rhj_ctx *ctx, const rhj_shard_plan *sp, const rhj_tuple *dR, uint64_t nR,
+                               const rhj_tuple *dS, uint64_t nS, uint64_t *d_hist, void *stream) {
+    if (!ctx || !sp || !d_hist) return RHJ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick(ctx, stream);
+    ctx->cur.valid = false;
+    ctx->nmarks = 0;
+    ctx->info = rhj_plan_info{};
+    Meta m;
+    int rc;
+    if ((rc = layout_meta(ctx, 1u << sp->bits_total, m))) return rc;
+    PartArgs a = shard_args(sp);
+    CK(cudaMemsetAsync(d_hist, 0, 2 * (size_t) a.ndig * sizeof(u64), st));
+    a.rel[0] = PartRel{(const Tup *) dR, nullptr, nR, (u64 *) d_hist, nullptr, nullptr, nullptr, 1, tiles_of(nR)};
+    a.rel[1] = PartRel{(const Tup *) dS, nullptr, nS, (u64 *) d_hist + a.ndig, nullptr, nullptr, nullptr, 1, tiles_of(nS)};
+    mark(ctx, st, RHJ_PHASE_HIST1);
+    if ((rc = launch_hist(ctx, st, a, kDigitShard, false))) return rc;
+    mark(ctx, st, RHJ_PHASE_SCAN1);
+    return RHJ_OK;
+}
+
+// Step 2: from the all-gathered histograms d_all_hist[world][2][world << bits_pass1], this rank's
+// write cursors inside every destination buffer and the layout of what it will receive.
+// recv_counts[2] (host; [0] = R, [1] = S) = tuples this rank receives.  Synchronises the stream.
+int rhj_shard_offsets_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rank, const uint64_t *d_all_hist,
+                             uint64_t *recv_counts, void *stream) {
+    if (!ctx || !sp || !d_all_hist || !recv_counts || rank < 0 || rank >= (int) sp->world) return RHJ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick(ctx, stream);
+    Meta m;
+    int rc;
+    if ((rc = layout_meta(ctx, 1u << sp->bits_total, m))) return rc;
+    if ((rc = ensure(ctx, ctx->filt_off, 16))) return rc;
+    ShardOffsetsArgs a{};
+    a.all_hist = (const u64 *) d_all_hist;
+    for (int i = 0; i < 2; ++i) {
+        a.cursor[i] = m.cur1[i];
+        a.off1[i] = m.off1[i];
+        a.tile0[i] = m.tile0[i];
+    }
+    a.recv_total = (u64 *) ctx->filt_off.p;
+    a.world = sp->world;
+    a.rank = (u32) rank;
+    a.sub_bits = sp->bits_pass1;
+    k_shard_offsets<<<2, kMaxDigits, 0, st>>>(a);
+    CK(cudaGetLastError());
+    ctx->info.kernel_launches++;
+    CK(cudaMemcpyAsync(ctx->h_scalars, a.recv_total, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    recv_counts[0] = ctx->h_scalars[0];
+    recv_counts[1] = ctx->h_scalars[1];
+    return RHJ_OK;
+}
+
+// Step 3: the scatter of pass 1 IS the shuffle: every tile is staged in shared memory sorted by
+// (destination rank, sub-digit) and each run is stored straight into the destination rank's
+// receive buffer (peer memory over NVLink, or local HBM for the rank itself).
+// peer_R[world] / peer_S[world] are device pointers to the ranks' receive buffers, valid in this
+// process (CUDA IPC / symmetric memory).  Enqueues only; the caller fences across ranks.
+int rhj_shard_scatter_device(rhj_ctx *ctx, const rhj_shard_plan *sp, const rhj_tuple *dR, uint64_t nR,
+                             const rhj_tuple *dS, uint64_t nS, void *const *peer_R, void *const *peer_S, void *stream) {
+    if (!ctx || !sp || !peer_R || !peer_S) return RHJ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick(ctx, stream);
+    Meta m;
+    int rc;
+    if ((rc = layout_meta(ctx, 1u << sp->bits_total, m))) return rc;
+    PartArgs a = shard_args(sp);
+    a.rel[0] = PartRel{(const Tup *) dR, nullptr, nR, nullptr, m.cur1[0], nullptr, nullptr, 1, tiles_of(nR)};
+    a.rel[1] = PartRel{(const Tup *) dS, nullptr, nS, nullptr, m.cur1[1], nullptr, nullptr, 1, tiles_of(nS)};
+    for (u32 r = 0; r < sp->world; ++r) {
+        a.peer_out[0][r] = (Tup *) peer_R[r];
+        a.peer_out[1][r] = (Tup *) peer_S[r];
+    }
+    mark(ctx, st, RHJ_PHASE_SCATTER1);
+    if ((rc = launch_scatter(ctx, st, a, kDigitShard, false))) return rc;
+    mark(ctx, st, RHJ_PHASE_HIST2);
+    return RHJ_OK;
+}
+
+// Step 4: local continuation on what this rank received (pass-1 partitioned by step 3): second
+// radix pass, build/probe, emit.  d_recvR[nR_recv] / d_recvS[nS_recv] are this rank's receive buffers.
+int rhj_shard_join_device(rhj_ctx *ctx, const rhj_shard_plan *sp, const rhj_tuple *d_recvR, uint64_t nR_recv,
+                          const rhj_tuple *d_recvS, uint64_t nS_recv, rhj_pair *d_out, uint64_t capacity,
+                          uint64_t *count, void *stream) {
+    if (!ctx || !sp || !count) return RHJ_ERR_ARG;
+    *count = 0;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick(ctx, stream);
+    if (nR_recv == 0 || nS_recv == 0) return RHJ_OK;
+    Plan pl{};
+    pl.build_is_S = sp->build_is_S;
+    pl.nB = pl.build_is_S ? nS_recv : nR_recv;
+    pl.nP = pl.build_is_S ? nR_recv : nS_recv;
+    pl.bits = sp->bits_total;
+    pl.b1 = sp->bits_pass1;
+    pl.b2 = sp->bits_pass2;
+    pl.nparts = 1u << pl.bits;
+    ctx->info.bits_total = pl.bits;
+    ctx->info.bits_pass1 = pl.b1;
+    ctx->info.bits_pass2 = pl.b2;
+    ctx->info.build_is_S = pl.build_is_S;
+    ctx->info.n_partitions = pl.nparts;
+    Meta m;
+    int rc;
+    if ((rc = layout_meta(ctx, pl.nparts, m))) return rc;
+    CK(cudaMemsetAsync(ctx->zero.p, 0, m.zero_bytes, st));
+    const int bi = pl.build_is_S ? 1 : 0;
+    const Tup *inX[2] = {(const Tup *) (bi ? d_recvS : d_recvR), (const Tup *) (bi ? d_recvR : d_recvS)};
+    const u64 *off1X[2] = {m.off1[bi], m.off1[bi ^ 1]};
+    const u32 *tile0X[2] = {m.tile0[bi], m.tile0[bi ^ 1]};
+    if ((rc = second_pass_and_plan(ctx, st, pl, m, inX, off1X, tile0X))) return rc;
+    JoinArgs j = join_args(ctx, kScWork0);
+    j.out = (Pair *) d_out;
+    j.capacity = capacity;
+    mark(ctx, st, RHJ_PHASE_JOIN);
+    if ((rc = launch_join<kJoinFused>(ctx, st, j, ctx->cur.item_cap))) return rc;
+    mark(ctx, st, -1);
+    if ((rc = read_scalars(ctx, st))) return rc;
+    *count = ctx->h_scalars[kScCursor];
+    if (*count > capacity) return fail(ctx, RHJ_ERR_CAPACITY, "output buffer too small for the fused emitter");
+    return RHJ_OK;
+}
+
+// ---- multi-GPU, DMA-shipped variant: pass 1 partitions locally on (destination rank | sub-digit) into
+// a staging buffer, the copy engines ship one contiguous chunk per destination over NVLink while the
+// SMs work on the other relation, and pass 2 consumes the received chunks as (source, partition) pieces.
+
+namespace {
+
+struct ShardMeta {
+    u64 *loc_off[2];   // [kMaxDigits + 1] source side: offsets of the (dest | p1) digits inside the staging buffer
+    u64 *seg_off[2];   // [kMaxDigits + 1] destination side: piece boundaries inside the receive buffer
+    u64 *tot;          // [kMaxPeers * kMaxPeers] ship matrix of the relation being laid out
+};
+
+int layout_shard_meta(rhj_ctx *ctx, ShardMeta &sm) {
+    size_t n = 4 * (size_t) (kMaxDigits + 1) + (size_t) kMaxPeers * kMaxPeers;
+    int rc = ensure(ctx, ctx->shard_meta, n * 8);
+    if (rc) return rc;
+    u64 *q = (u64 *) ctx->shard_meta.p;
+    for (int i = 0; i < 2; ++i) { sm.loc_off[i] = q; q += kMaxDigits + 1; }
+    for (int i = 0; i < 2; ++i) { sm.seg_off[i] = q; q += kMaxDigits + 1; }
+    sm.tot = q;
+    return RHJ_OK;
+}
+
+Plan shard_local_plan(const rhj_shard_plan *sp, u64 nR, u64 nS) {
+    Plan pl{};
+    pl.build_is_S = sp->build_is_S;
+    pl.nB = pl.build_is_S ? nS : nR;
+    pl.nP = pl.build_is_S ? nR : nS;
+    pl.bits = sp->bits_total;
+    pl.b1 = sp->bits_pass1;
+    pl.b2 = sp->bits_pass2;
+    pl.nparts = 1u << pl.bits;
+    return pl;
+}
+
+}  // namespace
+
+// Starts a sharded join on this context: sizes the metadata, zeroes the counters.  Enqueues only.
+int rhj_shardx_begin(rhj_ctx *ctx, const rhj_shard_plan *sp, void *stream) {
+    if (!ctx || !sp) return RHJ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick(ctx, stream);
+    ctx->cur.valid = false;
+    ctx->cur.counted = false;
+    ctx->nmarks = 0;
+    ctx->info = rhj_plan_info{};
+    ctx->info.bits_total = sp->bits_total;
+    ctx->info.bits_pass1 = sp->bits_pass1;
+    ctx->info.bits_pass2 = sp->bits_pass2;
+    ctx->info.build_is_S = sp->build_is_S;
+    ctx->info.n_partitions = 1u << sp->bits_total;
+    Meta m;
+    ShardMeta sm;
+    int rc;
+    if ((rc = layout_meta(ctx, 1u << sp->bits_total, m))) return rc;
+    if ((rc = layout_shard_meta(ctx, sm))) return rc;
+    CK(cudaMemsetAsync(ctx->zero.p, 0, m.zero_bytes, st));
+    ctx->shard_n[0] = ctx->shard_n[1] = 0;
+    return RHJ_OK;
+}
+
+// Pass 1 of relation `rel` (0 = R, 1 = S): histogram on (destination rank | sub-digit) into d_hist
+// [world << bits_pass1] (the caller all-gathers it), prefix sum, scatter into the local staging buffer
+// d_stage[n], which ends up ordered by destination rank, then by pass-1 partition.  Enqueues only.
+int rhj_shardx_pass1_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_in, uint64_t n,
+                            rhj_tuple *d_stage, uint64_t *d_hist, void *stream) {
+    if (!ctx || !sp || !d_hist || rel < 0 || rel > 1 || (n && (!d_in || !d_stage))) return RHJ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick(ctx, stream);
+    Meta m;
+    ShardMeta sm;
+    int rc;
+    if ((rc = layout_meta(ctx, 1u << sp->bits_total, m))) return rc;
+    if ((rc = layout_shard_meta(ctx, sm))) return rc;
+    PartArgs a = shard_args(sp);
+    a.shard_local = 1;
+    CK(cudaMemsetAsync(d_hist, 0, (size_t) a.ndig * sizeof(u64), st));
+    a.rel[0] = PartRel{(const Tup *) d_in, (Tup *) d_stage, n, (u64 *) d_hist, m.cur1[rel], nullptr, nullptr, 1, tiles_of(n)};
+    if (rel == 0) mark(ctx, st, RHJ_PHASE_HIST1);
+    if ((rc = launch_hist(ctx, st, a, kDigitShard, false))) return rc;
+    ScanDigitsArgs sd{};
+    sd.hist[0] = sd.hist[1] = (const u64 *) d_hist;
+    sd.off[0] = sd.off[1] = sm.loc_off[rel];
+    sd.cursor[0] = sd.cursor[1] = m.cur1[rel];
+    sd.tile0[0] = sd.tile0[1] = nullptr;
+    sd.ndig = a.ndig;
+    k_scan_digits<<<1, kMaxDigits, 0, st>>>(sd);
+    CK(cudaGetLastError());
+    ctx->info.kernel_launches++;
+    if ((rc = launch_scatter(ctx, st, a, kDigitShard, false))) return rc;
+    return RHJ_OK;
+}
+
+// Layout of relation `rel` from the all-gathered histograms d_all_hist[world][world << bits_pass1]:
+// device side, the piece tables pass 2 needs; host side, what to ship where:
+//   send_off[d], send_cnt[d]  this rank's chunk for destination d inside its staging buffer (tuples)
+//   dst_off[d]                where that chunk starts inside destination d's receive buffer
+//   *recv_total               tuples this rank receives
+// Synchronises the stream.
+int rhj_shardx_layout_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rank, int rel, const uint64_t *d_all_hist,
+                             uint64_t *send_off, uint64_t *send_cnt, uint64_t *dst_off, uint64_t *recv_total,
+                             void *stream) {
+    if (!ctx || !sp || !d_all_hist || !send_off || !send_cnt || !dst_off || !recv_total || rel < 0 || rel > 1 || rank < 0 ||
+        rank >= (int) sp->world)
+        return RHJ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick(ctx, stream);
+    Meta m;
+    ShardMeta sm;
+    int rc;
+    if ((rc = layout_meta(ctx, 1u << sp->bits_total, m))) return rc;
+    if ((rc = layout_shard_meta(ctx, sm))) return rc;
+    ShardLayoutArgs a{};
+    a.all_hist = (const u64 *) d_all_hist;
+    a.seg_off = sm.seg_off[rel];
+    a.seg_tile0 = m.tile0[rel];
+    a.off1 = m.off1[rel];
+    a.tot = sm.tot;
+    a.world = sp->world;
+    a.rank = (u32) rank;
+    a.sub_bits = sp->bits_pass1;
+    k_shard_layout<<<1, 1024, 0, st>>>(a);
+    CK(cudaGetLastError());
+    ctx->info.kernel_launches++;
+    const u32 W = sp->world, nd1 = 1u << sp->bits_pass1;
+    static thread_local u64 h_tot[kMaxPeers * kMaxPeers], h_loc[kMaxDigits + 1];
+    CK(cudaMemcpyAsync(h_tot, sm.tot, (size_t) W * W * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_loc, sm.loc_off[rel], ((size_t) (W << sp->bits_pass1) + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    u64 total = 0;
+    for (u32 d = 0; d < W; ++d) {
+        send_off[d] = h_loc[(size_t) d * nd1];
+        send_cnt[d] = h_loc[(size_t) (d + 1) * nd1] - h_loc[(size_t) d * nd1];
+        u64 before = 0;
+        for (u32 s2 = 0; s2 < (u32) rank; ++s2) before += h_tot[s2 * W + d];
+        dst_off[d] = before;
+        total += h_tot[d * W + rank];
+    }
+    *recv_total = total;
+    ctx->shard_n[rel] = total;
+    return RHJ_OK;
+}
+
+// Pass 2 of relation `rel` over what this rank received (d_recv[n_recv], world << bits_pass1 pieces):
+// histogram, per-partition offsets, scatter into the context's final partition buffer.  Enqueues only.
+int rhj_shardx_pass2_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_recv, uint64_t n_recv,
+                            void *stream) {
+    if (!ctx || !sp || rel < 0 || rel > 1 || (n_recv && !d_recv)) return RHJ_ERR_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick(ctx, stream);
+    Meta m;
+    ShardMeta sm;
+    int rc;
+    if ((rc = layout_meta(ctx, 1u << sp->bits_total, m))) return rc;
+    if ((rc = layout_shard_meta(ctx, sm))) return rc;
+    ctx->shard_recv[rel] = (const Tup *) d_recv;
+    DevBuf &out = rel ? ctx->bufB2 : ctx->bufB;
+    if ((rc = ensure(ctx, out, std::max<u64>(n_recv, 1) * sizeof(Tup)))) return rc;
+    const u32 nd1 = 1u << sp->bits_pass1, npieces = sp->world << sp->bits_pass1;
+    PartArgs b{};
+    // bits_pass2 == 0 (tiny relations): a one-digit pass that only merges the pieces of a partition
+    b.shift = std::min(31, 32 - (int) sp->bits_total);
+    b.mask = (1u << sp->bits_pass2) - 1;
+    b.ndig = 1u << sp->bits_pass2;
+    b.rel[0] = PartRel{(const Tup *) d_recv, (Tup *) out.p, n_recv, m.hist2[rel], m.cur2[rel], sm.seg_off[rel], m.tile0[rel],
+                       npieces, tiles_of(n_recv) + npieces, nd1 - 1};
+    if (nd1 == 1) b.rel[0].group_mask = 0x80000000u;  // every piece is partition 0: (seg & mask) == 0
+    if (rel == 0) mark(ctx, st, RHJ_PHASE_HIST2);
+    if ((rc = launch_hist(ctx, st, b, kDigitHash, true))) return rc;
+    ScanPartsRelArgs sr{};
+    sr.hist2 = m.hist2[rel];
+    sr.off1 = m.off1[rel];
+    sr.off2 = m.off2[rel];
+    sr.cursor2 = m.cur2[rel];
+    sr.nseg = nd1;
+    sr.ndig = b.ndig;
+    k_scan_parts_rel<<<nd1, kMaxDigits, 0, st>>>(sr);
+    CK(cudaGetLastError());
+    ctx->info.kernel_launches++;
+    if ((rc = launch_scatter(ctx, st, b, kDigitHash, true))) return rc;
+    return RHJ_OK;
+}
+
+// Work-item plan + build/probe + fused emit over the final partitions of both relations.
+int rhj_shardx_join_device(rhj_ctx *ctx, const rhj_shard_plan *sp, rhj_pair *d_out, uint64_t capacity, uint64_t *count,
+                           void *stream) {
+    if (!ctx || !sp || !count) return RHJ_ERR_ARG;
+    *count = 0;
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = pick(ctx, stream);
+    const u64 nR = ctx->shard_n[0], nS = ctx->shard_n[1];
+    if (nR == 0 || nS == 0) return RHJ_OK;
+    Plan pl = shard_local_plan(sp, nR, nS);
+    Meta m;
+    int rc;
+    if ((rc = layout_meta(ctx, pl.nparts, m))) return rc;
+    const int bi = pl.build_is_S ? 1 : 0;
+    u64 cap64 = (u64) pl.nparts + pl.nP / kProbeChunk + 2;
+    if (cap64 > 0x7fffffffull) return fail(ctx, RHJ_ERR_ARG, "relation too large for the work-item table");
+    u32 item_cap = (u32) cap64;
+    if ((rc = ensure(ctx, ctx->items, (size_t) item_cap * sizeof(Item)))) return rc;
+    mark(ctx, st, RHJ_PHASE_PLAN);
+    PlanPartsArgs pa{};
+    pa.offB = m.off2[bi];
+    pa.offP = m.off2[bi ^ 1];
+    pa.ndig = std::min<u32>(pl.nparts, kMaxDigits);
+    pa.items = (Item *) ctx->items.p;
+    pa.item_cap = item_cap;
+    pa.nitems = (u32 *) (m.scalars + kScNItems);
+    pa.err = (u32 *) (m.scalars + kScErr);
+    k_plan_parts<<<pl.nparts / pa.ndig, kMaxDigits, 0, st>>>(pa);
+    CK(cudaGetLastError());
+    ctx->info.kernel_launches++;
+    ctx->cur.valid = true;
+    ctx->cur.build = (const Tup *) (bi ? ctx->bufB2.p : ctx->bufB.p);
+    ctx->cur.probe = (const Tup *) (bi ? ctx->bufB.p : ctx->bufB2.p);
+    ctx->cur.offB = m.off2[bi];
+    ctx->cur.offP = m.off2[bi ^ 1];
+    ctx->cur.nparts = pl.nparts;
+    ctx->cur.item_cap = item_cap;
+    ctx->cur.build_is_S = pl.build_is_S;
+    JoinArgs j = join_args(ctx, kScWork0);
+    j.out = (Pair *) d_out;
+    j.capacity = capacity;
+    mark(ctx, st, RHJ_PHASE_JOIN);
+    if ((rc = launch_join<kJoinFused>(ctx, st, j, item_cap))) return rc;
+    mark(ctx, st, -1);
+    if ((rc = read_scalars(ctx, st))) return rc;
+    *count = ctx->h_scalars[kScCursor];
+    if (*count > capacity) return fail(ctx, RHJ_ERR_CAPACITY, "output buffer too small for the fused emitter");
     return RHJ_OK;
 }
 

@@ -30,17 +30,13 @@ namespace rhj {
 constexpr int kPartThreads = RHJ_PART_THREADS;  // threads per partition CTA
 constexpr int kPartItems = RHJ_PART_ITEMS;      // tuples per thread
 constexpr int kTile = kPartThreads * kPartItems;  // 4096 tuples = 64 KiB staged per CTA
-constexpr int kMaxBitsPerPass = 9;
-constexpr int kMaxDigits = 1 << kMaxBitsPerPass;  // 512 digits per pass
+constexpr int kMaxBitsPerPass = 10;               // a pass can fan out to 1024 digits (sharded pass 1: rank | sub-digit)
+constexpr int kMaxDigits = 1 << kMaxBitsPerPass;
+constexpr int kPlanBitsPerPass = 9;               // single-GPU plans use <= 512 digits per pass (longer runs)
+constexpr int kMaxPeers = 16;                     // ranks of the fused partition + shuffle pass
 
-enum DigitKind { kDigitRaw = 0, kDigitHash = 1, kDigitRank = 2 };
-
-template <int KIND>
-__device__ __forceinline__ u32 digit(u64 v, int shift, u32 mask) {
-    if (KIND == kDigitRaw) return (u32) (v >> shift) & mask;
-    if (KIND == kDigitHash) return (hash32(v) >> shift) & mask;
-    return (hash_hi32(v) >> shift) & mask;
-}
+// kDigitShard = (destination rank << sub_bits) | pass-1 digit: one pass both shuffles and partitions
+enum DigitKind { kDigitRaw = 0, kDigitHash = 1, kDigitRank = 2, kDigitShard = 3 };
 
 // ---- (1)+(3): descriptors of a partition pass over up to two relations at once ---------------
 struct PartRel {
@@ -53,13 +49,31 @@ struct PartRel {
     const u32 *seg_tile0;  // SEG: [nseg+1] first tile of each segment
     u32 nseg;
     u32 ntiles;            // tiles of this relation (SEG: host-side upper bound)
+    u32 group_mask;        // SEG: segments that share counters: group = seg & group_mask (0 = every segment
+                           // is its own group).  Sharded pass 2: segment = (source rank, pass-1 partition).
 };
+__device__ __forceinline__ u32 seg_group(const PartRel &r, u32 seg) { return r.group_mask ? (seg & r.group_mask) : seg; }
 struct PartArgs {
     PartRel rel[2];
     int shift;
     u32 mask;
     u32 ndig;
+    int rank_bits;                  // kDigitShard: log2(world)
+    int sub_bits;                   // kDigitShard: bits of the pass-1 digit below the rank
+    Tup *peer_out[2][kMaxPeers];    // kDigitShard: per relation, the destination ranks' receive buffers (peer memory)
+    int shard_local;                // kDigitShard: 1 = write to rel.out (local staging, shipped by DMA afterwards)
 };
+
+template <int KIND>
+__device__ __forceinline__ u32 digit(u64 v, const PartArgs &a) {
+    if (KIND == kDigitRaw) return (u32) (v >> a.shift) & a.mask;
+    if (KIND == kDigitHash) return (hash32(v) >> a.shift) & a.mask;
+    if (KIND == kDigitRank) return (hash_hi32(v) >> a.shift) & a.mask;
+    const u64 h = hash64(v);
+    const u32 rank = a.rank_bits ? (u32) (h >> (64 - a.rank_bits)) : 0u;
+    const u32 sub = a.sub_bits ? ((u32) h >> (32 - a.sub_bits)) : 0u;
+    return (rank << a.sub_bits) | sub;
+}
 
 // Maps a relation-local tile index to its tuple range.  SEG tiles never straddle a segment.
 template <bool SEG>
@@ -106,7 +120,7 @@ __global__ void __launch_bounds__(kPartThreads) k_hist(PartArgs a) {
         if (!tile_range<SEG>(r, t - (ri ? a.rel[0].ntiles : 0), seg, beg, end)) continue;
         if (cur_rel >= 0 && (ri != cur_rel || seg != cur_seg)) {
             __syncthreads();
-            u64 *h = a.rel[cur_rel].hist + (u64) cur_seg * a.ndig;
+            u64 *h = a.rel[cur_rel].hist + (u64) seg_group(a.rel[cur_rel], cur_seg) * a.ndig;
             for (u32 d = tid; d < a.ndig; d += kPartThreads) {
                 u32 c = s_h[d];
                 if (c) { atomicAdd(h + d, (u64) c); s_h[d] = 0; }
@@ -125,7 +139,7 @@ __global__ void __launch_bounds__(kPartThreads) k_hist(PartArgs a) {
         }
 #pragma unroll
         for (int j = 0; j < kPartItems; ++j) {
-            u32 d = ok[j] ? digit<KIND>(v[j].val, a.shift, a.mask) : kEmpty;
+            u32 d = ok[j] ? digit<KIND>(v[j].val, a) : kEmpty;
             if (AGG) {
                 u32 peers = __match_any_sync(0xffffffffu, d);
                 if (ok[j] && lane_id() == (u32) (__ffs(peers) - 1)) atomicAdd(&s_h[d], (u32) __popc(peers));
@@ -136,7 +150,7 @@ __global__ void __launch_bounds__(kPartThreads) k_hist(PartArgs a) {
     }
     __syncthreads();
     if (cur_rel >= 0) {
-        u64 *h = a.rel[cur_rel].hist + (u64) cur_seg * a.ndig;
+        u64 *h = a.rel[cur_rel].hist + (u64) seg_group(a.rel[cur_rel], cur_seg) * a.ndig;
         for (u32 d = tid; d < a.ndig; d += kPartThreads) {
             u32 c = s_h[d];
             if (c) atomicAdd(h + d, (u64) c);
@@ -262,7 +276,7 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
     for (int j = 0; j < kPartItems; ++j) {
         u32 i = j * kPartThreads + tid;
         if (i < ntile) {
-            u32 d = digit<KIND>(v[j].val, a.shift, a.mask);
+            u32 d = digit<KIND>(v[j].val, a);
             u32 rk = atomicAdd(&s_cnt[d], 1u);
             dr[j] = (d << 16) | rk;
         }
@@ -279,7 +293,7 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
         u32 d = tid * kDigitsPerThread + k;
         c[k] = d < a.ndig ? s_cnt[d] : 0;
         g[k] = 0;
-        if (c[k]) g[k] = atomicAdd(r.cursor + (u64) seg * a.ndig + d, (u64) c[k]);
+        if (c[k]) g[k] = atomicAdd(r.cursor + (u64) seg_group(r, seg) * a.ndig + d, (u64) c[k]);
         csum += c[k];
     }
     u32 inc = warp_incl_scan(csum);
@@ -315,7 +329,8 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
         __syncthreads();
         for (u32 d = tid; d < a.ndig; d += kPartThreads) {
             u32 cd = s_cnt[d];
-            if (cd) bulk_s2g(r.out + s_delta[d] + s_off[d], s_tup + s_off[d], cd * (u32) sizeof(Tup));
+            Tup *ob = (KIND == kDigitShard && !a.shard_local) ? a.peer_out[ri][d >> a.sub_bits] : r.out;
+            if (cd) bulk_s2g(ob + s_delta[d] + s_off[d], s_tup + s_off[d], cd * (u32) sizeof(Tup));
         }
         bulk_commit();
         bulk_wait_read0();
@@ -326,11 +341,75 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
             u32 i = j * kPartThreads + tid;
             if (i < ntile) {
                 Tup t = s_tup[i];
-                u32 d = digit<KIND>(t.val, a.shift, a.mask);
-                st_stream(r.out + s_delta[d] + i, t);
+                u32 d = digit<KIND>(t.val, a);
+                Tup *ob = (KIND == kDigitShard && !a.shard_local) ? a.peer_out[ri][d >> a.sub_bits] : r.out;
+                st_stream(ob + s_delta[d] + i, t);
             }
         }
     }
+    }
+}
+
+// Fused partition + shuffle bookkeeping.  all_hist[src][rel][dest << sub_bits | p1] are the pass-1
+// histograms of every rank (all-gathered).  For relation `rel` (one CTA each) this rank gets
+//   - as a DESTINATION: off1[p1] / tile table of what it will receive (pass-1 partition p1 holds
+//     the runs of all sources, source-major), and the received total;
+//   - as a SOURCE: its private write cursor inside every destination's partition p1
+//     (= that destination's off1[p1] + what lower-ranked sources put there), so the scatter needs
+//     no cross-GPU atomics.
+struct ShardOffsetsArgs {
+    const u64 *all_hist;   // [world][2][world << sub_bits]
+    u64 *cursor[2];        // [world << sub_bits] source-side cursors
+    u64 *off1[2];          // [(1 << sub_bits) + 1] destination-side pass-1 offsets
+    u32 *tile0[2];         // [(1 << sub_bits) + 1] first pass-2 tile of each pass-1 partition
+    u64 *recv_total;       // [2]
+    u32 world, rank;
+    int sub_bits;
+};
+__global__ void __launch_bounds__(kMaxDigits) k_shard_offsets(ShardOffsetsArgs a) {
+    __shared__ u64 s_w[32];
+    __shared__ u32 s_wt[32];
+    const int rel = blockIdx.x;
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 nd1 = 1u << a.sub_bits, ndig = a.world << a.sub_bits;
+    for (u32 dest = 0; dest < a.world; ++dest) {
+        u64 tot = 0, before_me = 0;   // over sources, for (dest, p1 = tid)
+        if (tid < nd1) {
+            for (u32 src = 0; src < a.world; ++src) {
+                u64 c = a.all_hist[((u64) src * 2 + rel) * ndig + (dest << a.sub_bits) + tid];
+                if (src < a.rank) before_me += c;
+                tot += c;
+            }
+        }
+        u32 tl = (u32) ((tot + kTile - 1) / kTile);
+        u64 inc = warp_incl_scan64(tot);
+        u32 tinc = warp_incl_scan(tl);
+        if (lane == 31) { s_w[warp] = inc; s_wt[warp] = tinc; }
+        __syncthreads();
+        if (warp == 0) {
+            u64 w = s_w[lane];
+            u32 wt = s_wt[lane];
+            u64 wi = warp_incl_scan64(w);
+            u32 wti = warp_incl_scan(wt);
+            s_w[lane] = wi - w;
+            s_wt[lane] = wti - wt;
+        }
+        __syncthreads();
+        u64 ex = inc - tot + s_w[warp];
+        u32 tex = tinc - tl + s_wt[warp];
+        if (tid < nd1) {
+            a.cursor[rel][(dest << a.sub_bits) + tid] = ex + before_me;
+            if (dest == a.rank) {
+                a.off1[rel][tid] = ex;
+                a.tile0[rel][tid] = tex;
+                if (tid == nd1 - 1) {
+                    a.off1[rel][nd1] = ex + tot;
+                    a.tile0[rel][nd1] = tex + tl;
+                    a.recv_total[rel] = ex + tot;
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -440,6 +519,138 @@ __global__ void __launch_bounds__(kMaxDigits) k_scan_parts_plan(ScanPlanArgs a) 
     __syncthreads();
     u32 at = s_base + inc - k + s_w32[warp];
     for (u32 ch = 0; ch < k; ++ch) {
+        if (at + ch < a.item_cap) a.items[at + ch] = Item{p, ch};
+        else *a.err = 1;
+    }
+}
+
+// block-wide exclusive scans for 1024-thread CTAs (one element per thread)
+__device__ __forceinline__ u64 block_excl_scan64(u64 v, u64 *s_w, u64 *total) {
+    const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 inc = warp_incl_scan64(v);
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        u64 w = s_w[lane];
+        u64 wi = warp_incl_scan64(w);
+        s_w[lane] = wi - w;
+        if (lane == 31) s_w[32] = wi;
+    }
+    __syncthreads();
+    u64 ex = inc - v + s_w[warp];
+    if (total) *total = s_w[32];
+    __syncthreads();
+    return ex;
+}
+
+// Receive-side layout of the DMA-shipped sharded join, for ONE relation.  all_hist[src][dest <<
+// sub_bits | p1] = pass-1 histograms of every rank.  Every source ships to this rank one
+// contiguous chunk that is already partitioned by p1, so the receive buffer is [src0: p1 = 0..][src1:
+// ...]: world << sub_bits contiguous PIECES.  Pass 2 treats each piece as a segment whose counters are
+// shared per p1 (group = piece & (2^sub_bits - 1)).
+//   seg_off / seg_tile0 [world << sub_bits | +1]   piece boundaries / first pass-2 tile
+//   off1 [2^sub_bits + 1]                           pass-1 partition sizes summed over sources (prefix)
+//   tot [world * world]                             tot[src * world + dest] = tuples src ships to dest
+struct ShardLayoutArgs {
+    const u64 *all_hist;  // [world][world << sub_bits]
+    u64 *seg_off;
+    u32 *seg_tile0;
+    u64 *off1;
+    u64 *tot;
+    u32 world, rank;
+    int sub_bits;
+};
+__global__ void __launch_bounds__(1024) k_shard_layout(ShardLayoutArgs a) {
+    __shared__ u64 s_w[33];
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 nd1 = 1u << a.sub_bits, ndig = a.world << a.sub_bits;
+    // tot[src][dest]
+    for (u32 pr = warp; pr < a.world * a.world; pr += 32) {
+        const u32 src = pr / a.world, dest = pr % a.world;
+        u64 c = 0;
+        for (u32 p = lane; p < nd1; p += 32) c += a.all_hist[(u64) src * ndig + (dest << a.sub_bits) + p];
+        c = warp_sum64(c);
+        if (lane == 0) a.tot[pr] = c;
+    }
+    // pieces this rank receives, in (src, p1) order
+    const u32 nseg = ndig;  // world * nd1
+    u64 cnt = 0;
+    if (tid < nseg) {
+        const u32 src = tid >> a.sub_bits, p1 = tid & (nd1 - 1);
+        cnt = a.all_hist[(u64) src * ndig + (a.rank << a.sub_bits) + p1];
+    }
+    u64 total;
+    u64 ex = block_excl_scan64(cnt, s_w, &total);
+    u64 tl = (cnt + kTile - 1) / kTile, ttotal;
+    u64 tex = block_excl_scan64(tl, s_w, &ttotal);
+    if (tid < nseg) {
+        a.seg_off[tid] = ex;
+        a.seg_tile0[tid] = (u32) tex;
+        if (tid == nseg - 1) {
+            a.seg_off[nseg] = total;
+            a.seg_tile0[nseg] = (u32) ttotal;
+        }
+    }
+    // pass-1 partitions summed over sources
+    u64 g = 0;
+    if (tid < nd1)
+        for (u32 src = 0; src < a.world; ++src) g += a.all_hist[(u64) src * ndig + (a.rank << a.sub_bits) + tid];
+    u64 gex = block_excl_scan64(g, s_w, &total);
+    if (tid < nd1) {
+        a.off1[tid] = gex;
+        if (tid == nd1 - 1) a.off1[nd1] = total;
+    }
+}
+
+// (2b'') per-relation half of k_scan_parts_plan: offsets + cursors of one relation's 2^b2
+// sub-partitions per pass-1 partition (one CTA each), so that a relation whose data has arrived can
+// run its second pass while the other relation is still in flight.
+struct ScanPartsRelArgs {
+    const u64 *hist2;  // [nseg * ndig]
+    const u64 *off1;   // [nseg + 1]
+    u64 *off2;         // [nseg * ndig + 1]
+    u64 *cursor2;      // [nseg * ndig]
+    u32 nseg, ndig;
+};
+__global__ void __launch_bounds__(kMaxDigits) k_scan_parts_rel(ScanPartsRelArgs a) {
+    __shared__ u64 s_w[33];
+    const u32 seg = blockIdx.x, tid = threadIdx.x;
+    const u32 p = seg * a.ndig + tid;
+    u64 c = tid < a.ndig ? a.hist2[p] : 0;
+    u64 ex = block_excl_scan64(c, s_w, nullptr);
+    if (tid < a.ndig) {
+        u64 off = a.off1[seg] + ex;
+        a.off2[p] = off;
+        a.cursor2[p] = off;
+        if (seg == a.nseg - 1 && tid == a.ndig - 1) a.off2[p + 1] = off + c;
+    }
+}
+// ... and the planning half: work items of every final partition from both relations' offsets
+struct PlanPartsArgs {
+    const u64 *offB;
+    const u64 *offP;
+    u32 ndig;  // partitions per CTA
+    Item *items;
+    u32 item_cap;
+    u32 *nitems;
+    u32 *err;
+};
+__global__ void __launch_bounds__(kMaxDigits) k_plan_parts(PlanPartsArgs a) {
+    __shared__ u64 s_w[33];
+    __shared__ u32 s_base;
+    const u32 tid = threadIdx.x;
+    const u32 p = blockIdx.x * a.ndig + tid;
+    u64 k = 0;
+    if (tid < a.ndig) {
+        u64 nb = a.offB[p + 1] - a.offB[p], np = a.offP[p + 1] - a.offP[p];
+        if (nb && np) k = (np + kProbeChunk - 1) / kProbeChunk;
+    }
+    u64 total;
+    u64 ex = block_excl_scan64(k, s_w, &total);
+    if (tid == 0) s_base = total ? atomicAdd(a.nitems, (u32) total) : 0;
+    __syncthreads();
+    u32 at = s_base + (u32) ex;
+    for (u32 ch = 0; ch < (u32) k; ++ch) {
         if (at + ch < a.item_cap) a.items[at + ch] = Item{p, ch};
         else *a.err = 1;
     }

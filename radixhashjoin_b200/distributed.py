@@ -100,3 +100,157 @@ def cpu_partition_by_rank(T, world):
     order = np.argsort(ranks, kind="stable")
     counts = np.bincount(ranks, minlength=world).tolist()
     return torch.from_numpy(a[order].view(np.int64).copy()), counts
+
+
+class FusedShardedJoin:
+    """Multi-GPU join with the exchange FUSED into pass 1 (rhj_shard_* in include/rhj.h).
+
+    Every rank owns two receive buffers in symmetric (peer-mapped) memory.  Pass 1 of the join
+    partitions on (destination rank | sub-digit) and its scatter kernel stores each run directly
+    into the destination's receive buffer over NVLink / NVSwitch -- no separate shuffle pass, no
+    staging copy, and the transfer overlaps the scatter tile by tile.  torch.distributed supplies
+    the plumbing: one all-gather of the 2 x (world << bits) histograms, symmetric-memory rendezvous
+    for the peer pointers, and two device-side barriers per join.
+    """
+
+    def __init__(self, engine, world, rank, nR_global, nS_global, recv_capacity, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.torch, self.dist = torch, dist
+        self.engine, self.world, self.rank = engine, world, rank
+        self.group = group if group is not None else dist.group.WORLD
+        self.plan = engine.shard_plan(nR_global, nS_global, world)
+        dev = torch.device("cuda", engine.device)
+        self.recvR = symm_mem.empty((recv_capacity, 2), dtype=torch.int64, device=dev)
+        self.recvS = symm_mem.empty((recv_capacity, 2), dtype=torch.int64, device=dev)
+        self.hR = symm_mem.rendezvous(self.recvR, self.group)
+        self.hS = symm_mem.rendezvous(self.recvS, self.group)
+        self.peers_R = [int(p) for p in self.hR.buffer_ptrs]
+        self.peers_S = [int(p) for p in self.hS.buffer_ptrs]
+        ndig = world << self.plan.bits_pass1
+        self.hist = torch.empty((2, ndig), dtype=torch.int64, device=dev)
+        self.all_hist = torch.empty((world, 2, ndig), dtype=torch.int64, device=dev)
+        self.capacity = recv_capacity
+
+    def step(self, R_local, S_local, out):
+        """One sharded join; returns (pairs, count, (received nR, nS))."""
+        eng, plan = self.engine, self.plan
+        eng.shard_histogram(plan, R_local, S_local, self.hist)
+        self.dist.all_gather_into_tensor(self.all_hist, self.hist, group=self.group)
+        nR, nS = eng.shard_offsets(plan, self.rank, self.all_hist)
+        if max(nR, nS) > self.capacity:
+            raise RuntimeError(f"rank {self.rank}: receive buffer too small ({max(nR, nS)} > {self.capacity})")
+        self.hR.barrier(channel=0)       # every rank is done reading its receive buffers (previous join)
+        eng.shard_scatter(plan, R_local, S_local, self.peers_R, self.peers_S)
+        self.hR.barrier(channel=1)       # every rank's stores have landed
+        pairs, count = eng.shard_join(plan, self.recvR[:nR], self.recvS[:nS], out)
+        return pairs, count, (nR, nS)
+
+
+class DmaShardedJoin:
+    """Multi-GPU join, DMA-shipped (rhj_shardx_* in include/rhj.h): the default at N > 1.
+
+    Pass 1 of the join partitions each local shard on (destination rank | sub-digit) into a local
+    staging buffer; the chunk for every destination is contiguous and already pass-1 partitioned, so
+    the copy engines ship it with ONE peer copy per destination over NVLink / NVSwitch (full-size
+    packets, no SM time) straight into the destination's symmetric receive buffer.  Relation S is
+    partitioned while R is in flight, and R's second pass runs while S is in flight; the join kernel
+    starts when S's second pass is done.  torch.distributed supplies the plumbing: two small
+    all-gathers (histograms), symmetric-memory rendezvous for the peer buffers, device-side barriers.
+    """
+
+    def __init__(self, engine, world, rank, nR_global, nS_global, n_local_max, recv_capacity, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.torch, self.dist = torch, dist
+        self.engine, self.world, self.rank = engine, world, rank
+        self.group = group if group is not None else dist.group.WORLD
+        self.plan = engine.shard_plan(nR_global, nS_global, world)
+        dev = torch.device("cuda", engine.device)
+        self.recv = [symm_mem.empty((recv_capacity, 2), dtype=torch.int64, device=dev) for _ in range(2)]
+        self.hdl = [symm_mem.rendezvous(t, self.group) for t in self.recv]
+        self.peer = [[h.get_buffer(p, (recv_capacity, 2), torch.int64) for p in range(world)] for h in self.hdl]
+        self.stage = [torch.empty((n_local_max, 2), dtype=torch.int64, device=dev) for _ in range(2)]
+        ndig = world << self.plan.bits_pass1
+        self.hist = [torch.empty(ndig, dtype=torch.int64, device=dev) for _ in range(2)]
+        self.all_hist = [torch.empty((world, ndig), dtype=torch.int64, device=dev) for _ in range(2)]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        # a few copy lanes: the peer copies of a relation run on different copy engines (measured on
+        # 8 x B200: 1 lane 10.9 ms/join, 8 lanes 14.6 ms -- too many concurrent flows through the switch)
+        import os
+        lanes = int(os.environ.get("RHJ_COPY_LANES", "2"))
+        self.peer_streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(world, lanes)))]
+        self.capacity = recv_capacity
+
+    def _ship(self, rel, lay, marks=None):
+        """peer copies of relation rel on the copy stream, fenced by device-side barriers"""
+        torch = self.torch
+        send_off, send_cnt, dst_off, _ = lay
+        cs = self.copy_stream
+        cs.wait_stream(torch.cuda.current_stream())        # the staging buffer is complete
+        with torch.cuda.stream(cs):
+            self.hdl[rel].barrier(channel=0)                 # every rank is done with this receive buffer
+            if marks is not None:
+                marks.append((f"dma{rel}_start", self._mark(cs)))
+            fork = torch.cuda.Event()
+            fork.record(cs)
+            for k in range(1, self.world + 1):
+                d = (self.rank + k) % self.world             # remote chunks first, staggered; own chunk last
+                if send_cnt[d]:
+                    ps = self.peer_streams[k % len(self.peer_streams)]
+                    ps.wait_event(fork)
+                    with torch.cuda.stream(ps):
+                        self.peer[rel][d][dst_off[d]:dst_off[d] + send_cnt[d]].copy_(
+                            self.stage[rel][send_off[d]:send_off[d] + send_cnt[d]], non_blocking=True)
+                    cs.wait_stream(ps)
+            if marks is not None:
+                marks.append((f"dma{rel}_sent", self._mark(cs)))
+            self.hdl[rel].barrier(channel=1)                 # every rank's copies have landed
+            done = torch.cuda.Event(enable_timing=marks is not None)
+            done.record(cs)
+            if marks is not None:
+                marks.append((f"dma{rel}_landed", done))
+        return done
+
+    def _mark(self, stream=None):
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record(stream if stream is not None else self.torch.cuda.current_stream())
+        return ev
+
+    def step(self, R_local, S_local, out, marks=None):
+        """One sharded join; returns (pairs, count, (received nR, nS)).  `marks` (a list) collects
+        (label, CUDA event) pairs for a timeline of the step."""
+        torch, eng, plan = self.torch, self.engine, self.plan
+        rels = (R_local, S_local)
+        if marks is not None:
+            marks.append(("start", self._mark()))
+        eng.shardx_begin(plan)
+        lay, landed = [None, None], [None, None]
+        for rel in (0, 1):
+            eng.shardx_pass1(plan, rel, rels[rel], self.stage[rel], self.hist[rel])
+            if marks is not None:
+                marks.append((f"pass1_{rel}_done", self._mark()))
+            self.dist.all_gather_into_tensor(self.all_hist[rel], self.hist[rel], group=self.group)
+            lay[rel] = eng.shardx_layout(plan, self.rank, rel, self.all_hist[rel])
+            if marks is not None:
+                marks.append((f"layout_{rel}_done", self._mark()))
+            if lay[rel][3] > self.capacity:
+                raise RuntimeError(f"rank {self.rank}: receive buffer too small ({lay[rel][3]} > {self.capacity})")
+            landed[rel] = self._ship(rel, lay[rel], marks)   # in flight while the next relation is partitioned
+        for rel in (0, 1):
+            torch.cuda.current_stream().wait_event(landed[rel])
+            eng.shardx_pass2(plan, rel, self.recv[rel][:lay[rel][3]])   # R's second pass overlaps S's transfer
+            if marks is not None:
+                marks.append((f"pass2_{rel}_done", self._mark()))
+        pairs, count = eng.shardx_join(plan, out)
+        if marks is not None:
+            marks.append(("join_done", self._mark()))
+        return pairs, count, (lay[0][3], lay[1][3])
+
+    @staticmethod
+    def timeline(marks):
+        """[(label, ms since 'start')] from the events a profiled step collected (after a synchronize)."""
+        t0 = marks[0][1]
+        return [(name, round(t0.elapsed_time(ev), 3)) for name, ev in marks]

@@ -362,3 +362,90 @@ def test_reference_program_with_dropin_translation_units(small_dir):
     out = subprocess.run([os.path.join(HOST_BIN, "join_b200_full")], input=data, cwd=cwd, capture_output=True, timeout=600)
     assert out.returncode == 0, out.stderr.decode()[-2000:]
     assert out.stdout.decode() == open(os.path.join(small_dir, "small.result")).read()
+
+
+# ---- multi-GPU fused partition + shuffle, emulated on one GPU ---------------------------------------------
+@pytest.mark.parametrize("world,n_local,dom", [(1, 50000, 20000), (2, 60000, 50000), (4, 40000, 1 << 40), (8, 300000, 1 << 20),
+                                               (8, 700, 300)])
+def test_fused_shard_join_emulated_ranks(world, n_local, dom):
+    """rhj_shard_*: every virtual rank (its own context and receive buffers, all on cuda:0) runs the
+    fused sequence; the union of the per-rank results must equal the oracle join of the global
+    relations, and every received tuple must belong to its rank."""
+    from radixhashjoin_b200 import RadixHashJoin
+    from radixhashjoin_b200.distributed import rank_of_values
+    rng = np.random.default_rng(world * 1000 + n_local)
+    Rg, Sg = rand_rel(rng, world * n_local, dom), rand_rel(rng, world * n_local, dom, 1 << 35)
+    expect = O.sort_pairs(O.oracle_join(Rg, Sg))
+    engines = [RadixHashJoin(0) for _ in range(world)]
+    shards = [(to_dev(Rg[r * n_local:(r + 1) * n_local]), to_dev(Sg[r * n_local:(r + 1) * n_local])) for r in range(world)]
+    plan = engines[0].shard_plan(len(Rg), len(Sg), world)
+    hists = torch.stack([engines[r].shard_histogram(plan, *shards[r]) for r in range(world)])   # the all-gather
+    recv = [engines[r].shard_offsets(plan, r, hists) for r in range(world)]
+    assert sum(n for n, _ in recv) == len(Rg) and sum(n for _, n in recv) == len(Sg)
+    bufR = [torch.empty((max(n, 1), 2), dtype=torch.int64, device=DEV) for n, _ in recv]
+    bufS = [torch.empty((max(n, 1), 2), dtype=torch.int64, device=DEV) for _, n in recv]
+    for r in range(world):                                                                         # barrier; scatter
+        engines[r].shard_scatter(plan, *shards[r], [b.data_ptr() for b in bufR], [b.data_ptr() for b in bufS])
+    torch.cuda.synchronize()                                                                       # barrier
+    got = []
+    for r in range(world):
+        nR, nS = recv[r]
+        myR, myS = tuples_np(bufR[r][:nR]), tuples_np(bufS[r][:nS])
+        assert (rank_of_values(myR["payload"], world) == r).all() and (rank_of_values(myS["payload"], world) == r).all()
+        out = torch.empty((max(len(expect), 1), 2), dtype=torch.int64, device=DEV)
+        pairs, n = engines[r].shard_join(plan, bufR[r][:nR], bufS[r][:nS], out)
+        got.append(pairs_np(pairs))
+    got = np.concatenate(got)
+    assert len(got) == len(expect)
+    assert np.array_equal(O.sort_pairs(got), expect)
+    for e in engines:
+        e.close()
+
+
+@pytest.mark.parametrize("world,n_local,dom", [(1, 50000, 20000), (2, 60000, 50000), (4, 40000, 1 << 40), (8, 300000, 1 << 20),
+                                               (4, 500, 200), (2, 3000, 1000)])
+def test_dma_shard_join_emulated_ranks(world, n_local, dom):
+    """rhj_shardx_*: pass 1 into local staging, chunks copied to the destinations (tensor copies stand
+    in for the peer DMA), pass 2 over (source, partition) pieces, join.  Union == oracle."""
+    from radixhashjoin_b200 import RadixHashJoin
+    from radixhashjoin_b200.distributed import rank_of_values
+    rng = np.random.default_rng(world * 77 + n_local)
+    Rg, Sg = rand_rel(rng, world * n_local, dom), rand_rel(rng, world * n_local, dom, 1 << 35)
+    expect = O.sort_pairs(O.oracle_join(Rg, Sg))
+    engines = [RadixHashJoin(0) for _ in range(world)]
+    shards = [(to_dev(Rg[r * n_local:(r + 1) * n_local]), to_dev(Sg[r * n_local:(r + 1) * n_local])) for r in range(world)]
+    plan = engines[0].shard_plan(len(Rg), len(Sg), world)
+    ndig = world << plan.bits_pass1
+    stage = [[torch.empty((n_local, 2), dtype=torch.int64, device=DEV) for _ in range(2)] for _ in range(world)]
+    hist = [[torch.empty(ndig, dtype=torch.int64, device=DEV) for _ in range(2)] for _ in range(world)]
+    for r in range(world):
+        engines[r].shardx_begin(plan)
+        for rel in (0, 1):
+            engines[r].shardx_pass1(plan, rel, shards[r][rel], stage[r][rel], hist[r][rel])
+    lay = [[None, None] for _ in range(world)]
+    for rel in (0, 1):
+        all_hist = torch.stack([hist[r][rel] for r in range(world)])                     # the all-gather
+        for r in range(world):
+            lay[r][rel] = engines[r].shardx_layout(plan, r, rel, all_hist)
+    recv = [[torch.empty((max(lay[r][rel][3], 1), 2), dtype=torch.int64, device=DEV) for rel in (0, 1)] for r in range(world)]
+    for rel in (0, 1):
+        assert sum(lay[r][rel][3] for r in range(world)) == world * n_local
+        for r in range(world):                                                           # the peer copies
+            so, sc, do, _ = lay[r][rel]
+            for d in range(world):
+                recv[d][rel][do[d]:do[d] + sc[d]].copy_(stage[r][rel][so[d]:so[d] + sc[d]])
+    torch.cuda.synchronize()
+    got = []
+    for r in range(world):
+        for rel in (0, 1):
+            mine = tuples_np(recv[r][rel][:lay[r][rel][3]])
+            assert (rank_of_values(mine["payload"], world) == r).all()
+            engines[r].shardx_pass2(plan, rel, recv[r][rel][:lay[r][rel][3]])
+        out = torch.empty((max(len(expect), 1), 2), dtype=torch.int64, device=DEV)
+        pairs, n = engines[r].shardx_join(plan, out)
+        got.append(pairs_np(pairs))
+    got = np.concatenate(got)
+    assert len(got) == len(expect)
+    assert np.array_equal(O.sort_pairs(got), expect)
+    for e in engines:
+        e.close()
