@@ -68,9 +68,15 @@ int launch_hist(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, bool
 template <int K, bool S, int W>
 cudaError_t launch_scatter_t(cudaStream_t st, const PartArgs &a, u32 grid) {
     const size_t smem = kScatterSmem;
-    cudaError_t e = set_smem(k_scatter<K, S, W>, smem);
+    if (a.ndig > 512) {  // 1024-digit passes (sharded plans) pay for the larger counter arrays, 512-digit ones do not
+        cudaError_t e = set_smem(k_scatter<K, S, W, kMaxDigits>, smem);
+        if (e != cudaSuccess) return e;
+        k_scatter<K, S, W, kMaxDigits><<<grid, kPartThreads, smem, st>>>(a);
+        return cudaGetLastError();
+    }
+    cudaError_t e = set_smem(k_scatter<K, S, W, 512>, smem);
     if (e != cudaSuccess) return e;
-    k_scatter<K, S, W><<<grid, kPartThreads, smem, st>>>(a);
+    k_scatter<K, S, W, 512><<<grid, kPartThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -26,11 +26,13 @@ struct __align__(16) Pair {
 
 constexpr u32 kEmpty = 0xFFFFFFFFu;
 
-// Mixed hash of the join value.  hash32 = low word: partition id = its TOP bits, table slot = its
-// LOW bits.  hash_hi32 = high word: destination rank of the multi-GPU shuffle (independent bits,
-// so a rank's local partitions stay balanced).  (The reference buckets on the raw low byte,
-// JobScheduler.cpp:151; any function of the value gives the same join result, and mixed bits
-// keep low-entropy contest columns balanced.)
+// Mixed hash of the join value (two multiply-xorshift rounds).  hash32 = low word: partition id =
+// its TOP bits, shared-memory table slot = its LOW bits.  hash_hi32 = high word: destination rank of
+// the multi-GPU shuffle (independent bits, so a rank's local partitions stay balanced).  The
+// reference buckets on the raw low byte (JobScheduler.cpp:151); any function of the value gives
+// the same join result, and mixed bits keep the low-entropy contest columns balanced.
+// (A one-multiply Fibonacci hash was measured: no kernel got faster, the join got 4 % slower --
+// profiles/r01_tuning_notes.md.)
 __device__ __forceinline__ u64 hash64(u64 v) {
     v ^= v >> 32;
     v *= 0xd6e8feb86659fd93ULL;

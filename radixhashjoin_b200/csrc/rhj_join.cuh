@@ -33,10 +33,12 @@ constexpr int kJoinThreads = 512;
 constexpr int kJoinItems = 4;                        // probe tuples per thread per round
 constexpr int kRound = kJoinThreads * kJoinItems;    // 2048 probe tuples per round
 constexpr u32 kBuildCap = 4096;                      // build tuples per shared-memory table (64 KiB)
+typedef u32 slot_t;
 constexpr u32 kSlots = 8192;                         // open-addressing slots (u32 index) (32 KiB)
+constexpr slot_t kSlotEmpty = 0xFFFFFFFFu;
 constexpr u32 kProbeChunk = 16384;                   // probe tuples per work item
 constexpr u32 kTargetBuildPerPart = 2048;            // radix bits are chosen for this average
-constexpr size_t kJoinSmemBytes = (size_t) kBuildCap * sizeof(Tup) + (size_t) kSlots * sizeof(u32);
+constexpr size_t kJoinSmemBytes = (size_t) kBuildCap * sizeof(Tup) + (size_t) kSlots * sizeof(slot_t);
 
 struct Item {
     u32 part;
@@ -67,7 +69,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kJoinThreads, 2) k_join(JoinArgs a) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     Tup *s_tup = reinterpret_cast<Tup *>(dyn_smem);
-    u32 *s_slot = reinterpret_cast<u32 *>(dyn_smem + (size_t) kBuildCap * sizeof(Tup));
+    slot_t *s_slot = reinterpret_cast<slot_t *>(dyn_smem + (size_t) kBuildCap * sizeof(Tup));
     __shared__ __align__(8) u64 s_bar;
     __shared__ u32 s_item;
     __shared__ u32 s_cnt[2];
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(kJoinThreads, 2) k_join(JoinArgs a) {
                     if (idx < p1) t[j] = ld_stream(a.probe + idx);
                 }
             }
-            for (u32 i = tid; i < kSlots / 4; i += kJoinThreads)
+            for (u32 i = tid; i < kSlots * sizeof(slot_t) / 16; i += kJoinThreads)
                 reinterpret_cast<uint4 *>(s_slot)[i] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
             mbar_wait(&s_bar, phase);
             phase ^= 1;
@@ -122,8 +124,8 @@ __global__ void __launch_bounds__(kJoinThreads, 2) k_join(JoinArgs a) {
                 const u64 v = s_tup[i].val;
                 u32 h = slot_of(v);
                 while (true) {
-                    u32 old = atomicCAS(&s_slot[h], kEmpty, i);
-                    if (old == kEmpty) break;
+                    u32 old = atomicCAS(&s_slot[h], kSlotEmpty, (slot_t) i);
+                    if (old == kSlotEmpty) break;
                     if (s_tup[old].val == v) dup = 1;
                     h = (h + 1) & (kSlots - 1);
                 }
@@ -149,7 +151,7 @@ __global__ void __launch_bounds__(kJoinThreads, 2) k_join(JoinArgs a) {
                         if (ok[j]) {
                             u32 h = slot_of(t[j].val);
                             u32 idx;
-                            while ((idx = s_slot[h]) != kEmpty) {
+                            while ((idx = s_slot[h]) != kSlotEmpty) {
                                 if (s_tup[idx].val == t[j].val) { m[j] = idx; break; }
                                 h = (h + 1) & (kSlots - 1);
                             }
@@ -198,7 +200,7 @@ __global__ void __launch_bounds__(kJoinThreads, 2) k_join(JoinArgs a) {
                         if (ok[j]) {
                             u32 h = slot_of(t[j].val);
                             u32 idx;
-                            while ((idx = s_slot[h]) != kEmpty) {
+                            while ((idx = s_slot[h]) != kSlotEmpty) {
                                 if (s_tup[idx].val == t[j].val) cnt[j]++;
                                 h = (h + 1) & (kSlots - 1);
                             }
@@ -230,7 +232,7 @@ __global__ void __launch_bounds__(kJoinThreads, 2) k_join(JoinArgs a) {
                         if (cnt[j]) {
                             u32 h = slot_of(t[j].val);
                             u32 idx;
-                            while ((idx = s_slot[h]) != kEmpty) {
+                            while ((idx = s_slot[h]) != kSlotEmpty) {
                                 if (s_tup[idx].val == t[j].val) {
                                     u64 bk = s_tup[idx].key;
                                     if (at < a.capacity) {

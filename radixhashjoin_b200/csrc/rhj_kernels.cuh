@@ -246,13 +246,13 @@ __global__ void __launch_bounds__(1024) k_scan_parts(ScanPartsArgs a) {
 //   or, with BULK, by one TMA bulk store (cp.async.bulk shared->global) per run.
 // Algorithmic bytes: 16 read + 16 written per tuple.
 enum ScatterWrite { kWriteStaged = 0, kWriteBulk = 1 };
-template <int KIND, bool SEG, int WMODE>
+template <int KIND, bool SEG, int WMODE, int MAXD>
 __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(PartArgs a) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     Tup *s_tup = reinterpret_cast<Tup *>(dyn_smem);
-    __shared__ u32 s_cnt[kMaxDigits];
-    __shared__ u32 s_off[kMaxDigits];
-    __shared__ u64 s_delta[kMaxDigits];  // global index of sorted slot i of digit d = s_delta[d] + i
+    __shared__ u32 s_cnt[MAXD];
+    __shared__ u32 s_off[MAXD];
+    __shared__ u64 s_delta[MAXD];  // global index of sorted slot i of digit d = s_delta[d] + i
     __shared__ u32 s_w[32];
 
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -265,7 +265,7 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
 
     for (u32 d = tid; d < a.ndig; d += kPartThreads) s_cnt[d] = 0;
     Tup v[kPartItems];
-    u32 dr[kPartItems];  // digit << 16 | rank   (rank < 4096)
+    u32 dr[kPartItems];  // digit << 16 | rank   (digit < 1024, rank < 4096)
 #pragma unroll
     for (int j = 0; j < kPartItems; ++j) {
         u32 i = j * kPartThreads + tid;
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
     __syncthreads();
     // reserve the runs (global atomics issued first so their latency overlaps the block scan);
     // thread t owns the kDigitsPerThread consecutive digits starting at t * kDigitsPerThread
-    constexpr int kDigitsPerThread = (kMaxDigits + kPartThreads - 1) / kPartThreads;
+    constexpr int kDigitsPerThread = (MAXD + kPartThreads - 1) / kPartThreads;
     u32 c[kDigitsPerThread];
     u64 g[kDigitsPerThread];
     u32 csum = 0;
