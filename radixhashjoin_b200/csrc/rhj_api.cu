@@ -146,6 +146,41 @@ u64 *scalars_of(rhj_ctx *ctx, u32 nparts) {
     return (u64 *) ctx->zero.p + 2 * (size_t) kMaxDigits + 2 * (size_t) nparts;
 }
 
+// Builds the per-tile descriptor tables of a segmented pass (one 16-byte entry per tile) and points
+// the relations at them.  `slot` 0/1 selects the half of ctx->tiles a lone relation uses.
+int build_tile_tables(rhj_ctx *ctx, cudaStream_t st, PartArgs &b, int nrel, int slot = 0) {
+    size_t need[2] = {0, 0}, total = 0;
+    for (int i = 0; i < nrel; ++i) {
+        need[i] = ((size_t) b.rel[i].ntiles + 1) * sizeof(TileDesc);
+        total += need[i];
+    }
+    // lone relations (sharded join: R and S arrive separately) use fixed halves so they never alias
+    size_t half = 0;
+    if (nrel == 1) {
+        half = need[0];
+        total = 2 * half;
+    }
+    if (total > ctx->tiles.cap) {
+        // growing would free a table a previously launched kernel may still read: finish that work first
+        CK(cudaStreamSynchronize(st));
+        int rc = ensure(ctx, ctx->tiles, std::max(total, 2 * ctx->tiles.cap));
+        if (rc) return rc;
+        if (nrel == 1) half = ctx->tiles.cap / 2 / sizeof(TileDesc) * sizeof(TileDesc);
+    } else if (nrel == 1) {
+        half = ctx->tiles.cap / 2 / sizeof(TileDesc) * sizeof(TileDesc);
+    }
+    char *base = (char *) ctx->tiles.p + (nrel == 1 ? (size_t) slot * half : 0);
+    for (int i = 0; i < nrel; ++i) {
+        TileDesc *t = (TileDesc *) base;
+        k_tile_table<<<b.rel[i].nseg + 1, 256, 0, st>>>(b.rel[i].seg_off, b.rel[i].seg_tile0, b.rel[i].nseg, b.rel[i].ntiles, t);
+        CK(cudaGetLastError());
+        ctx->info.kernel_launches++;
+        b.rel[i].tiles = t;
+        base += need[i];
+    }
+    return RHJ_OK;
+}
+
 // Second radix pass (if the plan has one) over pass-1-partitioned relations inX[0] (build) and
 // inX[1] (probe) whose pass-1 offsets / first-tile tables are off1X / tile0X, then the work-item
 // plan.  Leaves ctx->cur describing the final partitions.  Enqueues only; no host sync.
@@ -173,6 +208,7 @@ int second_pass_and_plan(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Me
         b.rel[0] = PartRel{inX[0], B, pl.nB, m.hist2[0], m.cur2[0], off1X[0], tile0X[0], nseg, tiles_of(pl.nB) + nseg};
         b.rel[1] = PartRel{inX[1], B + pl.nB, pl.nP, m.hist2[1], m.cur2[1], off1X[1], tile0X[1], nseg,
                            tiles_of(pl.nP) + nseg};
+        if ((rc = build_tile_tables(ctx, st, b, 2))) return rc;
         mark(ctx, st, RHJ_PHASE_HIST2);
         if ((rc = launch_hist(ctx, st, b, kDigitHash, true))) return rc;
         mark(ctx, st, RHJ_PHASE_SCAN2);
@@ -999,6 +1035,7 @@ int rhj_shardx_pass2_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, con
     b.rel[0] = PartRel{(const Tup *) d_recv, (Tup *) out.p, n_recv, m.hist2[rel], m.cur2[rel], sm.seg_off[rel], m.tile0[rel],
                        npieces, tiles_of(n_recv) + npieces, nd1 - 1};
     if (nd1 == 1) b.rel[0].group_mask = 0x80000000u;  // every piece is partition 0: (seg & mask) == 0
+    if ((rc = build_tile_tables(ctx, st, b, 1, rel))) return rc;
     if (rel == 0) mark(ctx, st, RHJ_PHASE_HIST2);
     if ((rc = launch_hist(ctx, st, b, kDigitHash, true))) return rc;
     ScanPartsRelArgs sr{};

@@ -45,6 +45,7 @@ struct rhj_ctx {
                                  // larger NVLink packets (measured 4.85 vs 5.17 ms at N=2) (RHJ_SHARD_SCATTER_MODE)
 
     DevBuf bufA, bufB;        // pass-1 / pass-2 partitioned tuples (build side first, then probe side)
+    DevBuf tiles;             // TileDesc tables of the second pass (both relations)
     DevBuf bufB2;             // sharded join: pass-2 output of relation S (relations arrive separately)
     DevBuf shard_meta;        // sharded join: local offsets, piece tables, ship matrix
     DevBuf zero;              // hist1 | hist2 | scalars   (memset to 0 per call)
@@ -84,7 +85,7 @@ struct rhj_ctx {
 
 template <typename F>
 inline void for_each_buf(rhj_ctx *c, F f) {
-    DevBuf *bufs[] = {&c->bufA, &c->bufB, &c->bufB2, &c->shard_meta, &c->zero, &c->meta, &c->items, &c->item_cnt, &c->item_off, &c->filt_cnt,
+    DevBuf *bufs[] = {&c->bufA, &c->bufB, &c->tiles, &c->bufB2, &c->shard_meta, &c->zero, &c->meta, &c->items, &c->item_cnt, &c->item_off, &c->filt_cnt,
                       &c->filt_off, &c->filt_tmp, &c->inR, &c->inS, &c->outP, &c->iu_col, &c->iu_pairs, &c->iu_A,
                       &c->iu_B, &c->iu_ep, &c->iu_out};
     for (DevBuf *b : bufs) f(*b);

@@ -51,6 +51,15 @@ struct PartRel {
     u32 ntiles;            // tiles of this relation (SEG: host-side upper bound)
     u32 group_mask;        // SEG: segments that share counters: group = seg & group_mask (0 = every segment
                            // is its own group).  Sharded pass 2: segment = (source rank, pass-1 partition).
+    const void *tiles;     // SEG: optional TileDesc[ntiles] built by k_tile_table (else binary search)
+};
+// One 16-byte descriptor per pass-2 tile (k_tile_table): a CTA finds its tuple range with ONE load
+// instead of a 9-step binary search over seg_tile0 -- that dependent-load chain sat in front of
+// every tile's first tuple load.
+struct __align__(16) TileDesc {
+    u64 beg;
+    u32 len;  // 0 = no such tile
+    u32 seg;
 };
 __device__ __forceinline__ u32 seg_group(const PartRel &r, u32 seg) { return r.group_mask ? (seg & r.group_mask) : seg; }
 struct PartArgs {
@@ -84,6 +93,14 @@ __device__ __forceinline__ bool tile_range(const PartRel &r, u32 lt, u32 &seg, u
         end = min(beg + (u64) kTile, r.n);
         return beg < r.n;
     }
+    if (r.tiles) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4 *>(r.tiles) + lt);  // {beg.lo, beg.hi, len, seg}
+        if (q.z == 0) return false;
+        beg = ((u64) q.y << 32) | q.x;
+        end = beg + q.z;
+        seg = q.w;
+        return true;
+    }
     if (lt >= r.seg_tile0[r.nseg]) return false;
     u32 lo = 0, hi = r.nseg;  // last seg with seg_tile0[seg] <= lt
     while (hi - lo > 1) {
@@ -94,6 +111,23 @@ __device__ __forceinline__ bool tile_range(const PartRel &r, u32 lt, u32 &seg, u
     beg = r.seg_off[lo] + (u64) (lt - r.seg_tile0[lo]) * kTile;
     end = min(beg + (u64) kTile, r.seg_off[lo + 1]);
     return true;
+}
+
+// Expands (seg_off, seg_tile0) into one TileDesc per tile; entries past the last tile get len 0.
+// One CTA per segment (+1 that clears the tail up to the host-side bound `ntiles`).
+__global__ void __launch_bounds__(256) k_tile_table(const u64 *seg_off, const u32 *seg_tile0, u32 nseg, u32 ntiles,
+                                                    TileDesc *tiles) {
+    const u32 seg = blockIdx.x;
+    if (seg == nseg) {
+        for (u32 t = seg_tile0[nseg] + threadIdx.x; t < ntiles; t += blockDim.x) tiles[t] = TileDesc{0, 0, 0};
+        return;
+    }
+    const u64 b = seg_off[seg], e = seg_off[seg + 1];
+    const u32 t0 = seg_tile0[seg], t1 = seg_tile0[seg + 1];
+    for (u32 t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
+        u64 beg = b + (u64) (t - t0) * kTile;
+        tiles[t] = TileDesc{beg, (u32) min((u64) kTile, e - beg), seg};
+    }
 }
 
 // (1) Histogram.  Each CTA owns a contiguous range of tiles, counts digits in shared memory
