@@ -347,10 +347,19 @@ def run_b200(args, rank, world, local_rank):
     dom = max((k for k in alg_bytes if acc.get(k, 0) > 0), key=lambda k: acc[k], default=None)
     peak, peak_src = measured_hbm_peak()
     roofline = None
+    traffic = None
+    try:  # dram bytes of the same kernel from the committed ncu --set full capture of this workload
+        with open(os.path.join(ROOT, "profiles", "r01_final_ncu_traffic.json")) as f:
+            tj = json.load(f)
+        if world == 1 and tj["workload"] == wname and tj["emitter"] == args.emit and dom in tj["phases"]:
+            traffic = tj["phases"][dom]["traffic_bytes"]
+    except Exception:
+        traffic = None
     if dom:
         ach = alg_bytes[dom] / (acc[dom] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": None, "peak_source": peak_src, "kernel_ms": acc[dom],
+                    "traffic": traffic, "traffic_source": "profiles/r01_final_ncu_traffic.json" if traffic else None,
+                    "peak_source": peak_src, "kernel_ms": acc[dom],
                     "algorithmic_bytes_per_launch": alg_bytes[dom]}
     b_alg_step = 96 * n_join + 16 * m_local     # canonical 2-pass plan
     step_gbs = b_alg_step / (ms_step * 1e-3) / 1e9
