@@ -406,6 +406,218 @@ int write_phase(rhj_ctx *ctx, cudaStream_t st, Pair *d_out, u64 capacity) {
 
 }  // namespace
 
+namespace {
+
+// One radix pass (histogram -> prefix sum -> scatter) of ONE relation occupying meta slot `slot`.
+// SEG = second pass inside the pass-1 partitions.  Enqueues only.
+int one_relation_pass(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Meta &m, int slot, bool second, const Tup *in,
+                      Tup *out, u64 n) {
+    int rc;
+    PartArgs a{};
+    if (!second) {
+        a.shift = 32 - pl.b1;
+        a.mask = (1u << pl.b1) - 1;
+        a.ndig = 1u << pl.b1;
+        a.rel[0] = PartRel{in, out, n, m.hist1[slot], m.cur1[slot], nullptr, nullptr, 1, tiles_of(n)};
+        if ((rc = launch_hist(ctx, st, a, kDigitHash, false))) return rc;
+        ScanDigitsArgs sd{};
+        sd.hist[0] = sd.hist[1] = m.hist1[slot];
+        sd.off[0] = sd.off[1] = m.off1[slot];
+        sd.cursor[0] = sd.cursor[1] = m.cur1[slot];
+        sd.tile0[0] = sd.tile0[1] = pl.b2 ? m.tile0[slot] : nullptr;
+        sd.ndig = a.ndig;
+        k_scan_digits<<<1, kMaxDigits, 0, st>>>(sd);
+        CK(cudaGetLastError());
+        ctx->info.kernel_launches++;
+        return launch_scatter(ctx, st, a, kDigitHash, false);
+    }
+    const u32 nseg = 1u << pl.b1;
+    a.shift = 32 - pl.bits;
+    a.mask = (1u << pl.b2) - 1;
+    a.ndig = 1u << pl.b2;
+    a.rel[0] = PartRel{in, out, n, m.hist2[slot], m.cur2[slot], m.off1[slot], m.tile0[slot], nseg, tiles_of(n) + nseg};
+    if ((rc = build_tile_tables(ctx, st, a, 1, slot))) return rc;
+    if ((rc = launch_hist(ctx, st, a, kDigitHash, true))) return rc;
+    ScanPartsRelArgs sr{};
+    sr.hist2 = m.hist2[slot];
+    sr.off1 = m.off1[slot];
+    sr.off2 = m.off2[slot];
+    sr.cursor2 = m.cur2[slot];
+    sr.nseg = nseg;
+    sr.ndig = a.ndig;
+    k_scan_parts_rel<<<nseg, kMaxDigits, 0, st>>>(sr);
+    CK(cudaGetLastError());
+    ctx->info.kernel_launches++;
+    return launch_scatter(ctx, st, a, kDigitHash, true);
+}
+
+// Partitions one relation completely (0, 1 or 2 passes).  On return *fin / *off describe its final
+// partitions (meta slot `slot`).  tmpA / tmpB are the pass outputs (n tuples each).
+int partition_relation(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Meta &m, int slot, const Tup *in, u64 n,
+                       Tup *tmpA, Tup *tmpB, const Tup **fin, const u64 **off) {
+    int rc;
+    if (pl.bits == 0) {
+        k_set_single_part<<<1, 1, 0, st>>>(m.off2[slot], n, m.off2[slot], n);
+        CK(cudaGetLastError());
+        ctx->info.kernel_launches++;
+        *fin = in;
+        *off = m.off2[slot];
+        return RHJ_OK;
+    }
+    if ((rc = one_relation_pass(ctx, st, pl, m, slot, false, in, tmpA, n))) return rc;
+    if (pl.b2 == 0) {
+        *fin = tmpA;
+        *off = m.off1[slot];
+        return RHJ_OK;
+    }
+    if ((rc = one_relation_pass(ctx, st, pl, m, slot, true, tmpA, tmpB, n))) return rc;
+    *fin = tmpB;
+    *off = m.off2[slot];
+    return RHJ_OK;
+}
+
+// Pipelined host join for large inputs: the build side is uploaded and partitioned once; the probe
+// side streams through in chunks -- H2D of chunk c+1, partition + count + write of chunk c and D2H
+// of chunk c-1's pairs run concurrently (three streams, double-buffered chunk and result buffers),
+// so the PCIe link is busy in both directions instead of H2D, compute and D2H taking turns.
+// Every chunk re-builds the shared-memory tables from the (resident) build partitions.
+int join_host_pipelined(rhj_ctx *ctx, const Tup *hR, u64 nR, const Tup *hS, u64 nS, const rhj_pair **out, uint64_t *count) {
+    cudaStream_t st = ctx->stream;
+    int rc;
+    if (!ctx->s_in) {
+        CK(cudaStreamCreateWithFlags(&ctx->s_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_cmp[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    Plan pl = make_plan(nR, nS);
+    const Tup *hB = pl.build_is_S ? hS : hR, *hP = pl.build_is_S ? hR : hS;
+    ctx->info = rhj_plan_info{};
+    ctx->info.bits_total = pl.bits;
+    ctx->info.bits_pass1 = pl.b1;
+    ctx->info.bits_pass2 = pl.b2;
+    ctx->info.build_is_S = pl.build_is_S;
+    ctx->info.n_partitions = pl.nparts;
+    ctx->cur.valid = false;
+    ctx->nmarks = 0;
+    Meta m;
+    if ((rc = layout_meta(ctx, pl.nparts, m))) return rc;
+    const u64 chunk = std::min<u64>(ctx->host_chunk, pl.nP);
+    const u64 nchunks = (pl.nP + chunk - 1) / chunk;
+
+    // ---- build side: upload, partition, keep ----
+    if ((rc = ensure(ctx, ctx->inR, pl.nB * sizeof(Tup)))) return rc;
+    if ((rc = ensure(ctx, ctx->bufA, pl.nB * sizeof(Tup)))) return rc;
+    if ((rc = ensure(ctx, ctx->bufB, pl.nB * sizeof(Tup)))) return rc;
+    for (int i = 0; i < 2; ++i)
+        if ((rc = ensure(ctx, ctx->pin[i], chunk * sizeof(Tup)))) return rc;
+    if ((rc = ensure(ctx, ctx->pA, chunk * sizeof(Tup)))) return rc;
+    if ((rc = ensure(ctx, ctx->pB, chunk * sizeof(Tup)))) return rc;
+    u64 cap64 = (u64) pl.nparts + chunk / kProbeChunk + 2;
+    if (cap64 > 0x7fffffffull) return fail(ctx, RHJ_ERR_ARG, "relation too large for the work-item table");
+    const u32 item_cap = (u32) cap64;
+    if ((rc = ensure(ctx, ctx->items, (size_t) item_cap * sizeof(Item)))) return rc;
+    if ((rc = ensure(ctx, ctx->item_cnt, (size_t) item_cap * 8))) return rc;
+    if ((rc = ensure(ctx, ctx->item_off, (size_t) item_cap * 8))) return rc;
+
+    CK(cudaMemcpyAsync(ctx->inR.p, hB, pl.nB * sizeof(Tup), cudaMemcpyHostToDevice, st));
+    // the first probe chunk goes up while the build side is partitioned
+    CK(cudaMemcpyAsync(ctx->pin[0].p, hP, std::min(chunk, pl.nP) * sizeof(Tup), cudaMemcpyHostToDevice, ctx->s_in));
+    CK(cudaEventRecord(ctx->ev_in[0], ctx->s_in));
+    CK(cudaMemsetAsync(ctx->zero.p, 0, m.zero_bytes, st));
+    const Tup *finB;
+    const u64 *offB;
+    if ((rc = partition_relation(ctx, st, pl, m, 0, (const Tup *) ctx->inR.p, pl.nB, (Tup *) ctx->bufA.p, (Tup *) ctx->bufB.p,
+                                 &finB, &offB)))
+        return rc;
+
+    u64 total = 0;
+    u64 *sc = m.scalars;
+    for (u64 c = 0; c < nchunks; ++c) {
+        const int b = (int) (c & 1);
+        const u64 n_c = std::min(chunk, pl.nP - c * chunk);
+        if (c + 1 < nchunks) {  // next chunk's upload: its buffer was last read by chunk c-1's kernels
+            const int nb = b ^ 1;
+            const u64 n_next = std::min(chunk, pl.nP - (c + 1) * chunk);
+            if (c >= 1) CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_cmp[nb], 0));
+            CK(cudaMemcpyAsync(ctx->pin[nb].p, hP + (c + 1) * chunk, n_next * sizeof(Tup), cudaMemcpyHostToDevice, ctx->s_in));
+            CK(cudaEventRecord(ctx->ev_in[nb], ctx->s_in));
+        }
+        CK(cudaStreamWaitEvent(st, ctx->ev_in[b], 0));
+        // counters of the probe side and the per-join scalars start from zero for every chunk
+        CK(cudaMemsetAsync(m.hist1[1], 0, (size_t) kMaxDigits * 8, st));
+        CK(cudaMemsetAsync(m.hist2[1], 0, ((size_t) pl.nparts + kScCount) * 8, st));  // hist2[1] | scalars are contiguous
+        const Tup *finP;
+        const u64 *offP;
+        if ((rc = partition_relation(ctx, st, pl, m, 1, (const Tup *) ctx->pin[b].p, n_c, (Tup *) ctx->pA.p, (Tup *) ctx->pB.p,
+                                     &finP, &offP)))
+            return rc;
+        PlanPartsArgs pa{};
+        pa.offB = offB;
+        pa.offP = offP;
+        pa.ndig = std::min<u32>(pl.nparts, kMaxDigits);
+        pa.items = (Item *) ctx->items.p;
+        pa.item_cap = item_cap;
+        pa.nitems = (u32 *) (sc + kScNItems);
+        pa.err = (u32 *) (sc + kScErr);
+        k_plan_parts<<<pl.nparts / pa.ndig, kMaxDigits, 0, st>>>(pa);
+        CK(cudaGetLastError());
+        ctx->info.kernel_launches++;
+        ctx->cur.valid = true;
+        ctx->cur.counted = false;
+        ctx->cur.build = finB;
+        ctx->cur.probe = finP;
+        ctx->cur.offB = offB;
+        ctx->cur.offP = offP;
+        ctx->cur.nparts = pl.nparts;
+        ctx->cur.item_cap = item_cap;
+        ctx->cur.build_is_S = pl.build_is_S;
+        if ((rc = count_phase(ctx, st))) return rc;  // host sync: this chunk's exact result size
+        const u64 n_out = ctx->cur.count;
+        if (n_out) {
+            if ((total + n_out) * sizeof(Pair) > ctx->h_out_cap) {
+                // grow the pinned result, keeping what earlier chunks delivered (their copies must have landed)
+                CK(cudaStreamSynchronize(ctx->s_out));
+                const u64 guess = std::max<u64>(total + n_out, (total + n_out) / (c + 1) * nchunks + (total + n_out) / 8);
+                void *nu = nullptr;
+                cudaError_t e = cudaHostAlloc(&nu, guess * sizeof(Pair), cudaHostAllocDefault);
+                if (e != cudaSuccess) {
+                    cudaGetLastError();
+                    return fail(ctx, RHJ_ERR_NOMEM, "cudaHostAlloc result", e);
+                }
+                if (total) memcpy(nu, ctx->h_out, total * sizeof(Pair));
+                if (ctx->h_out) cudaFreeHost(ctx->h_out);
+                ctx->h_out = nu;
+                ctx->h_out_cap = guess * sizeof(Pair);
+            }
+            if (c >= 2) CK(cudaStreamWaitEvent(st, ctx->ev_out[b], 0));  // result buffer b is free again
+            else if (n_out * sizeof(Pair) > ctx->pout[b].cap) CK(cudaStreamSynchronize(ctx->s_out));
+            if (n_out * sizeof(Pair) > ctx->pout[b].cap) CK(cudaStreamSynchronize(ctx->s_out));
+            if ((rc = ensure(ctx, ctx->pout[b], n_out * sizeof(Pair)))) return rc;
+            if ((rc = write_phase(ctx, st, (Pair *) ctx->pout[b].p, n_out))) return rc;
+        }
+        CK(cudaEventRecord(ctx->ev_cmp[b], st));
+        if (n_out) {
+            CK(cudaStreamWaitEvent(ctx->s_out, ctx->ev_cmp[b], 0));
+            CK(cudaMemcpyAsync((Pair *) ctx->h_out + total, ctx->pout[b].p, n_out * sizeof(Pair), cudaMemcpyDeviceToHost,
+                               ctx->s_out));
+            CK(cudaEventRecord(ctx->ev_out[b], ctx->s_out));
+        }
+        total += n_out;
+    }
+    CK(cudaStreamSynchronize(ctx->s_out));
+    CK(cudaStreamSynchronize(st));
+    ctx->cur.valid = false;
+    *count = total;
+    *out = total ? (const rhj_pair *) ctx->h_out : nullptr;
+    return RHJ_OK;
+}
+
+}  // namespace
+
 // =================================================================================================
 extern "C" {
 
@@ -428,6 +640,7 @@ int rhj_create(int device, rhj_ctx **out) {
     const char *e;
     if ((e = getenv("RHJ_HIST_AGG"))) ctx->hist_agg = atoi(e) != 0;
     if ((e = getenv("RHJ_SCATTER_MODE"))) ctx->scatter_mode = atoi(e);
+    if ((e = getenv("RHJ_HOST_CHUNK"))) ctx->host_chunk = std::max<long long>(1, atoll(e));
     if ((e = getenv("RHJ_SHARD_SCATTER_MODE"))) ctx->shard_scatter_mode = atoi(e);
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
@@ -449,6 +662,13 @@ int rhj_destroy(rhj_ctx *ctx) {
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     for (cudaEvent_t e : ctx->ev)
         if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]);
+        if (ctx->ev_cmp[i]) cudaEventDestroy(ctx->ev_cmp[i]);
+        if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]);
+    }
+    if (ctx->s_in) cudaStreamDestroy(ctx->s_in);
+    if (ctx->s_out) cudaStreamDestroy(ctx->s_out);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return RHJ_OK;
@@ -587,6 +807,9 @@ int rhj_join_host(rhj_ctx *ctx, const rhj_tuple *R, uint64_t nR, const rhj_tuple
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     int rc;
+    // large probe sides stream through in chunks so that H2D, compute and D2H overlap
+    if (std::max(nR, nS) >= 2 * ctx->host_chunk)
+        return join_host_pipelined(ctx, (const Tup *) R, nR, (const Tup *) S, nS, out, count);
     if ((rc = ensure(ctx, ctx->inR, nR * sizeof(Tup)))) return rc;
     if ((rc = ensure(ctx, ctx->inS, nS * sizeof(Tup)))) return rc;
     CK(cudaMemcpyAsync(ctx->inR.p, R, nR * sizeof(Tup), cudaMemcpyHostToDevice, st));

@@ -53,6 +53,10 @@ struct rhj_ctx {
     DevBuf items, item_cnt, item_off;
     DevBuf filt_cnt, filt_off, filt_tmp;
     DevBuf inR, inS, outP;    // device staging of the host entry point
+    DevBuf pin[2], pout[2], pA, pB;      // pipelined host join: probe chunk in (x2), result out (x2), chunk partitions
+    cudaStream_t s_in = nullptr, s_out = nullptr;    // pipelined host join: H2D and D2H streams
+    cudaEvent_t ev_in[2] = {}, ev_cmp[2] = {}, ev_out[2] = {};
+    uint64_t host_chunk = (uint64_t) 1 << 24;        // probe tuples per pipelined chunk (RHJ_HOST_CHUNK)
     DevBuf iu_col, iu_pairs, iu_A, iu_B, iu_ep, iu_out;  // update_intermediate staging (rhj_query.cu)
     void *h_iu = nullptr;     // pinned host result columns of the intermediate update
     size_t h_iu_cap = 0;
@@ -86,7 +90,8 @@ struct rhj_ctx {
 template <typename F>
 inline void for_each_buf(rhj_ctx *c, F f) {
     DevBuf *bufs[] = {&c->bufA, &c->bufB, &c->tiles, &c->bufB2, &c->shard_meta, &c->zero, &c->meta, &c->items, &c->item_cnt, &c->item_off, &c->filt_cnt,
-                      &c->filt_off, &c->filt_tmp, &c->inR, &c->inS, &c->outP, &c->iu_col, &c->iu_pairs, &c->iu_A,
+                      &c->filt_off, &c->filt_tmp, &c->inR, &c->inS, &c->outP, &c->pin[0], &c->pin[1], &c->pout[0], &c->pout[1],
+                      &c->pA, &c->pB, &c->iu_col, &c->iu_pairs, &c->iu_A,
                       &c->iu_B, &c->iu_ep, &c->iu_out};
     for (DevBuf *b : bufs) f(*b);
 }
