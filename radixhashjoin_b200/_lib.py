@@ -19,7 +19,7 @@ class PlanInfo(ctypes.Structure):
     """struct rhj_plan_info (include/rhj.h)."""
     _fields_ = [("bits_total", ctypes.c_uint32), ("bits_pass1", ctypes.c_uint32), ("bits_pass2", ctypes.c_uint32),
                 ("build_is_S", ctypes.c_uint32), ("n_partitions", ctypes.c_uint32), ("n_items", ctypes.c_uint32),
-                ("kernel_launches", ctypes.c_uint32), ("reserved", ctypes.c_uint32)]
+                ("kernel_launches", ctypes.c_uint32), ("optimistic_pass1", ctypes.c_uint32)]
 
 
 class ShardPlan(ctypes.Structure):

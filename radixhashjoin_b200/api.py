@@ -99,7 +99,7 @@ class RadixHashJoin:
     def last_plan(self):
         info = _lib.PlanInfo()
         self._ck(self._lib.rhj_last_plan(self._ctx, ctypes.byref(info)))
-        return {f: int(getattr(info, f)) for f, _ in _lib.PlanInfo._fields_ if f != "reserved"}
+        return {f: int(getattr(info, f)) for f, _ in _lib.PlanInfo._fields_}
 
     PHASES = ("hist1", "scan1", "scatter1", "hist2", "scan2", "scatter2", "plan", "join", "scan_items", "join_write")
 

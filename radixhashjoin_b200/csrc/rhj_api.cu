@@ -80,9 +80,16 @@ cudaError_t launch_scatter_t(cudaStream_t st, const PartArgs &a, u32 grid) {
     return cudaGetLastError();
 }
 
-int launch_scatter(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, bool seg) {
+int launch_scatter(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, bool seg, bool limit = false) {
     u32 grid = a.rel[0].ntiles + a.rel[1].ntiles;
     if (!grid) return RHJ_OK;
+    if (limit) {  // optimistic pass 1: fixed-capacity regions, bounds-checked staged stores
+        CK(set_smem(k_scatter<kDigitHash, false, kWriteStaged, 512, true>, kScatterSmem));
+        k_scatter<kDigitHash, false, kWriteStaged, 512, true><<<grid, kPartThreads, kScatterSmem, st>>>(a);
+        CK(cudaGetLastError());
+        ctx->info.kernel_launches++;
+        return RHJ_OK;
+    }
     const int w = kind == kDigitShard ? ctx->shard_scatter_mode : ctx->scatter_mode;
     cudaError_t e;
 #define SC(K, S) (w == 1 ? launch_scatter_t<K, S, kWriteBulk>(st, a, grid) : launch_scatter_t<K, S, kWriteStaged>(st, a, grid))
@@ -111,13 +118,14 @@ struct Meta {
     u64 *hist1[2], *hist2[2], *scalars;                  // zeroed
     u64 *off1[2], *cur1[2], *off2[2], *cur2[2];          // written by the scans
     u32 *tile0[2];
+    u64 *segb[2], *sege[2];                              // optimistic pass 1: where each pass-1 partition lies
     size_t zero_bytes;
 };
 
 int layout_meta(rhj_ctx *ctx, u32 nparts, Meta &m) {
     size_t zero_u64 = 2 * (size_t) kMaxDigits + 2 * (size_t) nparts + kScCount;
     size_t meta_u64 = 2 * (size_t) (kMaxDigits + 1) + 2 * (size_t) kMaxDigits + 2 * (size_t) (nparts + 1) +
-                      2 * (size_t) nparts + (size_t) (kMaxDigits + 2);
+                      2 * (size_t) nparts + (size_t) (kMaxDigits + 2) + 4 * (size_t) kMaxDigits;
     int rc;
     if ((rc = ensure(ctx, ctx->zero, zero_u64 * 8))) return rc;
     if ((rc = ensure(ctx, ctx->meta, meta_u64 * 8))) return rc;
@@ -139,6 +147,9 @@ int layout_meta(rhj_ctx *ctx, u32 nparts, Meta &m) {
     m.cur2[1] = q; q += nparts;
     m.tile0[0] = (u32 *) q;
     m.tile0[1] = m.tile0[0] + (kMaxDigits + 1);
+    q += kMaxDigits + 2;
+    for (int i = 0; i < 2; ++i) { m.segb[i] = q; q += kMaxDigits; }
+    for (int i = 0; i < 2; ++i) { m.sege[i] = q; q += kMaxDigits; }
     return RHJ_OK;
 }
 
@@ -172,7 +183,8 @@ int build_tile_tables(rhj_ctx *ctx, cudaStream_t st, PartArgs &b, int nrel, int 
     char *base = (char *) ctx->tiles.p + (nrel == 1 ? (size_t) slot * half : 0);
     for (int i = 0; i < nrel; ++i) {
         TileDesc *t = (TileDesc *) base;
-        k_tile_table<<<b.rel[i].nseg + 1, 256, 0, st>>>(b.rel[i].seg_off, b.rel[i].seg_tile0, b.rel[i].nseg, b.rel[i].ntiles, t);
+        k_tile_table<<<b.rel[i].nseg + 1, 256, 0, st>>>(b.rel[i].seg_off, b.rel[i].seg_end, b.rel[i].seg_tile0, b.rel[i].nseg,
+                                                        b.rel[i].ntiles, t);
         CK(cudaGetLastError());
         ctx->info.kernel_launches++;
         b.rel[i].tiles = t;
@@ -185,7 +197,8 @@ int build_tile_tables(rhj_ctx *ctx, cudaStream_t st, PartArgs &b, int nrel, int 
 // inX[1] (probe) whose pass-1 offsets / first-tile tables are off1X / tile0X, then the work-item
 // plan.  Leaves ctx->cur describing the final partitions.  Enqueues only; no host sync.
 int second_pass_and_plan(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Meta &m, const Tup *const inX[2],
-                         const u64 *const off1X[2], const u32 *const tile0X[2]) {
+                         const u64 *const off1X[2], const u32 *const tile0X[2], const u64 *const seg_begX[2] = nullptr,
+                         const u64 *const seg_endX[2] = nullptr) {
     int rc;
     const Tup *finB, *finP;
     const u64 *offB, *offP;
@@ -208,6 +221,12 @@ int second_pass_and_plan(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Me
         b.rel[0] = PartRel{inX[0], B, pl.nB, m.hist2[0], m.cur2[0], off1X[0], tile0X[0], nseg, tiles_of(pl.nB) + nseg};
         b.rel[1] = PartRel{inX[1], B + pl.nB, pl.nP, m.hist2[1], m.cur2[1], off1X[1], tile0X[1], nseg,
                            tiles_of(pl.nP) + nseg};
+        if (seg_begX) {  // pass 1 used fixed-capacity regions: where a segment lies is not where pass 2 packs it
+            for (int i = 0; i < 2; ++i) {
+                b.rel[i].seg_off = seg_begX[i];
+                b.rel[i].seg_end = seg_endX[i];
+            }
+        }
         if ((rc = build_tile_tables(ctx, st, b, 2))) return rc;
         mark(ctx, st, RHJ_PHASE_HIST2);
         if ((rc = launch_hist(ctx, st, b, kDigitHash, true))) return rc;
@@ -275,7 +294,47 @@ int second_pass_and_plan(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Me
 
 // Partition both relations on `bits` hash bits (one or two passes) and build the work-item list.
 // Leaves ctx->cur describing the partitioned relations.  Enqueues only; no host sync.
-int partition_and_plan(rhj_ctx *ctx, cudaStream_t st, const Tup *dR, u64 nR, const Tup *dS, u64 nS) {
+// Per-partition capacity of the optimistic pass-1 layout: expected size + 12.5 % + 8192 tuples.
+inline u64 fixed_cap(u64 n, u32 ndig) { return n / ndig + n / ndig / 8 + 8192; }
+
+// Samples 1/64 of both relations and decides whether every pass-1 partition will fit its fixed
+// region with room to spare.  One small kernel + a 4 KiB D2H + a stream synchronise.
+int sample_says_balanced(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Tup *inB, const Tup *inP, bool *ok) {
+    const u32 ndig = 1u << pl.b1;
+    int rc;
+    if ((rc = ensure(ctx, ctx->sample, 2 * (size_t) ndig * sizeof(u32)))) return rc;
+    CK(cudaMemsetAsync(ctx->sample.p, 0, 2 * (size_t) ndig * sizeof(u32), st));
+    SampleArgs sa{};
+    sa.in[0] = inB;
+    sa.in[1] = inP;
+    sa.n[0] = pl.nB;
+    sa.n[1] = pl.nP;
+    sa.shift = 32 - pl.b1;
+    sa.mask = ndig - 1;
+    sa.ndig = ndig;
+    sa.hist = (u32 *) ctx->sample.p;
+    const u64 nmax = std::max(pl.nB, pl.nP);
+    const u32 grid = (u32) ((nmax / 64 + 8 + 511) / 512);
+    k_sample_hist<<<dim3(grid, 2), 512, 0, st>>>(sa);
+    CK(cudaGetLastError());
+    ctx->info.kernel_launches++;
+    static thread_local u32 h[2 * kMaxDigits];
+    CK(cudaMemcpyAsync(h, ctx->sample.p, 2 * (size_t) ndig * sizeof(u32), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *ok = true;
+    const u64 ns[2] = {pl.nB, pl.nP};
+    for (int r = 0; r < 2; ++r) {
+        u32 mx = 0;
+        for (u32 d = 0; d < ndig; ++d) mx = std::max(mx, h[r * ndig + d]);
+        // sampled count s ~ true/64 with standard error sqrt(s): leave 5 sigma
+        const double est = 64.0 * (mx + 5.0 * std::sqrt((double) mx + 1.0));
+        if (est > (double) fixed_cap(ns[r], ndig)) *ok = false;
+    }
+    return RHJ_OK;
+}
+
+int partition_and_plan(rhj_ctx *ctx, cudaStream_t st, const Tup *dR, u64 nR, const Tup *dS, u64 nS,
+                       bool allow_optimistic = true) {
     Plan pl = make_plan(nR, nS);
     const Tup *inB = pl.build_is_S ? dS : dR;
     const Tup *inP = pl.build_is_S ? dR : dS;
@@ -307,6 +366,56 @@ int partition_and_plan(rhj_ctx *ctx, cudaStream_t st, const Tup *dR, u64 nR, con
         offB = m.off2[0];
         offP = m.off2[1];
     } else {
+        // ---- optimistic pass 1 (two-pass plans, large inputs): no histogram, fixed-capacity regions ----
+        bool optimistic = false;
+        if (allow_optimistic && ctx->optimistic && pl.b2 > 0 && ntot >= ((u64) 1 << 22)) {
+            if ((rc = sample_says_balanced(ctx, st, pl, inB, inP, &optimistic))) return rc;
+            if (ctx->force_optimistic) optimistic = true;  // test hook: exercise the overflow -> exact retry
+        }
+        if (optimistic) {
+            const u32 nd1 = 1u << pl.b1;
+            const u64 capB = fixed_cap(pl.nB, nd1), capP = fixed_cap(pl.nP, nd1);
+            if ((rc = ensure(ctx, ctx->bufA, (size_t) nd1 * (capB + capP) * sizeof(Tup)))) return rc;
+            Tup *A = (Tup *) ctx->bufA.p;
+            Tup *AP = A + (size_t) nd1 * capB;
+            FixedArgs fa{};
+            for (int i = 0; i < 2; ++i) {
+                fa.cursor[i] = m.cur1[i];
+                fa.seg_beg[i] = m.segb[i];
+                fa.seg_end[i] = m.sege[i];
+                fa.off1[i] = m.off1[i];
+                fa.tile0[i] = m.tile0[i];
+            }
+            fa.cap[0] = capB;
+            fa.cap[1] = capP;
+            fa.ndig = nd1;
+            fa.overflow = (u32 *) (m.scalars + kScOverflow);
+            k_fixed_cursors<<<2, 256, 0, st>>>(fa);
+            CK(cudaGetLastError());
+            ctx->info.kernel_launches++;
+            PartArgs a{};
+            a.shift = 32 - pl.b1;
+            a.mask = nd1 - 1;
+            a.ndig = nd1;
+            a.overflow = fa.overflow;
+            a.rel[0] = PartRel{inB, A, pl.nB, nullptr, m.cur1[0], nullptr, nullptr, 1, tiles_of(pl.nB)};
+            a.rel[1] = PartRel{inP, AP, pl.nP, nullptr, m.cur1[1], nullptr, nullptr, 1, tiles_of(pl.nP)};
+            a.rel[0].limit_cap = capB;
+            a.rel[1].limit_cap = capP;
+            mark(ctx, st, RHJ_PHASE_SCATTER1);
+            if ((rc = launch_scatter(ctx, st, a, kDigitHash, false, true))) return rc;
+            mark(ctx, st, RHJ_PHASE_SCAN1);
+            k_fixed_finish<<<2, kMaxDigits, 0, st>>>(fa);
+            CK(cudaGetLastError());
+            ctx->info.kernel_launches++;
+            const Tup *inX[2] = {A, AP};
+            const u64 *off1X[2] = {m.off1[0], m.off1[1]};
+            const u32 *tile0X[2] = {m.tile0[0], m.tile0[1]};
+            const u64 *segbX[2] = {m.segb[0], m.segb[1]};
+            const u64 *segeX[2] = {m.sege[0], m.sege[1]};
+            ctx->info.optimistic_pass1 = 1;
+            return second_pass_and_plan(ctx, st, pl, m, inX, off1X, tile0X, segbX, segeX);
+        }
         if ((rc = ensure(ctx, ctx->bufA, ntot * sizeof(Tup)))) return rc;
         Tup *A = (Tup *) ctx->bufA.p;
         // ---- pass 1: top b1 bits of hash32 ----
@@ -359,10 +468,13 @@ JoinArgs join_args(rhj_ctx *ctx, int work_slot) {
     return j;
 }
 
+constexpr int kRetryExact = 1000;  // internal: re-run the partition phase with the exact histogram path
+
 int read_scalars(rhj_ctx *ctx, cudaStream_t st) {
     u64 *sc = scalars_of(ctx, ctx->cur.nparts);
     CK(cudaMemcpyAsync(ctx->h_scalars, sc, kScCount * sizeof(u64), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (ctx->h_scalars[kScOverflow]) return kRetryExact;  // the optimistic pass-1 layout was too small
     if (ctx->h_scalars[kScErr]) return fail(ctx, RHJ_ERR_STATE, "device-side planning error (work-item table overflow)");
     ctx->info.n_items = (u32) ctx->h_scalars[kScNItems];
     return RHJ_OK;
@@ -640,6 +752,8 @@ int rhj_create(int device, rhj_ctx **out) {
     const char *e;
     if ((e = getenv("RHJ_HIST_AGG"))) ctx->hist_agg = atoi(e) != 0;
     if ((e = getenv("RHJ_SCATTER_MODE"))) ctx->scatter_mode = atoi(e);
+    if ((e = getenv("RHJ_NO_OPT"))) ctx->optimistic = atoi(e) == 0;
+    if ((e = getenv("RHJ_FORCE_OPT"))) ctx->force_optimistic = atoi(e) != 0;
     if ((e = getenv("RHJ_HOST_CHUNK"))) ctx->host_chunk = std::max<long long>(1, atoll(e));
     if ((e = getenv("RHJ_SHARD_SCATTER_MODE"))) ctx->shard_scatter_mode = atoi(e);
     if (cudaSetDevice(device) != cudaSuccess ||
@@ -746,8 +860,12 @@ int rhj_join_count_device(rhj_ctx *ctx, const rhj_tuple *dR, uint64_t nR, const 
     }
     if (!dR || !dS) return fail(ctx, RHJ_ERR_ARG, "null relation pointer");
     int rc;
-    if ((rc = partition_and_plan(ctx, st, (const Tup *) dR, nR, (const Tup *) dS, nS))) return rc;
-    if ((rc = count_phase(ctx, st))) return rc;
+    for (int attempt = 0; attempt < 2; ++attempt) {  // attempt 1 = exact histogram path after an optimistic overflow
+        if ((rc = partition_and_plan(ctx, st, (const Tup *) dR, nR, (const Tup *) dS, nS, attempt == 0))) return rc;
+        rc = count_phase(ctx, st);
+        if (rc != kRetryExact) break;
+    }
+    if (rc) return rc;
     *count = ctx->cur.count;
     return RHJ_OK;
 }
@@ -784,14 +902,18 @@ int rhj_join_device(rhj_ctx *ctx, const rhj_tuple *dR, uint64_t nR, const rhj_tu
     }
     if (!dR || !dS || (!d_out && capacity)) return fail(ctx, RHJ_ERR_ARG, "null pointer");
     int rc;
-    if ((rc = partition_and_plan(ctx, st, (const Tup *) dR, nR, (const Tup *) dS, nS))) return rc;
-    JoinArgs j = join_args(ctx, kScWork0);
-    j.out = (Pair *) d_out;
-    j.capacity = capacity;
-    mark(ctx, st, RHJ_PHASE_JOIN);
-    if ((rc = launch_join<kJoinFused>(ctx, st, j, ctx->cur.item_cap))) return rc;
-    mark(ctx, st, -1);
-    if ((rc = read_scalars(ctx, st))) return rc;
+    for (int attempt = 0; attempt < 2; ++attempt) {  // attempt 1 = exact histogram path after an optimistic overflow
+        if ((rc = partition_and_plan(ctx, st, (const Tup *) dR, nR, (const Tup *) dS, nS, attempt == 0))) return rc;
+        JoinArgs j = join_args(ctx, kScWork0);
+        j.out = (Pair *) d_out;
+        j.capacity = capacity;
+        mark(ctx, st, RHJ_PHASE_JOIN);
+        if ((rc = launch_join<kJoinFused>(ctx, st, j, ctx->cur.item_cap))) return rc;
+        mark(ctx, st, -1);
+        rc = read_scalars(ctx, st);
+        if (rc != kRetryExact) break;
+    }
+    if (rc) return rc;
     *count = ctx->h_scalars[kScCursor];
     if (*count > capacity) return fail(ctx, RHJ_ERR_CAPACITY, "output buffer too small for the fused emitter");
     return RHJ_OK;

@@ -2,6 +2,7 @@
 // units of librhj.so (rhj_api.cu: the join; rhj_query.cu: the join's neighbours on the query path).
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -31,6 +32,7 @@ enum Scalar {
     kScDigSum = 6,
     kScDigXor = 7,
     kScFilt = 8,
+    kScOverflow = 9,  // optimistic pass 1: a partition outgrew its fixed-capacity region
     kScCount = 16
 };
 
@@ -40,6 +42,9 @@ struct rhj_ctx {
     cudaStream_t stream = nullptr;
     std::string err;
     bool hist_agg = false;
+    bool optimistic = true;   // skip the pass-1 histogram when a sampled histogram says it is safe (RHJ_NO_OPT=1 disables)
+    bool force_optimistic = false;  // RHJ_FORCE_OPT=1 (tests): take the optimistic path even when the sample says skewed
+    DevBuf sample;            // sampled pass-1 histogram
     int scatter_mode = 0;     // 0 staged per-thread stores, 1 TMA bulk stores (RHJ_SCATTER_MODE)
     int shard_scatter_mode = 1;  // same choice for the fused partition+shuffle pass: bulk stores make
                                  // larger NVLink packets (measured 4.85 vs 5.17 ms at N=2) (RHJ_SHARD_SCATTER_MODE)
@@ -89,7 +94,7 @@ struct rhj_ctx {
 
 template <typename F>
 inline void for_each_buf(rhj_ctx *c, F f) {
-    DevBuf *bufs[] = {&c->bufA, &c->bufB, &c->tiles, &c->bufB2, &c->shard_meta, &c->zero, &c->meta, &c->items, &c->item_cnt, &c->item_off, &c->filt_cnt,
+    DevBuf *bufs[] = {&c->bufA, &c->bufB, &c->tiles, &c->sample, &c->bufB2, &c->shard_meta, &c->zero, &c->meta, &c->items, &c->item_cnt, &c->item_off, &c->filt_cnt,
                       &c->filt_off, &c->filt_tmp, &c->inR, &c->inS, &c->outP, &c->pin[0], &c->pin[1], &c->pout[0], &c->pout[1],
                       &c->pA, &c->pB, &c->iu_col, &c->iu_pairs, &c->iu_A,
                       &c->iu_B, &c->iu_ep, &c->iu_out};

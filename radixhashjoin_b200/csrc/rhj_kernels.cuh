@@ -52,6 +52,8 @@ struct PartRel {
     u32 group_mask;        // SEG: segments that share counters: group = seg & group_mask (0 = every segment
                            // is its own group).  Sharded pass 2: segment = (source rank, pass-1 partition).
     const void *tiles;     // SEG: optional TileDesc[ntiles] built by k_tile_table (else binary search)
+    const u64 *seg_end;    // SEG: optional [nseg] segment ends (null: seg_off[seg + 1]); fixed-capacity pass-1 layout
+    u64 limit_cap;         // k_scatter<LIMIT>: digit d may only fill [d * limit_cap, (d + 1) * limit_cap) of `out`
 };
 // One 16-byte descriptor per pass-2 tile (k_tile_table): a CTA finds its tuple range with ONE load
 // instead of a 9-step binary search over seg_tile0 -- that dependent-load chain sat in front of
@@ -71,6 +73,7 @@ struct PartArgs {
     int sub_bits;                   // kDigitShard: bits of the pass-1 digit below the rank
     Tup *peer_out[2][kMaxPeers];    // kDigitShard: per relation, the destination ranks' receive buffers (peer memory)
     int shard_local;                // kDigitShard: 1 = write to rel.out (local staging, shipped by DMA afterwards)
+    u32 *overflow;                  // k_scatter<LIMIT>: set to 1 when a digit outgrows its fixed-capacity region
 };
 
 template <int KIND>
@@ -109,20 +112,20 @@ __device__ __forceinline__ bool tile_range(const PartRel &r, u32 lt, u32 &seg, u
     }
     seg = lo;
     beg = r.seg_off[lo] + (u64) (lt - r.seg_tile0[lo]) * kTile;
-    end = min(beg + (u64) kTile, r.seg_off[lo + 1]);
+    end = min(beg + (u64) kTile, r.seg_end ? r.seg_end[lo] : r.seg_off[lo + 1]);
     return true;
 }
 
 // Expands (seg_off, seg_tile0) into one TileDesc per tile; entries past the last tile get len 0.
 // One CTA per segment (+1 that clears the tail up to the host-side bound `ntiles`).
-__global__ void __launch_bounds__(256) k_tile_table(const u64 *seg_off, const u32 *seg_tile0, u32 nseg, u32 ntiles,
-                                                    TileDesc *tiles) {
+__global__ void __launch_bounds__(256) k_tile_table(const u64 *seg_off, const u64 *seg_end, const u32 *seg_tile0, u32 nseg,
+                                                    u32 ntiles, TileDesc *tiles) {
     const u32 seg = blockIdx.x;
     if (seg == nseg) {
         for (u32 t = seg_tile0[nseg] + threadIdx.x; t < ntiles; t += blockDim.x) tiles[t] = TileDesc{0, 0, 0};
         return;
     }
-    const u64 b = seg_off[seg], e = seg_off[seg + 1];
+    const u64 b = seg_off[seg], e = seg_end ? seg_end[seg] : seg_off[seg + 1];
     const u32 t0 = seg_tile0[seg], t1 = seg_tile0[seg + 1];
     for (u32 t = t0 + threadIdx.x; t < t1; t += blockDim.x) {
         u64 beg = b + (u64) (t - t0) * kTile;
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(1024) k_scan_parts(ScanPartsArgs a) {
 //   or, with BULK, by one TMA bulk store (cp.async.bulk shared->global) per run.
 // Algorithmic bytes: 16 read + 16 written per tuple.
 enum ScatterWrite { kWriteStaged = 0, kWriteBulk = 1 };
-template <int KIND, bool SEG, int WMODE, int MAXD>
+template <int KIND, bool SEG, int WMODE, int MAXD, bool LIMIT = false>
 __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(PartArgs a) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     Tup *s_tup = reinterpret_cast<Tup *>(dyn_smem);
@@ -377,6 +380,10 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
                 Tup t = s_tup[i];
                 u32 d = digit<KIND>(t.val, a);
                 Tup *ob = (KIND == kDigitShard && !a.shard_local) ? a.peer_out[ri][d >> a.sub_bits] : r.out;
+                if (LIMIT && s_delta[d] + i >= (u64) (d + 1) * r.limit_cap) {  // the optimistic layout is too small
+                    *a.overflow = 1;
+                    continue;
+                }
                 st_stream(ob + s_delta[d] + i, t);
             }
         }
@@ -633,6 +640,84 @@ __global__ void __launch_bounds__(1024) k_shard_layout(ShardLayoutArgs a) {
     if (tid < nd1) {
         a.off1[tid] = gex;
         if (tid == nd1 - 1) a.off1[nd1] = total;
+    }
+}
+
+// ---- optimistic pass 1: no histogram -----------------------------------------------------------------
+// The pass-1 histogram only serves to place 2^b1 partitions back to back.  When a sampled histogram says
+// the partitions are balanced, pass 1 skips it: every partition gets a fixed-capacity region (expected
+// size + 12.5 % + 8192), the scatter appends with its usual per-digit cursors, and the exact sizes fall
+// out of the cursors afterwards.  A partition that outgrows its region raises `overflow` (nothing is
+// written out of bounds) and the host re-runs the join through the exact histogram path.
+
+// 1/64 sample: one 128-byte granule (8 tuples) out of every 64, at a position that varies per block.
+struct SampleArgs {
+    const Tup *in[2];
+    u64 n[2];
+    int shift;
+    u32 mask, ndig;
+    u32 *hist;  // [2][ndig]
+};
+__global__ void __launch_bounds__(512) k_sample_hist(SampleArgs a) {
+    __shared__ u32 s_h[kMaxDigits];
+    const int ri = blockIdx.y;
+    for (u32 d = threadIdx.x; d < a.ndig; d += blockDim.x) s_h[d] = 0;
+    __syncthreads();
+    const u64 t = (u64) blockIdx.x * blockDim.x + threadIdx.x;
+    const u64 k = t >> 3;
+    const u64 idx = ((k << 6) + ((k * 29) & 63)) * 8 + (t & 7);
+    if (idx < a.n[ri]) {
+        Tup v = ld_stream(a.in[ri] + idx);
+        atomicAdd(&s_h[(hash32(v.val) >> a.shift) & a.mask], 1u);
+    }
+    __syncthreads();
+    for (u32 d = threadIdx.x; d < a.ndig; d += blockDim.x) {
+        u32 c = s_h[d];
+        if (c) atomicAdd(&a.hist[ri * a.ndig + d], c);
+    }
+}
+
+struct FixedArgs {
+    u64 *cursor[2];       // [ndig] scatter cursors, start at d * cap
+    u64 cap[2];
+    u32 ndig;
+    // k_fixed_finish outputs, per relation
+    u64 *seg_beg[2];      // [ndig] d * cap
+    u64 *seg_end[2];      // [ndig] seg_beg + tuples appended
+    u64 *off1[2];         // [ndig + 1] exact prefix of the partition sizes (pass 2 packs its output with it)
+    u32 *tile0[2];        // [ndig + 1]
+    u32 *overflow;
+};
+__global__ void k_fixed_cursors(FixedArgs a) {
+    const int ri = blockIdx.x;
+    for (u32 d = threadIdx.x; d < a.ndig; d += blockDim.x) a.cursor[ri][d] = (u64) d * a.cap[ri];
+}
+__global__ void __launch_bounds__(kMaxDigits) k_fixed_finish(FixedArgs a) {
+    __shared__ u64 s_w[33];
+    const int ri = blockIdx.x;
+    const u32 tid = threadIdx.x;
+    u64 beg = 0, cnt = 0;
+    if (tid < a.ndig) {
+        beg = (u64) tid * a.cap[ri];
+        cnt = a.cursor[ri][tid] - beg;
+        if (cnt > a.cap[ri]) {
+            *a.overflow = 1;
+            cnt = a.cap[ri];
+        }
+    }
+    u64 total, ttotal;
+    u64 ex = block_excl_scan64(cnt, s_w, &total);
+    u64 tl = (cnt + kTile - 1) / kTile;
+    u64 tex = block_excl_scan64(tl, s_w, &ttotal);
+    if (tid < a.ndig) {
+        a.seg_beg[ri][tid] = beg;
+        a.seg_end[ri][tid] = beg + cnt;
+        a.off1[ri][tid] = ex;
+        a.tile0[ri][tid] = (u32) tex;
+        if (tid == a.ndig - 1) {
+            a.off1[ri][a.ndig] = total;
+            a.tile0[ri][a.ndig] = (u32) ttotal;
+        }
     }
 }
 

@@ -468,3 +468,33 @@ def test_pipelined_host_join_equals_oracle(nR, nS, dom, monkeypatch):
         assert len(got) == len(exp)
         assert np.array_equal(O.sort_pairs(got), exp)
     eng.close()
+
+
+# ---- optimistic pass 1 (no histogram when a sampled histogram says the partitions are balanced) ----------
+def test_optimistic_pass1_taken_and_correct(engine):
+    w = W.uniform_unique(23, DEV)
+    out, n = engine.join_device(w.R, w.S, capacity=w.expected[0], emit=EMIT_FUSED)
+    assert (n,) + engine.pairs_digest(out)[1:] == tuple(w.expected)
+    assert engine.last_plan()["optimistic_pass1"] == 1
+    z = W.zipf_probe(23, DEV)                      # a hot key: the sample must send this down the exact path
+    out, n = engine.join_device(z.R, z.S, capacity=z.expected[0], emit=EMIT_FUSED)
+    assert (n,) + engine.pairs_digest(out)[1:] == tuple(z.expected)
+    assert engine.last_plan()["optimistic_pass1"] == 0
+
+
+@pytest.mark.parametrize("emit", [EMIT_FUSED, EMIT_COUNT_THEN_WRITE])
+def test_optimistic_overflow_falls_back_to_exact_path(emit, monkeypatch):
+    """RHJ_FORCE_OPT makes skewed data take the fixed-capacity layout: a partition overflows, nothing is
+    written out of bounds, and the join is re-run through the histogram path -- same result."""
+    from radixhashjoin_b200 import RadixHashJoin
+    monkeypatch.setenv("RHJ_FORCE_OPT", "1")
+    eng = RadixHashJoin(0)
+    z = W.zipf_probe(22, DEV)
+    out, n = eng.join_device(z.R, z.S, capacity=z.expected[0], emit=emit)
+    assert (n,) + eng.pairs_digest(out)[1:] == tuple(z.expected)
+    assert eng.last_plan()["optimistic_pass1"] == 0     # the plan that produced the result is the exact one
+    u = W.uniform_unique(22, DEV)
+    out, n = eng.join_device(u.R, u.S, capacity=u.expected[0], emit=emit)
+    assert (n,) + eng.pairs_digest(out)[1:] == tuple(u.expected)
+    assert eng.last_plan()["optimistic_pass1"] == 1
+    eng.close()
