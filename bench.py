@@ -186,8 +186,10 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"uniform_unique_u64 2^{args.log2n} x 2^{args.log2n} per GPU "
-                                   f"(BASELINE.json configs[1]); each step a bounded 2^{log2n} x 2^{log2n} sample"},
+            "config": {"workload": f"uniform_unique_2^{args.log2n}x2^{args.log2n}", "tuples_per_gpu": 2 << args.log2n,
+                       "tuple_bytes": 16,
+                       "sample_per_step": f"2^{log2n} x 2^{log2n} tuples of the same generator (the reference's throughput is "
+                                          "flat in size: BASELINE.md 2.2)"},
             "cpu_baseline": dict(info, value=val, unit=UNIT),
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
