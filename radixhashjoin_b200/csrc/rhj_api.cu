@@ -105,7 +105,7 @@ int launch_scatter(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, b
 
 template <int MODE>
 int launch_join(rhj_ctx *ctx, cudaStream_t st, const JoinArgs &a, u32 item_cap) {
-    u32 grid = std::min<u32>(std::max<u32>(item_cap, 1), (u32) ctx->num_sms * 2);
+    u32 grid = std::min<u32>(std::max<u32>(item_cap, 1), (u32) ctx->num_sms * RHJ_JOIN_MINBLOCKS);
     CK(set_smem(k_join<MODE>, kJoinSmem));
     k_join<MODE><<<grid, kJoinThreads, kJoinSmem, st>>>(a);
     CK(cudaGetLastError());

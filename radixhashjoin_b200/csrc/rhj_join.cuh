@@ -4,16 +4,17 @@
 // bucket-chain index with `payload % prime` hashing, one pthread job per bucket) and the
 // add_result / addAll page list (Result.cpp:21-35,78-84,111-121).
 //
-// Persistent CTAs, two per SM, pull work items (partition p, probe chunk c) from a global
-// counter.  For each build chunk of <= 4096 tuples of partition p:
+// Persistent CTAs of 384 threads, three per SM (72 KiB of shared memory each: measured, the third
+// CTA hides the barriers and latencies of the other two: 2.03 -> 1.78 ms), pull work items
+// (partition p, probe chunk c) from a global counter.  For each build chunk of <= 2560 tuples:
 //   - one elected thread TMA-bulk-loads the chunk's tuples verbatim into shared memory
 //     (cp.async.bulk + mbarrier); meanwhile every thread issues the coalesced 16-B loads of its
 //     first 4 probe tuples and clears the slot table, so both global latencies overlap;
 //   - build: every staged tuple claims a slot of the open-addressing table (u32 index into the
-//     staged tuples, linear probing, shared-memory atomicCAS; 8192 slots => load factor <= 0.5,
+//     staged tuples, linear probing, shared-memory atomicCAS; 8192 slots => load factor <= 0.31,
 //     0.25 on average -- measured: the warp pays for its longest probe, load 0.5 costs +40 %).
 //     A claim that walks past an equal value flags the chunk as "has duplicate keys";
-//   - probe: rounds of 2048 probe tuples.  Unique-key chunks stop at the first hit;
+//   - probe: rounds of 1536 probe tuples.  Unique-key chunks stop at the first hit;
 //     duplicate-key chunks count, then re-walk to write;
 //   - emit: matches of a round are ranked with ballots + one shared atomic per warp; one thread
 //     reserves the round's output range (FUSED: one global atomic per round; WRITE: running
@@ -29,15 +30,33 @@
 
 namespace rhj {
 
-constexpr int kJoinThreads = 512;
-constexpr int kJoinItems = 4;                        // probe tuples per thread per round
-constexpr int kRound = kJoinThreads * kJoinItems;    // 2048 probe tuples per round
-constexpr u32 kBuildCap = 4096;                      // build tuples per shared-memory table (64 KiB)
+#ifndef RHJ_JOIN_THREADS
+#define RHJ_JOIN_THREADS 384
+#endif
+#ifndef RHJ_JOIN_CAP
+#define RHJ_JOIN_CAP 2560
+#endif
+#ifndef RHJ_JOIN_SLOTS
+#define RHJ_JOIN_SLOTS 8192
+#endif
+#ifndef RHJ_JOIN_TARGET
+#define RHJ_JOIN_TARGET 2048
+#endif
+#ifndef RHJ_JOIN_MINBLOCKS
+#define RHJ_JOIN_MINBLOCKS 3
+#endif
+constexpr int kJoinThreads = RHJ_JOIN_THREADS;
+#ifndef RHJ_JOIN_ITEMS
+#define RHJ_JOIN_ITEMS 4
+#endif
+constexpr int kJoinItems = RHJ_JOIN_ITEMS;           // probe tuples per thread per round
+constexpr int kRound = kJoinThreads * kJoinItems;    // probe tuples per round
+constexpr u32 kBuildCap = RHJ_JOIN_CAP;              // build tuples per shared-memory table
 typedef u32 slot_t;
-constexpr u32 kSlots = 8192;                         // open-addressing slots (u32 index) (32 KiB)
+constexpr u32 kSlots = RHJ_JOIN_SLOTS;               // open-addressing slots (u32 index)
 constexpr slot_t kSlotEmpty = 0xFFFFFFFFu;
 constexpr u32 kProbeChunk = 16384;                   // probe tuples per work item
-constexpr u32 kTargetBuildPerPart = 2048;            // radix bits are chosen for this average
+constexpr u32 kTargetBuildPerPart = RHJ_JOIN_TARGET; // radix bits are chosen for this average
 constexpr size_t kJoinSmemBytes = (size_t) kBuildCap * sizeof(Tup) + (size_t) kSlots * sizeof(slot_t);
 
 struct Item {
@@ -66,7 +85,7 @@ struct JoinArgs {
 __device__ __forceinline__ u32 slot_of(u64 v) { return hash32(v) & (kSlots - 1); }
 
 template <int MODE>
-__global__ void __launch_bounds__(kJoinThreads, 2) k_join(JoinArgs a) {
+__global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join(JoinArgs a) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     Tup *s_tup = reinterpret_cast<Tup *>(dyn_smem);
     slot_t *s_slot = reinterpret_cast<slot_t *>(dyn_smem + (size_t) kBuildCap * sizeof(Tup));
