@@ -804,7 +804,10 @@ int rhj_reserve(rhj_ctx *ctx, uint64_t nR, uint64_t nS) {
     Meta m;
     int rc;
     if ((rc = layout_meta(ctx, pl.nparts, m))) return rc;
-    if (pl.bits > 0 && (rc = ensure(ctx, ctx->bufA, (pl.nB + pl.nP) * sizeof(Tup)))) return rc;
+    size_t a_tuples = pl.nB + pl.nP;
+    if (pl.b2 > 0 && ctx->optimistic)  // the optimistic pass-1 layout gives every partition a fixed region with headroom
+        a_tuples = std::max<size_t>(a_tuples, ((size_t) 1 << pl.b1) * (fixed_cap(pl.nB, 1u << pl.b1) + fixed_cap(pl.nP, 1u << pl.b1)));
+    if (pl.bits > 0 && (rc = ensure(ctx, ctx->bufA, a_tuples * sizeof(Tup)))) return rc;
     if (pl.b2 > 0 && (rc = ensure(ctx, ctx->bufB, (pl.nB + pl.nP) * sizeof(Tup)))) return rc;
     u64 cap = (u64) pl.nparts + pl.nP / kProbeChunk + 2;
     if ((rc = ensure(ctx, ctx->items, cap * sizeof(Item)))) return rc;
