@@ -254,7 +254,8 @@ def run_b200(args, rank, world, local_rank):
         if args.shuffle == "dma":
             # pass 1 partitions on (rank | sub-digit) into staging; the copy engines ship one chunk per peer
             # while the SMs partition the other relation; pass 2 runs on the received (source, partition) pieces
-            dj = DmaShardedJoin(eng, world, rank, n_local * world, n_local * world, n_local, slack)
+            dj = DmaShardedJoin(eng, world, rank, n_local * world, n_local * world, n_local, slack,
+                                split_probe=args.split_probe)
             del recvR, recvS
 
             def step():
@@ -451,6 +452,7 @@ def main():
     ap.add_argument("--shuffle", default="dma", choices=["dma", "stores", "nccl"],
                     help="multi-GPU exchange: pass-1 chunks shipped by the copy engines (default), pass-1 scatter storing "
                          "straight into peer memory, or rank partition + NCCL all-to-all")
+    ap.add_argument("--split-probe", action="store_true", help="dma shuffle: ship the probe relation in two halves (measured slower)")
     ap.add_argument("--no-small-work", action="store_true")
     ap.add_argument("--small-work-ref", action="store_true", help="also time the unmodified reference program (minutes)")
     ap.add_argument("--no-e2e", action="store_true")

@@ -220,6 +220,12 @@ int rhj_shardx_pass2_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int rel, c
                             void *stream);
 int rhj_shardx_join_device(rhj_ctx *ctx, const rhj_shard_plan *plan, rhj_pair *d_out, uint64_t capacity, uint64_t *count,
                            void *stream);
+/* Slots: `rel` above is 0 = R, 1 = S, or 2 = the second half of the PROBE relation (the larger one) when the
+ * caller ships it in two halves.  rhj_shardx_join_slots_device joins one (build slot, probe slot) pair; with
+ * first = 0 it appends to the previous call's result, so the join of the first half overlaps the transfer of
+ * the second.  *count = pairs emitted so far. */
+int rhj_shardx_join_slots_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int build_slot, int probe_slot, int first,
+                                 rhj_pair *d_out, uint64_t capacity, uint64_t *count, void *stream);
 
 /* ---- introspection for benchmarks ------------------------------------------------------------ */
 

@@ -280,6 +280,18 @@ class RadixHashJoin:
         self._ck(rc)
         return out[:cnt.value], int(cnt.value)
 
+    def shardx_join_slots(self, plan, build_slot, probe_slot, first, out, stream=None):
+        """join one (build slot, probe slot) pair; first=False appends to the previous call's result"""
+        cnt = ctypes.c_uint64()
+        rc = self._lib.rhj_shardx_join_slots_device(self._ctx, ctypes.byref(plan), build_slot, probe_slot, 1 if first else 0,
+                                                    _ptr(out), out.shape[0], ctypes.byref(cnt), self._stream(stream))
+        if rc == 4:
+            e = RhjError(rc, self._lib.rhj_last_error(self._ctx).decode())
+            e.needed = int(cnt.value)
+            raise e
+        self._ck(rc)
+        return out[:cnt.value], int(cnt.value)
+
     # ---- neighbours on the query path ----------------------------------------------------------
     def filter(self, col, op, constant, rowids=None, stream=None):
         """Query::run_filters predicate (Query.cpp:94-146): surviving row ids, input order kept."""

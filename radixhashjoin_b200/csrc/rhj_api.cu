@@ -165,20 +165,20 @@ int build_tile_tables(rhj_ctx *ctx, cudaStream_t st, PartArgs &b, int nrel, int 
         need[i] = ((size_t) b.rel[i].ntiles + 1) * sizeof(TileDesc);
         total += need[i];
     }
-    // lone relations (sharded join: R and S arrive separately) use fixed halves so they never alias
+    // lone relations (sharded join: the slots arrive separately) use fixed thirds so they never alias
     size_t half = 0;
     if (nrel == 1) {
         half = need[0];
-        total = 2 * half;
+        total = 3 * half;
     }
     if (total > ctx->tiles.cap) {
         // growing would free a table a previously launched kernel may still read: finish that work first
         CK(cudaStreamSynchronize(st));
         int rc = ensure(ctx, ctx->tiles, std::max(total, 2 * ctx->tiles.cap));
         if (rc) return rc;
-        if (nrel == 1) half = ctx->tiles.cap / 2 / sizeof(TileDesc) * sizeof(TileDesc);
+        if (nrel == 1) half = ctx->tiles.cap / 3 / sizeof(TileDesc) * sizeof(TileDesc);
     } else if (nrel == 1) {
-        half = ctx->tiles.cap / 2 / sizeof(TileDesc) * sizeof(TileDesc);
+        half = ctx->tiles.cap / 3 / sizeof(TileDesc) * sizeof(TileDesc);
     }
     char *base = (char *) ctx->tiles.p + (nrel == 1 ? (size_t) slot * half : 0);
     for (int i = 0; i < nrel; ++i) {
@@ -1239,6 +1239,40 @@ int layout_shard_meta(rhj_ctx *ctx, ShardMeta &sm) {
     return RHJ_OK;
 }
 
+// Per-slot view of the sharded join's metadata.  Slots 0 / 1 are relations R / S (the arrays of
+// Meta / ShardMeta); slot 2 is the second half of the PROBE relation when it is shipped in two halves
+// so that the join of the first half overlaps the transfer of the second.
+struct SlotArrays {
+    u64 *cur1, *loc_off, *seg_off, *off1, *hist2, *cur2, *off2;
+    u32 *tile0;
+    DevBuf *out;
+};
+int slot_arrays(rhj_ctx *ctx, u32 nparts, int slot, SlotArrays &a) {
+    Meta m;
+    ShardMeta sm;
+    int rc;
+    if ((rc = layout_meta(ctx, nparts, m))) return rc;
+    if ((rc = layout_shard_meta(ctx, sm))) return rc;
+    if (slot < 2) {
+        a = SlotArrays{m.cur1[slot], sm.loc_off[slot], sm.seg_off[slot], m.off1[slot], m.hist2[slot], m.cur2[slot], m.off2[slot],
+                       m.tile0[slot], slot ? &ctx->bufB2 : &ctx->bufB};
+        return RHJ_OK;
+    }
+    size_t n = 3 * (size_t) nparts + 1 + 5 * (size_t) (kMaxDigits + 2);
+    if ((rc = ensure(ctx, ctx->shard_meta2, n * 8))) return rc;
+    u64 *q = (u64 *) ctx->shard_meta2.p;
+    a.hist2 = q; q += nparts;          // first: begin() zeroes exactly this part
+    a.off2 = q; q += nparts + 1;
+    a.cur2 = q; q += nparts;
+    a.cur1 = q; q += kMaxDigits + 2;
+    a.loc_off = q; q += kMaxDigits + 2;
+    a.seg_off = q; q += kMaxDigits + 2;
+    a.off1 = q; q += kMaxDigits + 2;
+    a.tile0 = (u32 *) q;               // (kMaxDigits + 2) u32 fit the remaining kMaxDigits + 2 u64... sized above with slack
+    a.out = &ctx->bufB3;
+    return RHJ_OK;
+}
+
 Plan shard_local_plan(const rhj_shard_plan *sp, u64 nR, u64 nS) {
     Plan pl{};
     pl.build_is_S = sp->build_is_S;
@@ -1268,38 +1302,38 @@ int rhj_shardx_begin(rhj_ctx *ctx, const rhj_shard_plan *sp, void *stream) {
     ctx->info.build_is_S = sp->build_is_S;
     ctx->info.n_partitions = 1u << sp->bits_total;
     Meta m;
-    ShardMeta sm;
     int rc;
     if ((rc = layout_meta(ctx, 1u << sp->bits_total, m))) return rc;
-    if ((rc = layout_shard_meta(ctx, sm))) return rc;
     CK(cudaMemsetAsync(ctx->zero.p, 0, m.zero_bytes, st));
-    ctx->shard_n[0] = ctx->shard_n[1] = 0;
+    SlotArrays s2;
+    if ((rc = slot_arrays(ctx, 1u << sp->bits_total, 2, s2))) return rc;
+    CK(cudaMemsetAsync(s2.hist2, 0, ((size_t) 1 << sp->bits_total) * 8, st));
+    ctx->shard_n[0] = ctx->shard_n[1] = ctx->shard_n[2] = 0;
     return RHJ_OK;
 }
 
-// Pass 1 of relation `rel` (0 = R, 1 = S): histogram on (destination rank | sub-digit) into d_hist
-// [world << bits_pass1] (the caller all-gathers it), prefix sum, scatter into the local staging buffer
-// d_stage[n], which ends up ordered by destination rank, then by pass-1 partition.  Enqueues only.
+// Pass 1 of slot `rel` (0 = R, 1 = S, 2 = second half of the probe relation): histogram on
+// (destination rank | sub-digit) into d_hist[world << bits_pass1] (the caller all-gathers it), prefix
+// sum, scatter into the local staging buffer d_stage[n], which ends up ordered by destination rank,
+// then by pass-1 partition.  Enqueues only.
 int rhj_shardx_pass1_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_in, uint64_t n,
                             rhj_tuple *d_stage, uint64_t *d_hist, void *stream) {
-    if (!ctx || !sp || !d_hist || rel < 0 || rel > 1 || (n && (!d_in || !d_stage))) return RHJ_ERR_ARG;
+    if (!ctx || !sp || !d_hist || rel < 0 || rel > 2 || (n && (!d_in || !d_stage))) return RHJ_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = pick(ctx, stream);
-    Meta m;
-    ShardMeta sm;
+    SlotArrays sl;
     int rc;
-    if ((rc = layout_meta(ctx, 1u << sp->bits_total, m))) return rc;
-    if ((rc = layout_shard_meta(ctx, sm))) return rc;
+    if ((rc = slot_arrays(ctx, 1u << sp->bits_total, rel, sl))) return rc;
     PartArgs a = shard_args(sp);
     a.shard_local = 1;
     CK(cudaMemsetAsync(d_hist, 0, (size_t) a.ndig * sizeof(u64), st));
-    a.rel[0] = PartRel{(const Tup *) d_in, (Tup *) d_stage, n, (u64 *) d_hist, m.cur1[rel], nullptr, nullptr, 1, tiles_of(n)};
+    a.rel[0] = PartRel{(const Tup *) d_in, (Tup *) d_stage, n, (u64 *) d_hist, sl.cur1, nullptr, nullptr, 1, tiles_of(n)};
     if (rel == 0) mark(ctx, st, RHJ_PHASE_HIST1);
     if ((rc = launch_hist(ctx, st, a, kDigitShard, false))) return rc;
     ScanDigitsArgs sd{};
     sd.hist[0] = sd.hist[1] = (const u64 *) d_hist;
-    sd.off[0] = sd.off[1] = sm.loc_off[rel];
-    sd.cursor[0] = sd.cursor[1] = m.cur1[rel];
+    sd.off[0] = sd.off[1] = sl.loc_off;
+    sd.cursor[0] = sd.cursor[1] = sl.cur1;
     sd.tile0[0] = sd.tile0[1] = nullptr;
     sd.ndig = a.ndig;
     k_scan_digits<<<1, kMaxDigits, 0, st>>>(sd);
@@ -1309,7 +1343,7 @@ int rhj_shardx_pass1_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, con
     return RHJ_OK;
 }
 
-// Layout of relation `rel` from the all-gathered histograms d_all_hist[world][world << bits_pass1]:
+// Layout of slot `rel` from the all-gathered histograms d_all_hist[world][world << bits_pass1]:
 // device side, the piece tables pass 2 needs; host side, what to ship where:
 //   send_off[d], send_cnt[d]  this rank's chunk for destination d inside its staging buffer (tuples)
 //   dst_off[d]                where that chunk starts inside destination d's receive buffer
@@ -1318,21 +1352,21 @@ int rhj_shardx_pass1_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, con
 int rhj_shardx_layout_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rank, int rel, const uint64_t *d_all_hist,
                              uint64_t *send_off, uint64_t *send_cnt, uint64_t *dst_off, uint64_t *recv_total,
                              void *stream) {
-    if (!ctx || !sp || !d_all_hist || !send_off || !send_cnt || !dst_off || !recv_total || rel < 0 || rel > 1 || rank < 0 ||
+    if (!ctx || !sp || !d_all_hist || !send_off || !send_cnt || !dst_off || !recv_total || rel < 0 || rel > 2 || rank < 0 ||
         rank >= (int) sp->world)
         return RHJ_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = pick(ctx, stream);
-    Meta m;
+    SlotArrays sl;
     ShardMeta sm;
     int rc;
-    if ((rc = layout_meta(ctx, 1u << sp->bits_total, m))) return rc;
+    if ((rc = slot_arrays(ctx, 1u << sp->bits_total, rel, sl))) return rc;
     if ((rc = layout_shard_meta(ctx, sm))) return rc;
     ShardLayoutArgs a{};
     a.all_hist = (const u64 *) d_all_hist;
-    a.seg_off = sm.seg_off[rel];
-    a.seg_tile0 = m.tile0[rel];
-    a.off1 = m.off1[rel];
+    a.seg_off = sl.seg_off;
+    a.seg_tile0 = sl.tile0;
+    a.off1 = sl.off1;
     a.tot = sm.tot;
     a.world = sp->world;
     a.rank = (u32) rank;
@@ -1343,7 +1377,7 @@ int rhj_shardx_layout_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rank, i
     const u32 W = sp->world, nd1 = 1u << sp->bits_pass1;
     static thread_local u64 h_tot[kMaxPeers * kMaxPeers], h_loc[kMaxDigits + 1];
     CK(cudaMemcpyAsync(h_tot, sm.tot, (size_t) W * W * 8, cudaMemcpyDeviceToHost, st));
-    CK(cudaMemcpyAsync(h_loc, sm.loc_off[rel], ((size_t) (W << sp->bits_pass1) + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_loc, sl.loc_off, ((size_t) (W << sp->bits_pass1) + 1) * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     u64 total = 0;
     for (u32 d = 0; d < W; ++d) {
@@ -1359,38 +1393,35 @@ int rhj_shardx_layout_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rank, i
     return RHJ_OK;
 }
 
-// Pass 2 of relation `rel` over what this rank received (d_recv[n_recv], world << bits_pass1 pieces):
-// histogram, per-partition offsets, scatter into the context's final partition buffer.  Enqueues only.
+// Pass 2 of slot `rel` over what this rank received (d_recv[n_recv], world << bits_pass1 pieces):
+// histogram, per-partition offsets, scatter into the slot's final partition buffer.  Enqueues only.
 int rhj_shardx_pass2_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_recv, uint64_t n_recv,
                             void *stream) {
-    if (!ctx || !sp || rel < 0 || rel > 1 || (n_recv && !d_recv)) return RHJ_ERR_ARG;
+    if (!ctx || !sp || rel < 0 || rel > 2 || (n_recv && !d_recv)) return RHJ_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = pick(ctx, stream);
-    Meta m;
-    ShardMeta sm;
+    SlotArrays sl;
     int rc;
-    if ((rc = layout_meta(ctx, 1u << sp->bits_total, m))) return rc;
-    if ((rc = layout_shard_meta(ctx, sm))) return rc;
+    if ((rc = slot_arrays(ctx, 1u << sp->bits_total, rel, sl))) return rc;
     ctx->shard_recv[rel] = (const Tup *) d_recv;
-    DevBuf &out = rel ? ctx->bufB2 : ctx->bufB;
-    if ((rc = ensure(ctx, out, std::max<u64>(n_recv, 1) * sizeof(Tup)))) return rc;
+    if ((rc = ensure(ctx, *sl.out, std::max<u64>(n_recv, 1) * sizeof(Tup)))) return rc;
     const u32 nd1 = 1u << sp->bits_pass1, npieces = sp->world << sp->bits_pass1;
     PartArgs b{};
     // bits_pass2 == 0 (tiny relations): a one-digit pass that only merges the pieces of a partition
     b.shift = std::min(31, 32 - (int) sp->bits_total);
     b.mask = (1u << sp->bits_pass2) - 1;
     b.ndig = 1u << sp->bits_pass2;
-    b.rel[0] = PartRel{(const Tup *) d_recv, (Tup *) out.p, n_recv, m.hist2[rel], m.cur2[rel], sm.seg_off[rel], m.tile0[rel],
+    b.rel[0] = PartRel{(const Tup *) d_recv, (Tup *) sl.out->p, n_recv, sl.hist2, sl.cur2, sl.seg_off, sl.tile0,
                        npieces, tiles_of(n_recv) + npieces, nd1 - 1};
     if (nd1 == 1) b.rel[0].group_mask = 0x80000000u;  // every piece is partition 0: (seg & mask) == 0
     if ((rc = build_tile_tables(ctx, st, b, 1, rel))) return rc;
     if (rel == 0) mark(ctx, st, RHJ_PHASE_HIST2);
     if ((rc = launch_hist(ctx, st, b, kDigitHash, true))) return rc;
     ScanPartsRelArgs sr{};
-    sr.hist2 = m.hist2[rel];
-    sr.off1 = m.off1[rel];
-    sr.off2 = m.off2[rel];
-    sr.cursor2 = m.cur2[rel];
+    sr.hist2 = sl.hist2;
+    sr.off1 = sl.off1;
+    sr.off2 = sl.off2;
+    sr.cursor2 = sl.cur2;
     sr.nseg = nd1;
     sr.ndig = b.ndig;
     k_scan_parts_rel<<<nd1, kMaxDigits, 0, st>>>(sr);
@@ -1400,54 +1431,72 @@ int rhj_shardx_pass2_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, con
     return RHJ_OK;
 }
 
-// Work-item plan + build/probe + fused emit over the final partitions of both relations.
-int rhj_shardx_join_device(rhj_ctx *ctx, const rhj_shard_plan *sp, rhj_pair *d_out, uint64_t capacity, uint64_t *count,
-                           void *stream) {
-    if (!ctx || !sp || !count) return RHJ_ERR_ARG;
-    *count = 0;
+// Work-item plan + build/probe + fused emit over the final partitions of a (build slot, probe slot)
+// pair.  `first` = 1 starts a new result (the output cursor is reset); 0 appends to it, which is how
+// the two halves of a probe relation are joined one after the other.  *count = pairs emitted so far.
+int rhj_shardx_join_slots_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int build_slot, int probe_slot, int first,
+                                 rhj_pair *d_out, uint64_t capacity, uint64_t *count, void *stream) {
+    if (!ctx || !sp || !count || build_slot < 0 || build_slot > 2 || probe_slot < 0 || probe_slot > 2 || build_slot == probe_slot)
+        return RHJ_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = pick(ctx, stream);
-    const u64 nR = ctx->shard_n[0], nS = ctx->shard_n[1];
-    if (nR == 0 || nS == 0) return RHJ_OK;
-    Plan pl = shard_local_plan(sp, nR, nS);
+    const u64 nB = ctx->shard_n[build_slot], nP = ctx->shard_n[probe_slot];
+    const u32 nparts = 1u << sp->bits_total;
     Meta m;
+    SlotArrays sb, spb;
     int rc;
-    if ((rc = layout_meta(ctx, pl.nparts, m))) return rc;
-    const int bi = pl.build_is_S ? 1 : 0;
-    u64 cap64 = (u64) pl.nparts + pl.nP / kProbeChunk + 2;
-    if (cap64 > 0x7fffffffull) return fail(ctx, RHJ_ERR_ARG, "relation too large for the work-item table");
-    u32 item_cap = (u32) cap64;
-    if ((rc = ensure(ctx, ctx->items, (size_t) item_cap * sizeof(Item)))) return rc;
-    mark(ctx, st, RHJ_PHASE_PLAN);
-    PlanPartsArgs pa{};
-    pa.offB = m.off2[bi];
-    pa.offP = m.off2[bi ^ 1];
-    pa.ndig = std::min<u32>(pl.nparts, kMaxDigits);
-    pa.items = (Item *) ctx->items.p;
-    pa.item_cap = item_cap;
-    pa.nitems = (u32 *) (m.scalars + kScNItems);
-    pa.err = (u32 *) (m.scalars + kScErr);
-    k_plan_parts<<<pl.nparts / pa.ndig, kMaxDigits, 0, st>>>(pa);
-    CK(cudaGetLastError());
-    ctx->info.kernel_launches++;
-    ctx->cur.valid = true;
-    ctx->cur.build = (const Tup *) (bi ? ctx->bufB2.p : ctx->bufB.p);
-    ctx->cur.probe = (const Tup *) (bi ? ctx->bufB.p : ctx->bufB2.p);
-    ctx->cur.offB = m.off2[bi];
-    ctx->cur.offP = m.off2[bi ^ 1];
-    ctx->cur.nparts = pl.nparts;
-    ctx->cur.item_cap = item_cap;
-    ctx->cur.build_is_S = pl.build_is_S;
-    JoinArgs j = join_args(ctx, kScWork0);
-    j.out = (Pair *) d_out;
-    j.capacity = capacity;
-    mark(ctx, st, RHJ_PHASE_JOIN);
-    if ((rc = launch_join<kJoinFused>(ctx, st, j, item_cap))) return rc;
-    mark(ctx, st, -1);
+    if ((rc = layout_meta(ctx, nparts, m))) return rc;
+    if ((rc = slot_arrays(ctx, nparts, build_slot, sb))) return rc;
+    if ((rc = slot_arrays(ctx, nparts, probe_slot, spb))) return rc;
+    // per-launch scalars start from zero; the output cursor only when a new result starts
+    CK(cudaMemsetAsync(m.scalars + kScWork0, 0, 8, st));
+    CK(cudaMemsetAsync(m.scalars + kScNItems, 0, 8, st));
+    if (first) CK(cudaMemsetAsync(m.scalars + kScCursor, 0, 8, st));
+    if (nB && nP) {
+        u64 cap64 = (u64) nparts + nP / kProbeChunk + 2;
+        if (cap64 > 0x7fffffffull) return fail(ctx, RHJ_ERR_ARG, "relation too large for the work-item table");
+        u32 item_cap = (u32) cap64;
+        if ((rc = ensure(ctx, ctx->items, (size_t) item_cap * sizeof(Item)))) return rc;
+        mark(ctx, st, RHJ_PHASE_PLAN);
+        PlanPartsArgs pa{};
+        pa.offB = sb.off2;
+        pa.offP = spb.off2;
+        pa.ndig = std::min<u32>(nparts, kMaxDigits);
+        pa.items = (Item *) ctx->items.p;
+        pa.item_cap = item_cap;
+        pa.nitems = (u32 *) (m.scalars + kScNItems);
+        pa.err = (u32 *) (m.scalars + kScErr);
+        k_plan_parts<<<nparts / pa.ndig, kMaxDigits, 0, st>>>(pa);
+        CK(cudaGetLastError());
+        ctx->info.kernel_launches++;
+        ctx->cur.valid = true;
+        ctx->cur.build = (const Tup *) sb.out->p;
+        ctx->cur.probe = (const Tup *) spb.out->p;
+        ctx->cur.offB = sb.off2;
+        ctx->cur.offP = spb.off2;
+        ctx->cur.nparts = nparts;
+        ctx->cur.item_cap = item_cap;
+        // slot 0 is R; slots 1 and 2 hold S tuples unless S is the (unsplit) build side
+        ctx->cur.build_is_S = build_slot != 0;
+        JoinArgs j = join_args(ctx, kScWork0);
+        j.out = (Pair *) d_out;
+        j.capacity = capacity;
+        mark(ctx, st, RHJ_PHASE_JOIN);
+        if ((rc = launch_join<kJoinFused>(ctx, st, j, item_cap))) return rc;
+        mark(ctx, st, -1);
+    }
     if ((rc = read_scalars(ctx, st))) return rc;
     *count = ctx->h_scalars[kScCursor];
     if (*count > capacity) return fail(ctx, RHJ_ERR_CAPACITY, "output buffer too small for the fused emitter");
     return RHJ_OK;
+}
+
+// Both relations whole: slots 0 (R) and 1 (S).
+int rhj_shardx_join_device(rhj_ctx *ctx, const rhj_shard_plan *sp, rhj_pair *d_out, uint64_t capacity, uint64_t *count,
+                           void *stream) {
+    if (!sp) return RHJ_ERR_ARG;
+    const int bi = sp->build_is_S ? 1 : 0;
+    return rhj_shardx_join_slots_device(ctx, sp, bi, bi ^ 1, 1, d_out, capacity, count, stream);
 }
 
 }  // extern "C"

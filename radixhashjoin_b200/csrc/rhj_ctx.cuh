@@ -51,7 +51,8 @@ struct rhj_ctx {
 
     DevBuf bufA, bufB;        // pass-1 / pass-2 partitioned tuples (build side first, then probe side)
     DevBuf tiles;             // TileDesc tables of the second pass (both relations)
-    DevBuf bufB2;             // sharded join: pass-2 output of relation S (relations arrive separately)
+    DevBuf bufB2, bufB3;      // sharded join: pass-2 outputs of slots 1 and 2 (relations / probe halves arrive separately)
+    DevBuf shard_meta2;       // sharded join: metadata of slot 2 (second half of the probe relation)
     DevBuf shard_meta;        // sharded join: local offsets, piece tables, ship matrix
     DevBuf zero;              // hist1 | hist2 | scalars   (memset to 0 per call)
     DevBuf meta;              // offsets, cursors, tile tables
@@ -81,8 +82,8 @@ struct rhj_ctx {
         u64 count = 0;
     } cur;
     rhj_plan_info info{};
-    u64 shard_n[2] = {0, 0};               // sharded join: tuples received per relation
-    const Tup *shard_recv[2] = {nullptr, nullptr};
+    u64 shard_n[3] = {0, 0, 0};            // sharded join: tuples received per slot
+    const Tup *shard_recv[3] = {nullptr, nullptr, nullptr};
 
     // optional per-phase timing (rhj_set_profiling)
     bool profiling = false;
@@ -94,7 +95,7 @@ struct rhj_ctx {
 
 template <typename F>
 inline void for_each_buf(rhj_ctx *c, F f) {
-    DevBuf *bufs[] = {&c->bufA, &c->bufB, &c->tiles, &c->sample, &c->bufB2, &c->shard_meta, &c->zero, &c->meta, &c->items, &c->item_cnt, &c->item_off, &c->filt_cnt,
+    DevBuf *bufs[] = {&c->bufA, &c->bufB, &c->tiles, &c->sample, &c->bufB2, &c->bufB3, &c->shard_meta2, &c->shard_meta, &c->zero, &c->meta, &c->items, &c->item_cnt, &c->item_off, &c->filt_cnt,
                       &c->filt_off, &c->filt_tmp, &c->inR, &c->inS, &c->outP, &c->pin[0], &c->pin[1], &c->pout[0], &c->pout[1],
                       &c->pA, &c->pB, &c->iu_col, &c->iu_pairs, &c->iu_A,
                       &c->iu_B, &c->iu_ep, &c->iu_out};

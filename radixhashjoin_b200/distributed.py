@@ -154,13 +154,19 @@ class DmaShardedJoin:
     Pass 1 of the join partitions each local shard on (destination rank | sub-digit) into a local
     staging buffer; the chunk for every destination is contiguous and already pass-1 partitioned, so
     the copy engines ship it with ONE peer copy per destination over NVLink / NVSwitch (full-size
-    packets, no SM time) straight into the destination's symmetric receive buffer.  Relation S is
-    partitioned while R is in flight, and R's second pass runs while S is in flight; the join kernel
-    starts when S's second pass is done.  torch.distributed supplies the plumbing: two small
-    all-gathers (histograms), symmetric-memory rendezvous for the peer buffers, device-side barriers.
+    packets, no SM time) straight into the destination's symmetric receive buffer.  The pipeline per
+    join: the build relation is partitioned and shipped first; the probe relation is partitioned while
+    it is in flight and shipped next; pass 2 of a relation runs as soon as it has landed, i.e. while the
+    other one is still on the wire.  With split_probe=True the probe relation goes in two row halves
+    (slots) and the first half is joined while the second is in flight -- implemented and verified, but
+    measured slower on 2 and 8 B200s (the extra kernels slow the concurrent peer copies and every half
+    re-builds the tables), so it is off by default.  torch.distributed supplies the plumbing: one small
+    all-gather per slot (histograms), symmetric-memory rendezvous for the peer buffers, device-side barriers.
     """
 
-    def __init__(self, engine, world, rank, nR_global, nS_global, n_local_max, recv_capacity, group=None):
+    def __init__(self, engine, world, rank, nR_global, nS_global, n_local_max, recv_capacity, group=None,
+                 split_probe=False):
+        import os
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -168,32 +174,43 @@ class DmaShardedJoin:
         self.engine, self.world, self.rank = engine, world, rank
         self.group = group if group is not None else dist.group.WORLD
         self.plan = engine.shard_plan(nR_global, nS_global, world)
+        self.build_rel = 1 if self.plan.build_is_S else 0
+        self.probe_rel = 1 - self.build_rel
+        self.split = bool(split_probe)
+        # slots in shipping order: build relation, probe relation (first half), probe second half
+        self.slots = [self.build_rel, self.probe_rel] + ([2] if self.split else [])
         dev = torch.device("cuda", engine.device)
-        self.recv = [symm_mem.empty((recv_capacity, 2), dtype=torch.int64, device=dev) for _ in range(2)]
-        self.hdl = [symm_mem.rendezvous(t, self.group) for t in self.recv]
-        self.peer = [[h.get_buffer(p, (recv_capacity, 2), torch.int64) for p in range(world)] for h in self.hdl]
-        self.stage = [torch.empty((n_local_max, 2), dtype=torch.int64, device=dev) for _ in range(2)]
+        cap = {s: recv_capacity for s in self.slots}
+        stage_n = {s: n_local_max for s in self.slots}
+        if self.split:
+            for s in (self.probe_rel, 2):
+                cap[s] = recv_capacity // 2 + 4096
+                stage_n[s] = n_local_max // 2 + 1
+        self.capacity = cap
+        self.recv = {s: symm_mem.empty((cap[s], 2), dtype=torch.int64, device=dev) for s in self.slots}
+        self.hdl = {s: symm_mem.rendezvous(self.recv[s], self.group) for s in self.slots}
+        self.peer = {s: [self.hdl[s].get_buffer(p, (cap[s], 2), torch.int64) for p in range(world)] for s in self.slots}
+        self.stage = {s: torch.empty((stage_n[s], 2), dtype=torch.int64, device=dev) for s in self.slots}
         ndig = world << self.plan.bits_pass1
-        self.hist = [torch.empty(ndig, dtype=torch.int64, device=dev) for _ in range(2)]
-        self.all_hist = [torch.empty((world, ndig), dtype=torch.int64, device=dev) for _ in range(2)]
+        self.hist = {s: torch.empty(ndig, dtype=torch.int64, device=dev) for s in self.slots}
+        self.all_hist = {s: torch.empty((world, ndig), dtype=torch.int64, device=dev) for s in self.slots}
         self.copy_stream = torch.cuda.Stream(device=dev)
-        # a few copy lanes: the peer copies of a relation run on different copy engines (measured on
-        # 8 x B200: 1 lane 10.9 ms/join, 8 lanes 14.6 ms -- too many concurrent flows through the switch)
-        import os
+        # a few copy lanes: the peer copies of a slot run on different copy engines (measured on
+        # 8 x B200: 1 lane 10.6 ms/join, 2 lanes 10.7, 4 lanes 13.9, 8 lanes 14.6 -- too many concurrent
+        # flows through the switch collapse)
         lanes = int(os.environ.get("RHJ_COPY_LANES", "2"))
         self.peer_streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(world, lanes)))]
-        self.capacity = recv_capacity
 
-    def _ship(self, rel, lay, marks=None):
-        """peer copies of relation rel on the copy stream, fenced by device-side barriers"""
+    def _ship(self, slot, lay, marks=None):
+        """peer copies of one slot on the copy stream, fenced by device-side barriers"""
         torch = self.torch
         send_off, send_cnt, dst_off, _ = lay
         cs = self.copy_stream
         cs.wait_stream(torch.cuda.current_stream())        # the staging buffer is complete
         with torch.cuda.stream(cs):
-            self.hdl[rel].barrier(channel=0)                 # every rank is done with this receive buffer
+            self.hdl[slot].barrier(channel=0)                # every rank is done with this receive buffer
             if marks is not None:
-                marks.append((f"dma{rel}_start", self._mark(cs)))
+                marks.append((f"dma{slot}_start", self._mark(cs)))
             fork = torch.cuda.Event()
             fork.record(cs)
             for k in range(1, self.world + 1):
@@ -202,16 +219,16 @@ class DmaShardedJoin:
                     ps = self.peer_streams[k % len(self.peer_streams)]
                     ps.wait_event(fork)
                     with torch.cuda.stream(ps):
-                        self.peer[rel][d][dst_off[d]:dst_off[d] + send_cnt[d]].copy_(
-                            self.stage[rel][send_off[d]:send_off[d] + send_cnt[d]], non_blocking=True)
+                        self.peer[slot][d][dst_off[d]:dst_off[d] + send_cnt[d]].copy_(
+                            self.stage[slot][send_off[d]:send_off[d] + send_cnt[d]], non_blocking=True)
                     cs.wait_stream(ps)
             if marks is not None:
-                marks.append((f"dma{rel}_sent", self._mark(cs)))
-            self.hdl[rel].barrier(channel=1)                 # every rank's copies have landed
+                marks.append((f"dma{slot}_sent", self._mark(cs)))
+            self.hdl[slot].barrier(channel=1)                # every rank's copies have landed
             done = torch.cuda.Event(enable_timing=marks is not None)
             done.record(cs)
             if marks is not None:
-                marks.append((f"dma{rel}_landed", done))
+                marks.append((f"dma{slot}_landed", done))
         return done
 
     def _mark(self, stream=None):
@@ -220,34 +237,40 @@ class DmaShardedJoin:
         return ev
 
     def step(self, R_local, S_local, out, marks=None):
-        """One sharded join; returns (pairs, count, (received nR, nS)).  `marks` (a list) collects
-        (label, CUDA event) pairs for a timeline of the step."""
+        """One sharded join; returns (pairs, count, (received build, received probe)).  `marks` (a list)
+        collects (label, CUDA event) pairs for a timeline of the step."""
         torch, eng, plan = self.torch, self.engine, self.plan
         rels = (R_local, S_local)
+        B, P = rels[self.build_rel], rels[self.probe_rel]
+        half = (P.shape[0] + 1) // 2 if self.split else P.shape[0]
+        src = {self.build_rel: B, self.probe_rel: P[:half]}
+        if self.split:
+            src[2] = P[half:]
         if marks is not None:
             marks.append(("start", self._mark()))
         eng.shardx_begin(plan)
-        lay, landed = [None, None], [None, None]
-        for rel in (0, 1):
-            eng.shardx_pass1(plan, rel, rels[rel], self.stage[rel], self.hist[rel])
+        lay, landed = {}, {}
+        for s in self.slots:
+            eng.shardx_pass1(plan, s, src[s], self.stage[s], self.hist[s])
             if marks is not None:
-                marks.append((f"pass1_{rel}_done", self._mark()))
-            self.dist.all_gather_into_tensor(self.all_hist[rel], self.hist[rel], group=self.group)
-            lay[rel] = eng.shardx_layout(plan, self.rank, rel, self.all_hist[rel])
+                marks.append((f"pass1_{s}_done", self._mark()))
+            self.dist.all_gather_into_tensor(self.all_hist[s], self.hist[s], group=self.group)
+            lay[s] = eng.shardx_layout(plan, self.rank, s, self.all_hist[s])
+            if lay[s][3] > self.capacity[s]:
+                raise RuntimeError(f"rank {self.rank}: receive buffer of slot {s} too small ({lay[s][3]} > {self.capacity[s]})")
+            landed[s] = self._ship(s, lay[s], marks)         # in flight while the next slot is partitioned
+        pairs, count = out[:0], 0
+        for i, s in enumerate(self.slots):
+            torch.cuda.current_stream().wait_event(landed[s])
+            eng.shardx_pass2(plan, s, self.recv[s][:lay[s][3]])  # overlaps the transfer of the slots behind it
             if marks is not None:
-                marks.append((f"layout_{rel}_done", self._mark()))
-            if lay[rel][3] > self.capacity:
-                raise RuntimeError(f"rank {self.rank}: receive buffer too small ({lay[rel][3]} > {self.capacity})")
-            landed[rel] = self._ship(rel, lay[rel], marks)   # in flight while the next relation is partitioned
-        for rel in (0, 1):
-            torch.cuda.current_stream().wait_event(landed[rel])
-            eng.shardx_pass2(plan, rel, self.recv[rel][:lay[rel][3]])   # R's second pass overlaps S's transfer
-            if marks is not None:
-                marks.append((f"pass2_{rel}_done", self._mark()))
-        pairs, count = eng.shardx_join(plan, out)
-        if marks is not None:
-            marks.append(("join_done", self._mark()))
-        return pairs, count, (lay[0][3], lay[1][3])
+                marks.append((f"pass2_{s}_done", self._mark()))
+            if i >= 1:                                           # a probe slot: join it against the build slot
+                pairs, count = eng.shardx_join_slots(plan, self.build_rel, s, i == 1, out)
+                if marks is not None:
+                    marks.append((f"join_{s}_done", self._mark()))
+        nP = sum(lay[s][3] for s in self.slots[1:])
+        return pairs, count, (lay[self.build_rel][3], nP)
 
     @staticmethod
     def timeline(marks):

@@ -498,3 +498,59 @@ def test_optimistic_overflow_falls_back_to_exact_path(emit, monkeypatch):
     assert (n,) + eng.pairs_digest(out)[1:] == tuple(u.expected)
     assert eng.last_plan()["optimistic_pass1"] == 1
     eng.close()
+
+
+@pytest.mark.parametrize("world,nR,nS,dom", [(2, 60000, 90000, 50000), (4, 40000, 40000, 1 << 40), (8, 100000, 300000, 1 << 20),
+                                             (2, 90000, 30000, 20000)])
+def test_dma_shard_join_split_probe_emulated_ranks(world, nR, nS, dom):
+    """three slots: the build relation whole, the probe relation in two row halves, each half joined
+    against the build slot as soon as its own second pass is done (rhj_shardx_join_slots_device)."""
+    from radixhashjoin_b200 import RadixHashJoin
+    rng = np.random.default_rng(world * 13 + nR)
+    Rg, Sg = rand_rel(rng, world * nR, dom), rand_rel(rng, world * nS, dom, 1 << 35)
+    expect = O.sort_pairs(O.oracle_join(Rg, Sg))
+    engines = [RadixHashJoin(0) for _ in range(world)]
+    plan = engines[0].shard_plan(len(Rg), len(Sg), world)
+    build_rel = 1 if plan.build_is_S else 0
+    probe_rel = 1 - build_rel
+    assert build_rel == (1 if nS < nR else 0)
+    glob, nloc = (Rg, Sg), (nR, nS)
+    slots = [build_rel, probe_rel, 2]
+    src = []
+    for r in range(world):
+        loc = [to_dev(glob[k][r * nloc[k]:(r + 1) * nloc[k]]) for k in (0, 1)]
+        P = loc[probe_rel]
+        h = (P.shape[0] + 1) // 2
+        src.append({build_rel: loc[build_rel], probe_rel: P[:h], 2: P[h:]})
+    ndig = world << plan.bits_pass1
+    stage = [{s: torch.empty((max(src[r][s].shape[0], 1), 2), dtype=torch.int64, device=DEV) for s in slots} for r in range(world)]
+    hist = [{s: torch.empty(ndig, dtype=torch.int64, device=DEV) for s in slots} for r in range(world)]
+    for r in range(world):
+        engines[r].shardx_begin(plan)
+        for s in slots:
+            engines[r].shardx_pass1(plan, s, src[r][s], stage[r][s], hist[r][s])
+    lay = [{} for _ in range(world)]
+    recv = [{} for _ in range(world)]
+    for s in slots:
+        all_hist = torch.stack([hist[r][s] for r in range(world)])
+        for r in range(world):
+            lay[r][s] = engines[r].shardx_layout(plan, r, s, all_hist)
+            recv[r][s] = torch.empty((max(lay[r][s][3], 1), 2), dtype=torch.int64, device=DEV)
+        for r in range(world):
+            so, sc, do, _ = lay[r][s]
+            for d in range(world):
+                recv[d][s][do[d]:do[d] + sc[d]].copy_(stage[r][s][so[d]:so[d] + sc[d]])
+    torch.cuda.synchronize()
+    got = []
+    for r in range(world):
+        out = torch.empty((max(len(expect), 1), 2), dtype=torch.int64, device=DEV)
+        for i, s in enumerate(slots):
+            engines[r].shardx_pass2(plan, s, recv[r][s][:lay[r][s][3]])
+            if i >= 1:
+                pairs, n = engines[r].shardx_join_slots(plan, build_rel, s, i == 1, out)
+        got.append(pairs_np(pairs))
+    got = np.concatenate(got)
+    assert len(got) == len(expect)
+    assert np.array_equal(O.sort_pairs(got), expect)
+    for e in engines:
+        e.close()
