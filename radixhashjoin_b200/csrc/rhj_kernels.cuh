@@ -2,7 +2,7 @@
 //
 // north_star step            reference loop it replaces                       kernel here
 //  (1) histogram             HistogramJob::run, JobScheduler.cpp:149-155      k_hist
-//  (2) prefix sum            PartitionJob::run 163-169, Result.cpp:100-107    k_scan_digits, k_scan_parts
+//  (2) prefix sum            PartitionJob::run 163-169, Result.cpp:100-107    k_scan_digits, k_scan_parts_plan
 //  (3) partition scatter     PartitionJob::run 170-174 + structs.cpp:183-194  k_scatter
 //  (4) per-bucket build/probe Result::join_buckets, Result.cpp:43-76           k_join            (rhj_join.cuh)
 //  (5) emitter               add_result/addAll, Result.cpp:21-35,78-84,111-121 k_join<COUNT|WRITE|FUSED>, k_scan_items
@@ -236,41 +236,6 @@ __global__ void __launch_bounds__(kMaxDigits) k_scan_digits(ScanDigitsArgs a) {
             if (a.tile0[ri]) a.tile0[ri][a.ndig] = tex + tl;
         }
     }
-}
-
-// (2b) Exclusive prefix sum over the 2^bits_total final partition counters (up to 2^18), one CTA
-// per relation, each thread owning a contiguous slice.
-struct ScanPartsArgs {
-    const u64 *hist[2];
-    u64 *off[2];
-    u64 *cursor[2];
-    u32 nparts;
-};
-__global__ void __launch_bounds__(1024) k_scan_parts(ScanPartsArgs a) {
-    __shared__ u64 s_w[32];
-    const int ri = blockIdx.x;
-    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 per = (a.nparts + 1023) / 1024;
-    const u32 p0 = min(a.nparts, tid * per), p1 = min(a.nparts, p0 + per);
-    u64 c = 0;
-    for (u32 p = p0; p < p1; ++p) c += a.hist[ri][p];
-    u64 inc = warp_incl_scan64(c);
-    if (lane == 31) s_w[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        u64 w = s_w[lane];
-        u64 wi = warp_incl_scan64(w);
-        s_w[lane] = wi - w;
-    }
-    __syncthreads();
-    u64 run = inc - c + s_w[warp];
-    for (u32 p = p0; p < p1; ++p) {
-        a.off[ri][p] = run;
-        a.cursor[ri][p] = run;
-        run += a.hist[ri][p];
-    }
-    if (p1 == a.nparts && p0 < p1) a.off[ri][a.nparts] = run;
-    if (a.nparts == 0 && tid == 0) a.off[ri][0] = 0;
 }
 
 // (3) Partition scatter with shared-memory staging (software write-combining).
