@@ -299,7 +299,7 @@ inline u64 fixed_cap(u64 n, u32 ndig) { return n / ndig + n / ndig / 8 + 8192; }
 
 // Samples 1/64 of both relations and decides whether every pass-1 partition will fit its fixed
 // region with room to spare.  One small kernel + a 4 KiB D2H + a stream synchronise.
-int sample_says_balanced(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Tup *inB, const Tup *inP, bool *ok) {
+int sample_says_balanced(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Tup *inB, const Tup *inP, bool ok[2]) {
     const u32 ndig = 1u << pl.b1;
     int rc;
     if ((rc = ensure(ctx, ctx->sample, 2 * (size_t) ndig * sizeof(u32)))) return rc;
@@ -321,14 +321,13 @@ int sample_says_balanced(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Tu
     static thread_local u32 h[2 * kMaxDigits];
     CK(cudaMemcpyAsync(h, ctx->sample.p, 2 * (size_t) ndig * sizeof(u32), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    *ok = true;
     const u64 ns[2] = {pl.nB, pl.nP};
     for (int r = 0; r < 2; ++r) {
         u32 mx = 0;
         for (u32 d = 0; d < ndig; ++d) mx = std::max(mx, h[r * ndig + d]);
         // sampled count s ~ true/64 with standard error sqrt(s): leave 5 sigma
         const double est = 64.0 * (mx + 5.0 * std::sqrt((double) mx + 1.0));
-        if (est > (double) fixed_cap(ns[r], ndig)) *ok = false;
+        ok[r] = est <= (double) fixed_cap(ns[r], ndig);
     }
     return RHJ_OK;
 }
@@ -367,17 +366,29 @@ int partition_and_plan(rhj_ctx *ctx, cudaStream_t st, const Tup *dR, u64 nR, con
         offP = m.off2[1];
     } else {
         // ---- optimistic pass 1 (two-pass plans, large inputs): no histogram, fixed-capacity regions ----
-        bool optimistic = false;
+        bool opt[2] = {false, false};  // per relation (0 = build, 1 = probe): a skewed probe side does not cost the build side its shortcut
         if (allow_optimistic && ctx->optimistic && pl.b2 > 0 && ntot >= ((u64) 1 << 22)) {
-            if ((rc = sample_says_balanced(ctx, st, pl, inB, inP, &optimistic))) return rc;
-            if (ctx->force_optimistic) optimistic = true;  // test hook: exercise the overflow -> exact retry
+            if ((rc = sample_says_balanced(ctx, st, pl, inB, inP, opt))) return rc;
+            if (ctx->force_optimistic) opt[0] = opt[1] = true;  // test hook: exercise the overflow -> exact retry
         }
-        if (optimistic) {
+        if (opt[0] || opt[1]) {
             const u32 nd1 = 1u << pl.b1;
-            const u64 capB = fixed_cap(pl.nB, nd1), capP = fixed_cap(pl.nP, nd1);
-            if ((rc = ensure(ctx, ctx->bufA, (size_t) nd1 * (capB + capP) * sizeof(Tup)))) return rc;
+            const u64 cap[2] = {fixed_cap(pl.nB, nd1), fixed_cap(pl.nP, nd1)};
+            const u64 nX[2] = {pl.nB, pl.nP};
+            const Tup *inX0[2] = {inB, inP};
+            const size_t regB = opt[0] ? (size_t) nd1 * cap[0] : pl.nB, regP = opt[1] ? (size_t) nd1 * cap[1] : pl.nP;
+            if ((rc = ensure(ctx, ctx->bufA, (regB + regP) * sizeof(Tup)))) return rc;
             Tup *A = (Tup *) ctx->bufA.p;
-            Tup *AP = A + (size_t) nd1 * capB;
+            Tup *outX[2] = {A, A + regB};
+            PartArgs a{};
+            a.shift = 32 - pl.b1;
+            a.mask = nd1 - 1;
+            a.ndig = nd1;
+            a.overflow = (u32 *) (m.scalars + kScOverflow);
+            for (int i = 0; i < 2; ++i) {
+                a.rel[i] = PartRel{inX0[i], outX[i], nX[i], m.hist1[i], m.cur1[i], nullptr, nullptr, 1, tiles_of(nX[i])};
+                a.rel[i].limit_cap = opt[i] ? cap[i] : ((u64) 1 << 50);  // no bound for a relation with exact offsets
+            }
             FixedArgs fa{};
             for (int i = 0; i < 2; ++i) {
                 fa.cursor[i] = m.cur1[i];
@@ -385,35 +396,45 @@ int partition_and_plan(rhj_ctx *ctx, cudaStream_t st, const Tup *dR, u64 nR, con
                 fa.seg_end[i] = m.sege[i];
                 fa.off1[i] = m.off1[i];
                 fa.tile0[i] = m.tile0[i];
+                fa.cap[i] = cap[i];
             }
-            fa.cap[0] = capB;
-            fa.cap[1] = capP;
             fa.ndig = nd1;
-            fa.overflow = (u32 *) (m.scalars + kScOverflow);
+            fa.overflow = a.overflow;
+            fa.rel_mask = (opt[0] ? 1u : 0u) | (opt[1] ? 2u : 0u);
+            if (!(opt[0] && opt[1])) {
+                // the skewed relation keeps its histogram + prefix sum (only its tiles are launched)
+                const int x = opt[0] ? 1 : 0;
+                PartArgs ah = a;
+                ah.rel[x ^ 1].ntiles = 0;
+                mark(ctx, st, RHJ_PHASE_HIST1);
+                if ((rc = launch_hist(ctx, st, ah, kDigitHash, false))) return rc;
+                ScanDigitsArgs sd{};
+                sd.hist[0] = sd.hist[1] = m.hist1[x];
+                sd.off[0] = sd.off[1] = m.off1[x];
+                sd.cursor[0] = sd.cursor[1] = m.cur1[x];
+                sd.tile0[0] = sd.tile0[1] = m.tile0[x];
+                sd.ndig = nd1;
+                mark(ctx, st, RHJ_PHASE_SCAN1);
+                k_scan_digits<<<1, kMaxDigits, 0, st>>>(sd);
+                CK(cudaGetLastError());
+                ctx->info.kernel_launches++;
+            }
             k_fixed_cursors<<<2, 256, 0, st>>>(fa);
             CK(cudaGetLastError());
             ctx->info.kernel_launches++;
-            PartArgs a{};
-            a.shift = 32 - pl.b1;
-            a.mask = nd1 - 1;
-            a.ndig = nd1;
-            a.overflow = fa.overflow;
-            a.rel[0] = PartRel{inB, A, pl.nB, nullptr, m.cur1[0], nullptr, nullptr, 1, tiles_of(pl.nB)};
-            a.rel[1] = PartRel{inP, AP, pl.nP, nullptr, m.cur1[1], nullptr, nullptr, 1, tiles_of(pl.nP)};
-            a.rel[0].limit_cap = capB;
-            a.rel[1].limit_cap = capP;
             mark(ctx, st, RHJ_PHASE_SCATTER1);
             if ((rc = launch_scatter(ctx, st, a, kDigitHash, false, true))) return rc;
             mark(ctx, st, RHJ_PHASE_SCAN1);
             k_fixed_finish<<<2, kMaxDigits, 0, st>>>(fa);
             CK(cudaGetLastError());
             ctx->info.kernel_launches++;
-            const Tup *inX[2] = {A, AP};
+            const Tup *inX[2] = {outX[0], outX[1]};
             const u64 *off1X[2] = {m.off1[0], m.off1[1]};
             const u32 *tile0X[2] = {m.tile0[0], m.tile0[1]};
-            const u64 *segbX[2] = {m.segb[0], m.segb[1]};
-            const u64 *segeX[2] = {m.sege[0], m.sege[1]};
-            ctx->info.optimistic_pass1 = 1;
+            // a relation with exact offsets lies where pass 2 will pack it from: [off1[s], off1[s + 1])
+            const u64 *segbX[2] = {opt[0] ? m.segb[0] : m.off1[0], opt[1] ? m.segb[1] : m.off1[1]};
+            const u64 *segeX[2] = {opt[0] ? m.sege[0] : m.off1[0] + 1, opt[1] ? m.sege[1] : m.off1[1] + 1};
+            ctx->info.optimistic_pass1 = fa.rel_mask;
             return second_pass_and_plan(ctx, st, pl, m, inX, off1X, tile0X, segbX, segeX);
         }
         if ((rc = ensure(ctx, ctx->bufA, ntot * sizeof(Tup)))) return rc;

@@ -652,14 +652,17 @@ struct FixedArgs {
     u64 *off1[2];         // [ndig + 1] exact prefix of the partition sizes (pass 2 packs its output with it)
     u32 *tile0[2];        // [ndig + 1]
     u32 *overflow;
+    u32 rel_mask;         // bit r set: relation r uses the fixed-capacity layout (the other one has a histogram)
 };
 __global__ void k_fixed_cursors(FixedArgs a) {
     const int ri = blockIdx.x;
+    if (!((a.rel_mask >> ri) & 1u)) return;
     for (u32 d = threadIdx.x; d < a.ndig; d += blockDim.x) a.cursor[ri][d] = (u64) d * a.cap[ri];
 }
 __global__ void __launch_bounds__(kMaxDigits) k_fixed_finish(FixedArgs a) {
     __shared__ u64 s_w[33];
     const int ri = blockIdx.x;
+    if (!((a.rel_mask >> ri) & 1u)) return;
     const u32 tid = threadIdx.x;
     u64 beg = 0, cnt = 0;
     if (tid < a.ndig) {

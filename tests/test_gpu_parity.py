@@ -475,11 +475,11 @@ def test_optimistic_pass1_taken_and_correct(engine):
     w = W.uniform_unique(23, DEV)
     out, n = engine.join_device(w.R, w.S, capacity=w.expected[0], emit=EMIT_FUSED)
     assert (n,) + engine.pairs_digest(out)[1:] == tuple(w.expected)
-    assert engine.last_plan()["optimistic_pass1"] == 1
-    z = W.zipf_probe(23, DEV)                      # a hot key: the sample must send this down the exact path
+    assert engine.last_plan()["optimistic_pass1"] == 3     # both relations
+    z = W.zipf_probe(23, DEV)                      # a hot probe key: the sample keeps the histogram for the probe side only
     out, n = engine.join_device(z.R, z.S, capacity=z.expected[0], emit=EMIT_FUSED)
     assert (n,) + engine.pairs_digest(out)[1:] == tuple(z.expected)
-    assert engine.last_plan()["optimistic_pass1"] == 0
+    assert engine.last_plan()["optimistic_pass1"] == 1     # build relation only
 
 
 @pytest.mark.parametrize("emit", [EMIT_FUSED, EMIT_COUNT_THEN_WRITE])
@@ -496,7 +496,7 @@ def test_optimistic_overflow_falls_back_to_exact_path(emit, monkeypatch):
     u = W.uniform_unique(22, DEV)
     out, n = eng.join_device(u.R, u.S, capacity=u.expected[0], emit=emit)
     assert (n,) + eng.pairs_digest(out)[1:] == tuple(u.expected)
-    assert eng.last_plan()["optimistic_pass1"] == 1
+    assert eng.last_plan()["optimistic_pass1"] == 3
     eng.close()
 
 
