@@ -236,6 +236,7 @@ def run_b200(args, rank, world, local_rank):
         wname = f"uniform_unique_global_2^{gbits}x2^{gbits}_sharded_over_{world}"
     nR, nS = R.shape[0], S.shape[0]
     n_in_local = nR + nS
+    compact = False
 
     if world == 1:
         cap = nS if args.workload != "dup" else nS
@@ -254,8 +255,12 @@ def run_b200(args, rank, world, local_rank):
         if args.shuffle == "dma":
             # pass 1 partitions on (rank | sub-digit) into staging; the copy engines ship one chunk per peer
             # while the SMs partition the other relation; pass 2 runs on the received (source, partition) pieces
+            # 12-byte shipping when every row id fits 32 bits (checked here once, and by the kernels every step)
+            mx = torch.stack([R[:, 0].max(), S[:, 0].max()]).max()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            compact = args.ship_bytes == 12 and int(mx.item()) < (1 << 32)
             dj = DmaShardedJoin(eng, world, rank, n_local * world, n_local * world, n_local, slack,
-                                split_probe=args.split_probe)
+                                split_probe=args.split_probe, compact_rowids=compact)
             del recvR, recvS
 
             def step():
@@ -416,7 +421,8 @@ def run_b200(args, rank, world, local_rank):
                                     % (nR * 16 / 2**30),
                            "radix_bits": [plan["bits_pass1"], plan["bits_pass2"]],
                            "parallelism": "1 GPU" if world == 1 else (
-                               f"{world} ranks: pass 1 partitions on (rank | sub-digit), copy engines ship one chunk per peer over "
+                               f"{world} ranks: pass 1 partitions on (rank | sub-digit), copy engines ship one chunk per peer "
+                               f"({12 if compact else 16} B per tuple) over "
                                "NVLink overlapped with the other relation's passes, then local pass 2 + join" if args.shuffle == "dma" else
                                f"{world} ranks: pass-1 scatter stores into peer receive buffers over NVLink (fused partition+shuffle), "
                                "then local pass 2 + join" if args.shuffle == "stores" else
@@ -452,6 +458,8 @@ def main():
     ap.add_argument("--shuffle", default="dma", choices=["dma", "stores", "nccl"],
                     help="multi-GPU exchange: pass-1 chunks shipped by the copy engines (default), pass-1 scatter storing "
                          "straight into peer memory, or rank partition + NCCL all-to-all")
+    ap.add_argument("--ship-bytes", type=int, default=16, choices=[12, 16],
+                    help="dma shuffle: bytes per tuple on the wire; 12 = {u64 value, u32 row id}, used when row ids fit 32 bits")
     ap.add_argument("--split-probe", action="store_true", help="dma shuffle: ship the probe relation in two halves (measured slower)")
     ap.add_argument("--no-small-work", action="store_true")
     ap.add_argument("--small-work-ref", action="store_true", help="also time the unmodified reference program (minutes)")

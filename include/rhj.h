@@ -220,6 +220,14 @@ int rhj_shardx_pass2_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int rel, c
                             void *stream);
 int rhj_shardx_join_device(rhj_ctx *ctx, const rhj_shard_plan *plan, rhj_pair *d_out, uint64_t capacity, uint64_t *count,
                            void *stream);
+/* 12-byte shipping: pass 1 stages {u64 value, u32 row id} in two arrays and pass 2 reads what arrived in that
+ * form (the final partitions are 16-byte tuples again), so 25 % fewer bytes cross NVLink.  The caller promises
+ * that every row id fits 32 bits (relation cardinality < 2^32); a wider one makes the join call fail with
+ * RHJ_ERR_ARG.  The chunk arithmetic of rhj_shardx_layout_device is the same: offsets and counts are in tuples. */
+int rhj_shardx_pass1_soa_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int rel, const rhj_tuple *d_in, uint64_t n,
+                                uint64_t *d_stage_val, uint32_t *d_stage_rid, uint64_t *d_hist, void *stream);
+int rhj_shardx_pass2_soa_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int rel, const uint64_t *d_recv_val,
+                                const uint32_t *d_recv_rid, uint64_t n_recv, void *stream);
 /* Slots: `rel` above is 0 = R, 1 = S, or 2 = the second half of the PROBE relation (the larger one) when the
  * caller ships it in two halves.  rhj_shardx_join_slots_device joins one (build slot, probe slot) pair; with
  * first = 0 it appends to the previous call's result, so the join of the first half overlaps the transfer of

@@ -63,6 +63,9 @@ SIGNATURES = {
     "rhj_shardx_layout_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, ctypes.c_int, c_vp, c_u64p,
                                                 c_u64p, c_u64p, c_u64p, c_vp]),
     "rhj_shardx_pass2_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, c_vp, c_u64, c_vp]),
+    "rhj_shardx_pass1_soa_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, c_vp, c_u64, c_vp, c_vp, c_vp,
+                                                   c_vp]),
+    "rhj_shardx_pass2_soa_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, c_vp, c_vp, c_u64, c_vp]),
     "rhj_shardx_join_slots_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                     c_vp, c_u64, c_u64p, c_vp]),
     "rhj_shardx_join_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), c_vp, c_u64, c_u64p, c_vp]),

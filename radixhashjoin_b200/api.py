@@ -256,6 +256,20 @@ class RadixHashJoin:
         self._ck(self._lib.rhj_shardx_pass1_device(self._ctx, ctypes.byref(plan), rel, _ptr(T), n, _ptr(stage), _ptr(hist),
                                                    self._stream(stream)))
 
+    def shardx_pass1_soa(self, plan, rel, T, stage_val, stage_rid, hist, stream=None):
+        """pass 1 staging 12-byte tuples: stage_val int64[n] + stage_rid int32[n] (row ids must fit 32 bits)"""
+        n = _check_rel(T)
+        if stage_val.numel() < n or stage_rid.numel() < n:
+            raise ValueError("staging arrays too small")
+        self._ck(self._lib.rhj_shardx_pass1_soa_device(self._ctx, ctypes.byref(plan), rel, _ptr(T), n, _ptr(stage_val),
+                                                       _ptr(stage_rid), _ptr(hist), self._stream(stream)))
+
+    def shardx_pass2_soa(self, plan, rel, recv_val, recv_rid, n, stream=None):
+        if recv_val.numel() < n or recv_rid.numel() < n:
+            raise ValueError("receive arrays too small")
+        self._ck(self._lib.rhj_shardx_pass2_soa_device(self._ctx, ctypes.byref(plan), rel, _ptr(recv_val), _ptr(recv_rid), n,
+                                                       self._stream(stream)))
+
     def shardx_layout(self, plan, rank, rel, all_hist, stream=None):
         """(send_off[d], send_cnt[d], dst_off[d], recv_total) from the all-gathered histograms"""
         W = plan.world

@@ -50,6 +50,14 @@ int launch_hist(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, bool
     if (!total) return RHJ_OK;
     u32 grid = std::min<u32>(total, (u32) ctx->num_sms * 4);
     bool agg = ctx->hist_agg;
+    if (!a.rel[0].in && a.rel[0].in_val) {  // 12-byte input (received shards): pass 2 of the DMA-shipped sharded join
+        if (kind != kDigitHash || !seg) return fail(ctx, RHJ_ERR_STATE, "12-byte input is only wired for the segmented hash pass");
+        if (agg) k_hist<kDigitHash, true, true, kIoSoaIn><<<grid, kPartThreads, 0, st>>>(a);
+        else k_hist<kDigitHash, true, false, kIoSoaIn><<<grid, kPartThreads, 0, st>>>(a);
+        CK(cudaGetLastError());
+        ctx->info.kernel_launches++;
+        return RHJ_OK;
+    }
 #define HIST(K, S)                                                            \
     do {                                                                      \
         if (agg) k_hist<K, S, true><<<grid, kPartThreads, 0, st>>>(a);        \
@@ -65,18 +73,18 @@ int launch_hist(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, bool
     return RHJ_OK;
 }
 
-template <int K, bool S, int W>
+template <int K, bool S, int W, int IO = kIoAos>
 cudaError_t launch_scatter_t(cudaStream_t st, const PartArgs &a, u32 grid) {
     const size_t smem = kScatterSmem;
     if (a.ndig > 512) {  // 1024-digit passes (sharded plans) pay for the larger counter arrays, 512-digit ones do not
-        cudaError_t e = set_smem(k_scatter<K, S, W, kMaxDigits>, smem);
+        cudaError_t e = set_smem(k_scatter<K, S, W, kMaxDigits, false, IO>, smem);
         if (e != cudaSuccess) return e;
-        k_scatter<K, S, W, kMaxDigits><<<grid, kPartThreads, smem, st>>>(a);
+        k_scatter<K, S, W, kMaxDigits, false, IO><<<grid, kPartThreads, smem, st>>>(a);
         return cudaGetLastError();
     }
-    cudaError_t e = set_smem(k_scatter<K, S, W, 512>, smem);
+    cudaError_t e = set_smem(k_scatter<K, S, W, 512, false, IO>, smem);
     if (e != cudaSuccess) return e;
-    k_scatter<K, S, W, 512><<<grid, kPartThreads, smem, st>>>(a);
+    k_scatter<K, S, W, 512, false, IO><<<grid, kPartThreads, smem, st>>>(a);
     return cudaGetLastError();
 }
 
@@ -92,6 +100,21 @@ int launch_scatter(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, b
     }
     const int w = kind == kDigitShard ? ctx->shard_scatter_mode : ctx->scatter_mode;
     cudaError_t e;
+    if (!a.rel[0].in && a.rel[0].in_val) {  // 12-byte input -> 16-byte partitions (pass 2 of the DMA-shipped sharded join)
+        if (kind != kDigitHash || !seg) return fail(ctx, RHJ_ERR_STATE, "12-byte input is only wired for the segmented hash pass");
+        if (w == 1) e = launch_scatter_t<kDigitHash, true, kWriteBulk, kIoSoaIn>(st, a, grid);
+        else e = launch_scatter_t<kDigitHash, true, kWriteStaged, kIoSoaIn>(st, a, grid);
+        CK(e);
+        ctx->info.kernel_launches++;
+        return RHJ_OK;
+    }
+    if (!a.rel[0].out && a.rel[0].out_val) {  // 16-byte input -> 12-byte staging (pass 1 of the same); per-thread stores
+        if (kind != kDigitShard || !a.shard_local) return fail(ctx, RHJ_ERR_STATE, "12-byte output is only wired for local staging");
+        e = launch_scatter_t<kDigitShard, false, kWriteStaged, kIoSoaOut>(st, a, grid);
+        CK(e);
+        ctx->info.kernel_launches++;
+        return RHJ_OK;
+    }
 #define SC(K, S) (w == 1 ? launch_scatter_t<K, S, kWriteBulk>(st, a, grid) : launch_scatter_t<K, S, kWriteStaged>(st, a, grid))
     if (kind == kDigitRaw) e = seg ? SC(kDigitRaw, true) : SC(kDigitRaw, false);
     else if (kind == kDigitHash) e = seg ? SC(kDigitHash, true) : SC(kDigitHash, false);
@@ -495,6 +518,8 @@ int read_scalars(rhj_ctx *ctx, cudaStream_t st) {
     u64 *sc = scalars_of(ctx, ctx->cur.nparts);
     CK(cudaMemcpyAsync(ctx->h_scalars, sc, kScCount * sizeof(u64), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (ctx->h_scalars[kScWideKey])
+        return fail(ctx, RHJ_ERR_ARG, "a row id does not fit 32 bits: 12-byte shipping (rhj_shardx_*_soa_device) cannot be used");
     if (ctx->h_scalars[kScOverflow]) return kRetryExact;  // the optimistic pass-1 layout was too small
     if (ctx->h_scalars[kScErr]) return fail(ctx, RHJ_ERR_STATE, "device-side planning error (work-item table overflow)");
     ctx->info.n_items = (u32) ctx->h_scalars[kScNItems];
@@ -1337,18 +1362,27 @@ int rhj_shardx_begin(rhj_ctx *ctx, const rhj_shard_plan *sp, void *stream) {
 // (destination rank | sub-digit) into d_hist[world << bits_pass1] (the caller all-gathers it), prefix
 // sum, scatter into the local staging buffer d_stage[n], which ends up ordered by destination rank,
 // then by pass-1 partition.  Enqueues only.
-int rhj_shardx_pass1_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_in, uint64_t n,
-                            rhj_tuple *d_stage, uint64_t *d_hist, void *stream) {
-    if (!ctx || !sp || !d_hist || rel < 0 || rel > 2 || (n && (!d_in || !d_stage))) return RHJ_ERR_ARG;
+static int shardx_pass1_impl(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_in, uint64_t n,
+                             rhj_tuple *d_stage, uint64_t *d_stage_val, uint32_t *d_stage_rid, uint64_t *d_hist,
+                             void *stream) {
+    if (!ctx || !sp || !d_hist || rel < 0 || rel > 2 || (n && (!d_in || (!d_stage && (!d_stage_val || !d_stage_rid)))))
+        return RHJ_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = pick(ctx, stream);
     SlotArrays sl;
+    Meta m;
     int rc;
     if ((rc = slot_arrays(ctx, 1u << sp->bits_total, rel, sl))) return rc;
+    if ((rc = layout_meta(ctx, 1u << sp->bits_total, m))) return rc;
     PartArgs a = shard_args(sp);
     a.shard_local = 1;
+    a.overflow = (u32 *) (m.scalars + kScWideKey);
     CK(cudaMemsetAsync(d_hist, 0, (size_t) a.ndig * sizeof(u64), st));
     a.rel[0] = PartRel{(const Tup *) d_in, (Tup *) d_stage, n, (u64 *) d_hist, sl.cur1, nullptr, nullptr, 1, tiles_of(n)};
+    if (!d_stage) {  // 12-byte staging: values and 32-bit row ids in two arrays
+        a.rel[0].out_val = (u64 *) d_stage_val;
+        a.rel[0].out_rid = d_stage_rid;
+    }
     if (rel == 0) mark(ctx, st, RHJ_PHASE_HIST1);
     if ((rc = launch_hist(ctx, st, a, kDigitShard, false))) return rc;
     ScanDigitsArgs sd{};
@@ -1362,6 +1396,21 @@ int rhj_shardx_pass1_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, con
     ctx->info.kernel_launches++;
     if ((rc = launch_scatter(ctx, st, a, kDigitShard, false))) return rc;
     return RHJ_OK;
+}
+
+int rhj_shardx_pass1_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_in, uint64_t n,
+                            rhj_tuple *d_stage, uint64_t *d_hist, void *stream) {
+    if (n && !d_stage) return RHJ_ERR_ARG;
+    return shardx_pass1_impl(ctx, sp, rel, d_in, n, d_stage, nullptr, nullptr, d_hist, stream);
+}
+
+// Same, staging the tuples as 12 bytes: d_stage_val[n] (u64 values) + d_stage_rid[n] (u32 row ids).  The
+// caller promises that every row id fits 32 bits (relation cardinality < 2^32); a wider one is reported
+// by the join call as RHJ_ERR_ARG.  25 % fewer bytes cross NVLink.
+int rhj_shardx_pass1_soa_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_in, uint64_t n,
+                                uint64_t *d_stage_val, uint32_t *d_stage_rid, uint64_t *d_hist, void *stream) {
+    if (n && (!d_stage_val || !d_stage_rid)) return RHJ_ERR_ARG;
+    return shardx_pass1_impl(ctx, sp, rel, d_in, n, nullptr, d_stage_val, d_stage_rid, d_hist, stream);
 }
 
 // Layout of slot `rel` from the all-gathered histograms d_all_hist[world][world << bits_pass1]:
@@ -1416,9 +1465,9 @@ int rhj_shardx_layout_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rank, i
 
 // Pass 2 of slot `rel` over what this rank received (d_recv[n_recv], world << bits_pass1 pieces):
 // histogram, per-partition offsets, scatter into the slot's final partition buffer.  Enqueues only.
-int rhj_shardx_pass2_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_recv, uint64_t n_recv,
-                            void *stream) {
-    if (!ctx || !sp || rel < 0 || rel > 2 || (n_recv && !d_recv)) return RHJ_ERR_ARG;
+static int shardx_pass2_impl(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_recv,
+                             const uint64_t *d_recv_val, const uint32_t *d_recv_rid, uint64_t n_recv, void *stream) {
+    if (!ctx || !sp || rel < 0 || rel > 2 || (n_recv && !d_recv && (!d_recv_val || !d_recv_rid))) return RHJ_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = pick(ctx, stream);
     SlotArrays sl;
@@ -1435,6 +1484,10 @@ int rhj_shardx_pass2_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, con
     b.rel[0] = PartRel{(const Tup *) d_recv, (Tup *) sl.out->p, n_recv, sl.hist2, sl.cur2, sl.seg_off, sl.tile0,
                        npieces, tiles_of(n_recv) + npieces, nd1 - 1};
     if (nd1 == 1) b.rel[0].group_mask = 0x80000000u;  // every piece is partition 0: (seg & mask) == 0
+    if (!d_recv) {  // received as 12-byte SoA; the final partitions are 16-byte tuples again
+        b.rel[0].in_val = (const u64 *) d_recv_val;
+        b.rel[0].in_rid = d_recv_rid;
+    }
     if ((rc = build_tile_tables(ctx, st, b, 1, rel))) return rc;
     if (rel == 0) mark(ctx, st, RHJ_PHASE_HIST2);
     if ((rc = launch_hist(ctx, st, b, kDigitHash, true))) return rc;
@@ -1450,6 +1503,18 @@ int rhj_shardx_pass2_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, con
     ctx->info.kernel_launches++;
     if ((rc = launch_scatter(ctx, st, b, kDigitHash, true))) return rc;
     return RHJ_OK;
+}
+
+int rhj_shardx_pass2_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_recv, uint64_t n_recv,
+                            void *stream) {
+    if (n_recv && !d_recv) return RHJ_ERR_ARG;
+    return shardx_pass2_impl(ctx, sp, rel, d_recv, nullptr, nullptr, n_recv, stream);
+}
+
+int rhj_shardx_pass2_soa_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const uint64_t *d_recv_val,
+                                const uint32_t *d_recv_rid, uint64_t n_recv, void *stream) {
+    if (n_recv && (!d_recv_val || !d_recv_rid)) return RHJ_ERR_ARG;
+    return shardx_pass2_impl(ctx, sp, rel, nullptr, d_recv_val, d_recv_rid, n_recv, stream);
 }
 
 // Work-item plan + build/probe + fused emit over the final partitions of a (build slot, probe slot)

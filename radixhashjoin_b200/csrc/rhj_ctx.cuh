@@ -33,6 +33,7 @@ enum Scalar {
     kScDigXor = 7,
     kScFilt = 8,
     kScOverflow = 9,  // optimistic pass 1: a partition outgrew its fixed-capacity region
+    kScWideKey = 10,  // 12-byte shipping: a row id did not fit 32 bits
     kScCount = 16
 };
 

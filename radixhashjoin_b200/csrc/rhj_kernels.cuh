@@ -54,7 +54,24 @@ struct PartRel {
     const void *tiles;     // SEG: optional TileDesc[ntiles] built by k_tile_table (else binary search)
     const u64 *seg_end;    // SEG: optional [nseg] segment ends (null: seg_off[seg + 1]); fixed-capacity pass-1 layout
     u64 limit_cap;         // k_scatter<LIMIT>: digit d may only fill [d * limit_cap, (d + 1) * limit_cap) of `out`
+    // 12-byte SoA form of a relation {u64 value, u32 row id} (multi-GPU shipping: -25 % NVLink bytes):
+    const u64 *in_val;     // input when `in` is null
+    const u32 *in_rid;
+    u64 *out_val;          // output when `out` is null (non-peer scatter only)
+    u32 *out_rid;
 };
+// tuple idx of a relation in either form
+// How a partitioning kernel reads / writes tuples: 16-byte AoS both ways (everything single-GPU), or the
+// 12-byte form the DMA-shipped sharded join puts on the wire ({u64 value}[n] + {u32 row id}[n]) on one side.
+enum TupleIo { kIoAos = 0, kIoSoaIn = 1, kIoSoaOut = 2 };
+template <int IO>
+__device__ __forceinline__ Tup ld_tuple(const PartRel &r, u64 idx) {
+    if (IO != kIoSoaIn) return ld_stream(r.in + idx);
+    Tup t;
+    t.key = __ldg(r.in_rid + idx);
+    t.val = __ldg(r.in_val + idx);
+    return t;
+}
 // One 16-byte descriptor per pass-2 tile (k_tile_table): a CTA finds its tuple range with ONE load
 // instead of a 9-step binary search over seg_tile0 -- that dependent-load chain sat in front of
 // every tile's first tuple load.
@@ -138,7 +155,7 @@ __global__ void __launch_bounds__(256) k_tile_table(const u64 *seg_off, const u6
 // first by match.any so a skewed digit costs one atomic per warp instead of 32 serialised ones)
 // and flushes to the global u64 counters only when its (relation, segment) changes.
 // Algorithmic bytes: 16 per tuple read.
-template <int KIND, bool SEG, bool AGG>
+template <int KIND, bool SEG, bool AGG, int IO = kIoAos>
 __global__ void __launch_bounds__(kPartThreads) k_hist(PartArgs a) {
     __shared__ u32 s_h[kMaxDigits];
     const u32 tid = threadIdx.x;
@@ -172,7 +189,10 @@ __global__ void __launch_bounds__(kPartThreads) k_hist(PartArgs a) {
         for (int j = 0; j < kPartItems; ++j) {
             u64 idx = beg + (u64) j * kPartThreads + tid;
             ok[j] = idx < end;
-            if (ok[j]) v[j] = ld_stream(r.in + idx);
+            if (ok[j]) {
+                if (IO != kIoSoaIn) v[j] = ld_stream(r.in + idx);
+                else v[j].val = __ldg(r.in_val + idx);  // the histogram only needs the value: 8 bytes per tuple
+            }
         }
 #pragma unroll
         for (int j = 0; j < kPartItems; ++j) {
@@ -248,7 +268,7 @@ __global__ void __launch_bounds__(kMaxDigits) k_scan_digits(ScanDigitsArgs a) {
 //   or, with BULK, by one TMA bulk store (cp.async.bulk shared->global) per run.
 // Algorithmic bytes: 16 read + 16 written per tuple.
 enum ScatterWrite { kWriteStaged = 0, kWriteBulk = 1 };
-template <int KIND, bool SEG, int WMODE, int MAXD, bool LIMIT = false>
+template <int KIND, bool SEG, int WMODE, int MAXD, bool LIMIT = false, int IO = kIoAos>
 __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(PartArgs a) {
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     Tup *s_tup = reinterpret_cast<Tup *>(dyn_smem);
@@ -271,7 +291,7 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
 #pragma unroll
     for (int j = 0; j < kPartItems; ++j) {
         u32 i = j * kPartThreads + tid;
-        if (i < ntile) v[j] = ld_stream(r.in + beg + i);
+        if (i < ntile) v[j] = ld_tuple<IO>(r, beg + i);
     }
     __syncthreads();
 #pragma unroll
@@ -349,7 +369,13 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
                     *a.overflow = 1;
                     continue;
                 }
-                st_stream(ob + s_delta[d] + i, t);
+                if (IO != kIoSoaOut) {
+                    st_stream(ob + s_delta[d] + i, t);
+                } else {  // 12-byte SoA output; a row id that does not fit 32 bits is an error the host reports
+                    if (t.key >> 32) *a.overflow = 2;
+                    r.out_val[s_delta[d] + i] = t.val;
+                    r.out_rid[s_delta[d] + i] = (u32) t.key;
+                }
             }
         }
     }

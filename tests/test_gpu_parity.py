@@ -451,6 +451,65 @@ def test_dma_shard_join_emulated_ranks(world, n_local, dom):
         e.close()
 
 
+@pytest.mark.parametrize("world,n_local,dom,id_base", [(1, 50000, 20000, 0), (2, 60000, 50000, (1 << 32) - 120000),
+                                                       (4, 40000, 1 << 40, 1 << 31), (8, 300000, 1 << 20, 7), (4, 500, 200, 0),
+                                                       (2, 3000, 1000, 1 << 32)])
+def test_dma_shard_join_compact_rowids_emulated_ranks(world, n_local, dom, id_base):
+    """rhj_shardx_pass1_soa / pass2_soa: the staged and shipped form is {u64 value}[n] + {u32 row id}[n]
+    (12 bytes per tuple on the wire).  Union == oracle; a row id >= 2^32 makes the join call fail."""
+    from radixhashjoin_b200 import RadixHashJoin, RhjError
+    rng = np.random.default_rng(world * 91 + n_local)
+    Rg, Sg = rand_rel(rng, world * n_local, dom), rand_rel(rng, world * n_local, dom, id_base)
+    wide = int(Sg["key"].max()) >= (1 << 32)
+    expect = O.sort_pairs(O.oracle_join(Rg, Sg))
+    engines = [RadixHashJoin(0) for _ in range(world)]
+    shards = [(to_dev(Rg[r * n_local:(r + 1) * n_local]), to_dev(Sg[r * n_local:(r + 1) * n_local])) for r in range(world)]
+    plan = engines[0].shard_plan(len(Rg), len(Sg), world)
+    ndig = world << plan.bits_pass1
+    sval = [[torch.empty(n_local, dtype=torch.int64, device=DEV) for _ in range(2)] for _ in range(world)]
+    srid = [[torch.empty(n_local, dtype=torch.int32, device=DEV) for _ in range(2)] for _ in range(world)]
+    hist = [[torch.empty(ndig, dtype=torch.int64, device=DEV) for _ in range(2)] for _ in range(world)]
+    for r in range(world):
+        engines[r].shardx_begin(plan)
+        for rel in (0, 1):
+            engines[r].shardx_pass1_soa(plan, rel, shards[r][rel], sval[r][rel], srid[r][rel], hist[r][rel])
+    lay = [[None, None] for _ in range(world)]
+    for rel in (0, 1):
+        all_hist = torch.stack([hist[r][rel] for r in range(world)])
+        for r in range(world):
+            lay[r][rel] = engines[r].shardx_layout(plan, r, rel, all_hist)
+    rval = [[torch.empty(max(lay[r][rel][3], 1), dtype=torch.int64, device=DEV) for rel in (0, 1)] for r in range(world)]
+    rrid = [[torch.empty(max(lay[r][rel][3], 1), dtype=torch.int32, device=DEV) for rel in (0, 1)] for r in range(world)]
+    for rel in (0, 1):
+        assert sum(lay[r][rel][3] for r in range(world)) == world * n_local
+        for r in range(world):
+            so, sc, do, _ = lay[r][rel]
+            for d in range(world):
+                rval[d][rel][do[d]:do[d] + sc[d]].copy_(sval[r][rel][so[d]:so[d] + sc[d]])
+                rrid[d][rel][do[d]:do[d] + sc[d]].copy_(srid[r][rel][so[d]:so[d] + sc[d]])
+    torch.cuda.synchronize()
+    got, failed = [], 0
+    for r in range(world):
+        for rel in (0, 1):
+            engines[r].shardx_pass2_soa(plan, rel, rval[r][rel], rrid[r][rel], lay[r][rel][3])
+        out = torch.empty((max(len(expect), 1), 2), dtype=torch.int64, device=DEV)
+        if wide:
+            with pytest.raises(RhjError, match="32 bits"):
+                engines[r].shardx_join(plan, out)
+            failed += 1
+            continue
+        pairs, n = engines[r].shardx_join(plan, out)
+        got.append(pairs_np(pairs))
+    if wide:
+        assert failed == world
+    else:
+        got = np.concatenate(got)
+        assert len(got) == len(expect)
+        assert np.array_equal(O.sort_pairs(got), expect)
+    for e in engines:
+        e.close()
+
+
 # ---- pipelined host join (large inputs: chunked probe side, H2D / compute / D2H overlapped) ----------------
 @pytest.mark.parametrize("nR,nS,dom", [(30000, 100000, 20000), (100000, 30000, 1 << 40), (4000, 50000, 700), (200000, 200000, 150000),
                                        (5000, 2001, 3)])
