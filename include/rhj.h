@@ -244,7 +244,8 @@ typedef struct rhj_plan_info {
     uint32_t n_items;                            /* probe work items of the last join                 */
     uint32_t kernel_launches;                    /* kernels launched by the last join call            */
     uint32_t optimistic_pass1;                   /* bit 0 / 1: pass 1 of the build / probe relation ran without a
-                                                    histogram (fixed-capacity regions)                     */
+                                                    histogram (fixed-capacity regions); bit 2: so did pass 2
+                                                    of both (fixed-capacity final partitions)              */
 } rhj_plan_info;
 int rhj_last_plan(const rhj_ctx *ctx, rhj_plan_info *info);
 

@@ -91,9 +91,15 @@ cudaError_t launch_scatter_t(cudaStream_t st, const PartArgs &a, u32 grid) {
 int launch_scatter(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, bool seg, bool limit = false) {
     u32 grid = a.rel[0].ntiles + a.rel[1].ntiles;
     if (!grid) return RHJ_OK;
-    if (limit) {  // optimistic pass 1: fixed-capacity regions, bounds-checked staged stores
-        CK(set_smem(k_scatter<kDigitHash, false, kWriteStaged, 512, true>, kScatterSmem));
-        k_scatter<kDigitHash, false, kWriteStaged, 512, true><<<grid, kPartThreads, kScatterSmem, st>>>(a);
+    if (limit) {  // optimistic passes: fixed-capacity regions, bounds-checked staged stores
+        if (kind != kDigitHash || a.ndig > 512) return fail(ctx, RHJ_ERR_STATE, "bounds-checked scatter: hash digits, <= 512 per pass");
+        if (seg) {
+            CK(set_smem(k_scatter<kDigitHash, true, kWriteStaged, 512, true>, kScatterSmem));
+            k_scatter<kDigitHash, true, kWriteStaged, 512, true><<<grid, kPartThreads, kScatterSmem, st>>>(a);
+        } else {
+            CK(set_smem(k_scatter<kDigitHash, false, kWriteStaged, 512, true>, kScatterSmem));
+            k_scatter<kDigitHash, false, kWriteStaged, 512, true><<<grid, kPartThreads, kScatterSmem, st>>>(a);
+        }
         CK(cudaGetLastError());
         ctx->info.kernel_launches++;
         return RHJ_OK;
@@ -216,15 +222,23 @@ int build_tile_tables(rhj_ctx *ctx, cudaStream_t st, PartArgs &b, int nrel, int 
     return RHJ_OK;
 }
 
+// Per-partition capacity of the optimistic pass-2 layout: a final partition of hashed, mostly distinct keys holds
+// Poisson(mean) tuples; mean + 16 sigma + 64 leaves room for keys repeated a few times.  Multiple of 8 tuples so
+// every region starts on a 128-byte line.
+inline u64 fixed_cap2(u64 n, u32 nparts) {
+    const double mean = (double) n / nparts;
+    return ((u64) (mean + 16.0 * std::sqrt(mean) + 64.0) + 8) & ~(u64) 7;
+}
+
 // Second radix pass (if the plan has one) over pass-1-partitioned relations inX[0] (build) and
 // inX[1] (probe) whose pass-1 offsets / first-tile tables are off1X / tile0X, then the work-item
 // plan.  Leaves ctx->cur describing the final partitions.  Enqueues only; no host sync.
 int second_pass_and_plan(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Meta &m, const Tup *const inX[2],
                          const u64 *const off1X[2], const u32 *const tile0X[2], const u64 *const seg_begX[2] = nullptr,
-                         const u64 *const seg_endX[2] = nullptr) {
+                         const u64 *const seg_endX[2] = nullptr, bool fixed2 = false) {
     int rc;
     const Tup *finB, *finP;
-    const u64 *offB, *offP;
+    const u64 *offB, *offP, *endB = nullptr, *endP = nullptr;
     bool planned = false;
     u32 item_cap = 0;
     if (pl.b2 == 0) {
@@ -232,6 +246,62 @@ int second_pass_and_plan(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Me
         finP = inX[1];
         offB = off1X[0];
         offP = off1X[1];
+    } else if (fixed2) {
+        // ---- optimistic pass 2: no histogram; final partition p scatters into the fixed region [p * cap, (p + 1) * cap) ----
+        const u64 cap[2] = {fixed_cap2(pl.nB, pl.nparts), fixed_cap2(pl.nP, pl.nparts)};
+        const size_t regB = (size_t) pl.nparts * cap[0], regP = (size_t) pl.nparts * cap[1];
+        if ((rc = ensure(ctx, ctx->bufB, (regB + regP) * sizeof(Tup)))) return rc;
+        Tup *B = (Tup *) ctx->bufB.p;
+        PartArgs b{};
+        b.shift = 32 - pl.bits;
+        b.mask = (1u << pl.b2) - 1;
+        b.ndig = 1u << pl.b2;
+        b.overflow = (u32 *) (m.scalars + kScOverflow);
+        const u32 nseg = 1u << pl.b1;
+        b.rel[0] = PartRel{inX[0], B, pl.nB, m.hist2[0], m.cur2[0], off1X[0], tile0X[0], nseg, tiles_of(pl.nB) + nseg};
+        b.rel[1] = PartRel{inX[1], B + regB, pl.nP, m.hist2[1], m.cur2[1], off1X[1], tile0X[1], nseg, tiles_of(pl.nP) + nseg};
+        for (int i = 0; i < 2; ++i) {
+            b.rel[i].limit_cap = cap[i];
+            if (seg_begX) {
+                b.rel[i].seg_off = seg_begX[i];
+                b.rel[i].seg_end = seg_endX[i];
+            }
+        }
+        if ((rc = build_tile_tables(ctx, st, b, 2))) return rc;
+        u64 cap64 = (u64) pl.nparts + pl.nP / kProbeChunk + 2;
+        if (cap64 > 0x7fffffffull) return fail(ctx, RHJ_ERR_ARG, "relation too large for the work-item table");
+        item_cap = (u32) cap64;
+        if ((rc = ensure(ctx, ctx->items, (size_t) item_cap * sizeof(Item)))) return rc;
+        PlanFixedArgs pf{};
+        for (int i = 0; i < 2; ++i) {
+            pf.end[i] = m.cur2[i];
+            pf.beg[i] = m.off2[i];
+            pf.cap[i] = cap[i];
+        }
+        pf.nseg = nseg;
+        pf.ndig = b.ndig;
+        pf.items = (Item *) ctx->items.p;
+        pf.item_cap = item_cap;
+        pf.nitems = (u32 *) (m.scalars + kScNItems);
+        pf.err = (u32 *) (m.scalars + kScErr);
+        pf.overflow = b.overflow;
+        k_fixed_cursors2<<<dim3((pl.nparts + 255) / 256, 2), 256, 0, st>>>(pf);
+        CK(cudaGetLastError());
+        ctx->info.kernel_launches++;
+        mark(ctx, st, RHJ_PHASE_SCATTER2);
+        if ((rc = launch_scatter(ctx, st, b, kDigitHash, true, true))) return rc;
+        mark(ctx, st, RHJ_PHASE_PLAN);
+        k_plan_fixed<<<nseg, kMaxDigits, 0, st>>>(pf);
+        CK(cudaGetLastError());
+        ctx->info.kernel_launches++;
+        planned = true;
+        finB = B;
+        finP = B + regB;
+        offB = m.off2[0];
+        offP = m.off2[1];
+        endB = m.cur2[0];
+        endP = m.cur2[1];
+        ctx->info.optimistic_pass1 |= 4u;
     } else {
         // ---- pass 2: next b2 bits, inside every pass-1 partition ----
         if ((rc = ensure(ctx, ctx->bufB, (pl.nB + pl.nP) * sizeof(Tup)))) return rc;
@@ -309,6 +379,8 @@ int second_pass_and_plan(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Me
     ctx->cur.probe = finP;
     ctx->cur.offB = offB;
     ctx->cur.offP = offP;
+    ctx->cur.endB = endB ? endB : offB + 1;
+    ctx->cur.endP = endP ? endP : offP + 1;
     ctx->cur.nparts = pl.nparts;
     ctx->cur.item_cap = item_cap;
     ctx->cur.build_is_S = pl.build_is_S;
@@ -322,7 +394,8 @@ inline u64 fixed_cap(u64 n, u32 ndig) { return n / ndig + n / ndig / 8 + 8192; }
 
 // Samples 1/64 of both relations and decides whether every pass-1 partition will fit its fixed
 // region with room to spare.  One small kernel + a 4 KiB D2H + a stream synchronise.
-int sample_says_balanced(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Tup *inB, const Tup *inP, bool ok[2]) {
+int sample_says_balanced(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Tup *inB, const Tup *inP, bool ok[2],
+                         bool poisson[2]) {
     const u32 ndig = 1u << pl.b1;
     int rc;
     if ((rc = ensure(ctx, ctx->sample, 2 * (size_t) ndig * sizeof(u32)))) return rc;
@@ -351,6 +424,16 @@ int sample_says_balanced(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Tu
         // sampled count s ~ true/64 with standard error sqrt(s): leave 5 sigma
         const double est = 64.0 * (mx + 5.0 * std::sqrt((double) mx + 1.0));
         ok[r] = est <= (double) fixed_cap(ns[r], ndig);
+        // Index of dispersion of the sampled counts: 1 for hashed distinct keys; a key repeated f times moves as one
+        // clump and raises it to 1 + (f - 1) / 64.  Fixed-capacity FINAL partitions (pass 2) are sized for Poisson
+        // counts, so they are only tried when the sample shows no clumping (f < ~20; smaller f fits or is retried).
+        double sum = 0, sq = 0;
+        for (u32 d = 0; d < ndig; ++d) {
+            sum += h[r * ndig + d];
+            sq += (double) h[r * ndig + d] * h[r * ndig + d];
+        }
+        const double mean = sum / ndig, var = sq / ndig - mean * mean;
+        poisson[r] = mean >= 64.0 && var <= 1.3 * mean;
     }
     return RHJ_OK;
 }
@@ -390,9 +473,16 @@ int partition_and_plan(rhj_ctx *ctx, cudaStream_t st, const Tup *dR, u64 nR, con
     } else {
         // ---- optimistic pass 1 (two-pass plans, large inputs): no histogram, fixed-capacity regions ----
         bool opt[2] = {false, false};  // per relation (0 = build, 1 = probe): a skewed probe side does not cost the build side its shortcut
+        bool poisson[2] = {false, false};
+        if (!allow_optimistic) ctx->opt2_skip = 16;  // an optimistic layout just overflowed: stay exact in pass 2 for a while
         if (allow_optimistic && ctx->optimistic && pl.b2 > 0 && ntot >= ((u64) 1 << 22)) {
-            if ((rc = sample_says_balanced(ctx, st, pl, inB, inP, opt))) return rc;
-            if (ctx->force_optimistic) opt[0] = opt[1] = true;  // test hook: exercise the overflow -> exact retry
+            if ((rc = sample_says_balanced(ctx, st, pl, inB, inP, opt, poisson))) return rc;
+            if (ctx->force_optimistic) opt[0] = opt[1] = poisson[0] = poisson[1] = true;  // test hook: exercise the overflow -> exact retry
+        }
+        bool fixed2 = opt[0] && opt[1] && poisson[0] && poisson[1] && ctx->optimistic2 && pl.b2 <= 9;
+        if (fixed2 && ctx->opt2_skip > 0 && !ctx->force_optimistic) {
+            ctx->opt2_skip--;
+            fixed2 = false;
         }
         if (opt[0] || opt[1]) {
             const u32 nd1 = 1u << pl.b1;
@@ -458,7 +548,7 @@ int partition_and_plan(rhj_ctx *ctx, cudaStream_t st, const Tup *dR, u64 nR, con
             const u64 *segbX[2] = {opt[0] ? m.segb[0] : m.off1[0], opt[1] ? m.segb[1] : m.off1[1]};
             const u64 *segeX[2] = {opt[0] ? m.sege[0] : m.off1[0] + 1, opt[1] ? m.sege[1] : m.off1[1] + 1};
             ctx->info.optimistic_pass1 = fa.rel_mask;
-            return second_pass_and_plan(ctx, st, pl, m, inX, off1X, tile0X, segbX, segeX);
+            return second_pass_and_plan(ctx, st, pl, m, inX, off1X, tile0X, segbX, segeX, fixed2);
         }
         if ((rc = ensure(ctx, ctx->bufA, ntot * sizeof(Tup)))) return rc;
         Tup *A = (Tup *) ctx->bufA.p;
@@ -504,6 +594,8 @@ JoinArgs join_args(rhj_ctx *ctx, int work_slot) {
     j.probe = ctx->cur.probe;
     j.offB = ctx->cur.offB;
     j.offP = ctx->cur.offP;
+    j.endB = ctx->cur.endB;
+    j.endP = ctx->cur.endP;
     j.items = (const Item *) ctx->items.p;
     j.nitems = (const u32 *) (sc + kScNItems);
     j.work_counter = (u32 *) (sc + work_slot);
@@ -730,6 +822,8 @@ int join_host_pipelined(rhj_ctx *ctx, const Tup *hR, u64 nR, const Tup *hS, u64 
         ctx->cur.probe = finP;
         ctx->cur.offB = offB;
         ctx->cur.offP = offP;
+        ctx->cur.endB = offB + 1;
+        ctx->cur.endP = offP + 1;
         ctx->cur.nparts = pl.nparts;
         ctx->cur.item_cap = item_cap;
         ctx->cur.build_is_S = pl.build_is_S;
@@ -800,6 +894,7 @@ int rhj_create(int device, rhj_ctx **out) {
     if ((e = getenv("RHJ_SCATTER_MODE"))) ctx->scatter_mode = atoi(e);
     if ((e = getenv("RHJ_NO_OPT"))) ctx->optimistic = atoi(e) == 0;
     if ((e = getenv("RHJ_FORCE_OPT"))) ctx->force_optimistic = atoi(e) != 0;
+    if ((e = getenv("RHJ_NO_OPT2"))) ctx->optimistic2 = atoi(e) == 0;
     if ((e = getenv("RHJ_HOST_CHUNK"))) ctx->host_chunk = std::max<long long>(1, atoll(e));
     if ((e = getenv("RHJ_SHARD_SCATTER_MODE"))) ctx->shard_scatter_mode = atoi(e);
     if (cudaSetDevice(device) != cudaSuccess ||
@@ -854,7 +949,10 @@ int rhj_reserve(rhj_ctx *ctx, uint64_t nR, uint64_t nS) {
     if (pl.b2 > 0 && ctx->optimistic)  // the optimistic pass-1 layout gives every partition a fixed region with headroom
         a_tuples = std::max<size_t>(a_tuples, ((size_t) 1 << pl.b1) * (fixed_cap(pl.nB, 1u << pl.b1) + fixed_cap(pl.nP, 1u << pl.b1)));
     if (pl.bits > 0 && (rc = ensure(ctx, ctx->bufA, a_tuples * sizeof(Tup)))) return rc;
-    if (pl.b2 > 0 && (rc = ensure(ctx, ctx->bufB, (pl.nB + pl.nP) * sizeof(Tup)))) return rc;
+    size_t b_tuples = pl.nB + pl.nP;
+    if (pl.b2 > 0 && ctx->optimistic && ctx->optimistic2)  // fixed-capacity final partitions
+        b_tuples = std::max<size_t>(b_tuples, (size_t) pl.nparts * (fixed_cap2(pl.nB, pl.nparts) + fixed_cap2(pl.nP, pl.nparts)));
+    if (pl.b2 > 0 && (rc = ensure(ctx, ctx->bufB, b_tuples * sizeof(Tup)))) return rc;
     u64 cap = (u64) pl.nparts + pl.nP / kProbeChunk + 2;
     if ((rc = ensure(ctx, ctx->items, cap * sizeof(Item)))) return rc;
     if ((rc = ensure(ctx, ctx->item_cnt, cap * 8))) return rc;
@@ -1560,6 +1658,8 @@ int rhj_shardx_join_slots_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int bui
         ctx->cur.probe = (const Tup *) spb.out->p;
         ctx->cur.offB = sb.off2;
         ctx->cur.offP = spb.off2;
+        ctx->cur.endB = sb.off2 + 1;
+        ctx->cur.endP = spb.off2 + 1;
         ctx->cur.nparts = nparts;
         ctx->cur.item_cap = item_cap;
         // slot 0 is R; slots 1 and 2 hold S tuples unless S is the (unsplit) build side

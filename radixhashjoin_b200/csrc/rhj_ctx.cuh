@@ -45,6 +45,8 @@ struct rhj_ctx {
     bool hist_agg = false;
     bool optimistic = true;   // skip the pass-1 histogram when a sampled histogram says it is safe (RHJ_NO_OPT=1 disables)
     bool force_optimistic = false;  // RHJ_FORCE_OPT=1 (tests): take the optimistic path even when the sample says skewed
+    bool optimistic2 = true;  // also skip the pass-2 histogram (fixed-capacity final partitions; RHJ_NO_OPT2=1 disables)
+    int opt2_skip = 0;        // joins left to run without the pass-2 shortcut after it overflowed (duplicate-heavy data)
     DevBuf sample;            // sampled pass-1 histogram
     int scatter_mode = 0;     // 0 staged per-thread stores, 1 TMA bulk stores (RHJ_SCATTER_MODE)
     int shard_scatter_mode = 1;  // same choice for the fused partition+shuffle pass: bulk stores make
@@ -76,7 +78,8 @@ struct rhj_ctx {
         bool valid = false;
         bool counted = false;
         const Tup *build = nullptr, *probe = nullptr;
-        const u64 *offB = nullptr, *offP = nullptr;
+        const u64 *offB = nullptr, *offP = nullptr;   // partition starts
+        const u64 *endB = nullptr, *endP = nullptr;   // partition ends (off + 1 unless the layout has fixed-capacity regions)
         u32 nparts = 0;
         u32 item_cap = 0;
         int build_is_S = 0;

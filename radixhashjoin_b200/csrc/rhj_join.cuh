@@ -69,8 +69,10 @@ enum JoinMode { kJoinCount = 0, kJoinWrite = 1, kJoinFused = 2 };
 struct JoinArgs {
     const Tup *build;    // partitioned build relation (the smaller input)
     const Tup *probe;    // partitioned probe relation
-    const u64 *offB;
+    const u64 *offB;     // [nparts] where each build partition starts ...
     const u64 *offP;
+    const u64 *endB;     // ... and ends: offB + 1 for packed layouts, the scatter cursors for fixed-capacity regions
+    const u64 *endP;
     const Item *items;
     const u32 *nitems;
     u32 *work_counter;   // dynamic item scheduler
@@ -112,9 +114,9 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join(JoinA
         const u32 item = s_item;
         if (item >= nitems) break;
         const Item it = a.items[item];
-        const u64 b0 = a.offB[it.part], b1 = a.offB[it.part + 1];
+        const u64 b0 = a.offB[it.part], b1 = a.endB[it.part];
         const u64 p0 = a.offP[it.part] + (u64) it.chunk * kProbeChunk;
-        const u64 p1 = min(a.offP[it.part + 1], p0 + (u64) kProbeChunk);
+        const u64 p1 = min(a.endP[it.part], p0 + (u64) kProbeChunk);
         u64 my_count = 0;                                   // COUNT
         u64 run_base = (MODE == kJoinWrite && tid == 0) ? a.item_off[item] : 0;  // WRITE (thread 0 only)
 

@@ -365,7 +365,8 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
                 Tup t = s_tup[i];
                 u32 d = digit<KIND>(t.val, a);
                 Tup *ob = (KIND == kDigitShard && !a.shard_local) ? a.peer_out[ri][d >> a.sub_bits] : r.out;
-                if (LIMIT && s_delta[d] + i >= (u64) (d + 1) * r.limit_cap) {  // the optimistic layout is too small
+                // the optimistic layout is too small: partition (segment group, digit) ends at (index + 1) * capacity
+                if (LIMIT && s_delta[d] + i >= ((u64) seg_group(r, seg) * a.ndig + d + 1) * r.limit_cap) {
                     *a.overflow = 1;
                     continue;
                 }
@@ -712,6 +713,66 @@ __global__ void __launch_bounds__(kMaxDigits) k_fixed_finish(FixedArgs a) {
             a.off1[ri][a.ndig] = total;
             a.tile0[ri][a.ndig] = (u32) ttotal;
         }
+    }
+}
+
+// Optimistic pass 2: every final partition p owns the fixed region [p * cap, (p + 1) * cap) of the output, so
+// the pass needs no histogram (16 bytes per tuple less HBM traffic).  k_fixed_cursors2 starts the scatter
+// cursors at the region starts; after the scatter the cursors ARE the partition ends, and k_plan_fixed (one
+// CTA per pass-1 partition, like k_scan_parts_plan) writes the region starts, clamps an overflowed end
+// (the host then re-runs the exact path) and appends the work items.
+struct PlanFixedArgs {
+    u64 *end[2];      // [nparts] scatter cursors: in = region start + tuples appended, out = clamped partition end
+    u64 *beg[2];      // [nparts] p * cap
+    u64 cap[2];
+    u32 nseg, ndig;
+    Item *items;
+    u32 item_cap;
+    u32 *nitems;
+    u32 *err;
+    u32 *overflow;
+};
+__global__ void k_fixed_cursors2(PlanFixedArgs a) {
+    const int ri = blockIdx.y;
+    const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < a.nseg * a.ndig) a.end[ri][p] = (u64) p * a.cap[ri];
+}
+__global__ void __launch_bounds__(kMaxDigits) k_plan_fixed(PlanFixedArgs a) {
+    __shared__ u32 s_w32[32];
+    __shared__ u32 s_base;
+    const u32 seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 p = seg * a.ndig + tid;
+    u64 cnt[2] = {0, 0};
+    if (tid < a.ndig) {
+#pragma unroll
+        for (int ri = 0; ri < 2; ++ri) {
+            const u64 b = (u64) p * a.cap[ri];
+            u64 c = a.end[ri][p] - b;
+            if (c > a.cap[ri]) {
+                *a.overflow = 1;
+                c = a.cap[ri];
+                a.end[ri][p] = b + c;
+            }
+            a.beg[ri][p] = b;
+            cnt[ri] = c;
+        }
+    }
+    u32 k = (cnt[0] && cnt[1]) ? (u32) ((cnt[1] + kProbeChunk - 1) / kProbeChunk) : 0;
+    u32 inc = warp_incl_scan(k);
+    if (lane == 31) s_w32[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        u32 w = lane < (kMaxDigits / 32) ? s_w32[lane] : 0;
+        u32 wi = warp_incl_scan(w);
+        s_w32[lane] = wi - w;
+        u32 total = __shfl_sync(0xffffffffu, wi, 31);
+        if (lane == 0) s_base = total ? atomicAdd(a.nitems, total) : 0;
+    }
+    __syncthreads();
+    u32 at = s_base + inc - k + s_w32[warp];
+    for (u32 ch = 0; ch < k; ++ch) {
+        if (at + ch < a.item_cap) a.items[at + ch] = Item{p, ch};
+        else *a.err = 1;
     }
 }
 

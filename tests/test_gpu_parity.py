@@ -534,7 +534,7 @@ def test_optimistic_pass1_taken_and_correct(engine):
     w = W.uniform_unique(23, DEV)
     out, n = engine.join_device(w.R, w.S, capacity=w.expected[0], emit=EMIT_FUSED)
     assert (n,) + engine.pairs_digest(out)[1:] == tuple(w.expected)
-    assert engine.last_plan()["optimistic_pass1"] == 3     # both relations
+    assert engine.last_plan()["optimistic_pass1"] == 7     # both relations in pass 1 (1 | 2) and pass 2 (4)
     z = W.zipf_probe(23, DEV)                      # a hot probe key: the sample keeps the histogram for the probe side only
     out, n = engine.join_device(z.R, z.S, capacity=z.expected[0], emit=EMIT_FUSED)
     assert (n,) + engine.pairs_digest(out)[1:] == tuple(z.expected)
@@ -555,7 +555,52 @@ def test_optimistic_overflow_falls_back_to_exact_path(emit, monkeypatch):
     u = W.uniform_unique(22, DEV)
     out, n = eng.join_device(u.R, u.S, capacity=u.expected[0], emit=emit)
     assert (n,) + eng.pairs_digest(out)[1:] == tuple(u.expected)
-    assert eng.last_plan()["optimistic_pass1"] == 3
+    assert eng.last_plan()["optimistic_pass1"] == 7
+    eng.close()
+
+
+@pytest.mark.parametrize("emit", [EMIT_FUSED, EMIT_COUNT_THEN_WRITE])
+def test_optimistic_pass2_switch_and_parity(emit, monkeypatch):
+    """fixed-capacity final partitions (no pass-2 histogram) give the same pairs as the exact layout"""
+    from radixhashjoin_b200 import RadixHashJoin
+    u = W.uniform_unique(23, DEV)
+    rng = np.random.default_rng(31)
+    R, S = rand_rel(rng, 1 << 21, 1 << 62), rand_rel(rng, 3 << 20, 1 << 62)
+    S["payload"][::3] = R["payload"][:1 << 20]                       # a third of the probe side matches
+    exp = O.pairs_digest(O.oracle_join(R, S))
+    for no_opt2, want in (("0", 7), ("1", 3)):
+        monkeypatch.setenv("RHJ_NO_OPT2", no_opt2)
+        eng = RadixHashJoin(0)
+        out, n = eng.join_device(u.R, u.S, capacity=u.expected[0], emit=emit)
+        assert (n,) + eng.pairs_digest(out)[1:] == tuple(u.expected)
+        assert eng.last_plan()["optimistic_pass1"] == want
+        out, n = eng.join_device(to_dev(R), to_dev(S), capacity=exp[0], emit=emit)
+        assert (n,) + eng.pairs_digest(out)[1:] == exp    # whichever layout the sample chose
+        eng.close()
+
+
+@pytest.mark.parametrize("emit", [EMIT_FUSED, EMIT_COUNT_THEN_WRITE])
+def test_optimistic_pass2_overflow_falls_back_to_exact_path(emit, monkeypatch):
+    """every build key 64 times: balanced at pass 1, but the final partitions are not Poisson-sized.  Unforced, the
+    sample's dispersion keeps the pass-2 histogram; forced, a final partition overflows its region and the join is
+    re-run through the exact path.  Same pairs either way."""
+    from radixhashjoin_b200 import RadixHashJoin
+    n = 1 << 21
+    perm = np.random.default_rng(64).permutation(n).astype(np.uint64)   # shuffled rows: the 1/64 sample sees the repeats
+    R = O.as_tuples(np.arange(n, dtype=np.uint64), perm // np.uint64(64) * np.uint64(7919))
+    S = O.as_tuples(np.arange(n, dtype=np.uint64) + np.uint64(1 << 33), np.arange(n, dtype=np.uint64) * np.uint64(7919 * 16))
+    exp = O.pairs_digest(O.oracle_join(R, S))
+    assert exp[0] == (n // 64 // 16) * 64
+    eng = RadixHashJoin(0)
+    out, cnt = eng.join_device(to_dev(R), to_dev(S), capacity=exp[0], emit=emit)
+    assert (cnt,) + eng.pairs_digest(out)[1:] == exp
+    assert eng.last_plan()["optimistic_pass1"] & 4 == 0      # clumped build side: pass 2 keeps its histogram
+    eng.close()
+    monkeypatch.setenv("RHJ_FORCE_OPT", "1")
+    eng = RadixHashJoin(0)
+    out, cnt = eng.join_device(to_dev(R), to_dev(S), capacity=exp[0], emit=emit)
+    assert (cnt,) + eng.pairs_digest(out)[1:] == exp
+    assert eng.last_plan()["optimistic_pass1"] == 0          # the plan that produced the result is the exact one
     eng.close()
 
 
