@@ -250,7 +250,7 @@ int second_pass_and_plan(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Me
         // ---- optimistic pass 2: no histogram; final partition p scatters into the fixed region [p * cap, (p + 1) * cap) ----
         const u64 cap[2] = {fixed_cap2(pl.nB, pl.nparts), fixed_cap2(pl.nP, pl.nparts)};
         const size_t regB = (size_t) pl.nparts * cap[0], regP = (size_t) pl.nparts * cap[1];
-        if ((rc = ensure(ctx, ctx->bufB, (regB + regP) * sizeof(Tup)))) return rc;
+        if ((rc = ensure(ctx, ctx->bufB, (regB + regP + kTile) * sizeof(Tup)))) return rc;
         Tup *B = (Tup *) ctx->bufB.p;
         PartArgs b{};
         b.shift = 32 - pl.bits;
@@ -260,6 +260,8 @@ int second_pass_and_plan(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Me
         const u32 nseg = 1u << pl.b1;
         b.rel[0] = PartRel{inX[0], B, pl.nB, m.hist2[0], m.cur2[0], off1X[0], tile0X[0], nseg, tiles_of(pl.nB) + nseg};
         b.rel[1] = PartRel{inX[1], B + regB, pl.nP, m.hist2[1], m.cur2[1], off1X[1], tile0X[1], nseg, tiles_of(pl.nP) + nseg};
+        b.rel[0].dump = regB + regP;  // one dump tile behind both relations (indices are relative to each `out`)
+        b.rel[1].dump = regP;
         for (int i = 0; i < 2; ++i) {
             b.rel[i].limit_cap = cap[i];
             if (seg_begX) {
@@ -490,7 +492,7 @@ int partition_and_plan(rhj_ctx *ctx, cudaStream_t st, const Tup *dR, u64 nR, con
             const u64 nX[2] = {pl.nB, pl.nP};
             const Tup *inX0[2] = {inB, inP};
             const size_t regB = opt[0] ? (size_t) nd1 * cap[0] : pl.nB, regP = opt[1] ? (size_t) nd1 * cap[1] : pl.nP;
-            if ((rc = ensure(ctx, ctx->bufA, (regB + regP) * sizeof(Tup)))) return rc;
+            if ((rc = ensure(ctx, ctx->bufA, (regB + regP + kTile) * sizeof(Tup)))) return rc;
             Tup *A = (Tup *) ctx->bufA.p;
             Tup *outX[2] = {A, A + regB};
             PartArgs a{};
@@ -501,6 +503,7 @@ int partition_and_plan(rhj_ctx *ctx, cudaStream_t st, const Tup *dR, u64 nR, con
             for (int i = 0; i < 2; ++i) {
                 a.rel[i] = PartRel{inX0[i], outX[i], nX[i], m.hist1[i], m.cur1[i], nullptr, nullptr, 1, tiles_of(nX[i])};
                 a.rel[i].limit_cap = opt[i] ? cap[i] : ((u64) 1 << 50);  // no bound for a relation with exact offsets
+                a.rel[i].dump = i == 0 ? regB + regP : regP;             // one dump tile behind both relations
             }
             FixedArgs fa{};
             for (int i = 0; i < 2; ++i) {
@@ -947,11 +950,11 @@ int rhj_reserve(rhj_ctx *ctx, uint64_t nR, uint64_t nS) {
     if ((rc = layout_meta(ctx, pl.nparts, m))) return rc;
     size_t a_tuples = pl.nB + pl.nP;
     if (pl.b2 > 0 && ctx->optimistic)  // the optimistic pass-1 layout gives every partition a fixed region with headroom
-        a_tuples = std::max<size_t>(a_tuples, ((size_t) 1 << pl.b1) * (fixed_cap(pl.nB, 1u << pl.b1) + fixed_cap(pl.nP, 1u << pl.b1)));
+        a_tuples = std::max<size_t>(a_tuples, ((size_t) 1 << pl.b1) * (fixed_cap(pl.nB, 1u << pl.b1) + fixed_cap(pl.nP, 1u << pl.b1)) + kTile);
     if (pl.bits > 0 && (rc = ensure(ctx, ctx->bufA, a_tuples * sizeof(Tup)))) return rc;
     size_t b_tuples = pl.nB + pl.nP;
     if (pl.b2 > 0 && ctx->optimistic && ctx->optimistic2)  // fixed-capacity final partitions
-        b_tuples = std::max<size_t>(b_tuples, (size_t) pl.nparts * (fixed_cap2(pl.nB, pl.nparts) + fixed_cap2(pl.nP, pl.nparts)));
+        b_tuples = std::max<size_t>(b_tuples, (size_t) pl.nparts * (fixed_cap2(pl.nB, pl.nparts) + fixed_cap2(pl.nP, pl.nparts)) + kTile);
     if (pl.b2 > 0 && (rc = ensure(ctx, ctx->bufB, b_tuples * sizeof(Tup)))) return rc;
     u64 cap = (u64) pl.nparts + pl.nP / kProbeChunk + 2;
     if ((rc = ensure(ctx, ctx->items, cap * sizeof(Item)))) return rc;

@@ -59,6 +59,9 @@ struct PartRel {
     const u32 *in_rid;
     u64 *out_val;          // output when `out` is null (non-peer scatter only)
     u32 *out_rid;
+    // k_scatter<LIMIT>: a run that does not fit its partition's region is written to the kTile tuples at out[dump..]
+    // instead (nothing out of bounds, no per-tuple check); the overflow flag makes the host discard the attempt.
+    u64 dump;
 };
 // tuple idx of a relation in either form
 // How a partitioning kernel reads / writes tuples: 16-byte AoS both ways (everything single-GPU), or the
@@ -334,7 +337,13 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
             u32 d = tid * kDigitsPerThread + k;
             if (d < a.ndig) {
                 s_off[d] = ex;
-                s_delta[d] = g[k] - ex;
+                u64 delta = g[k] - ex;
+                // (the reservation's result is first looked at here, after the scan, so its latency stays hidden)
+                if (LIMIT && c[k] && g[k] + c[k] > ((u64) seg_group(r, seg) * a.ndig + d + 1) * r.limit_cap) {
+                    *a.overflow = 1;  // the optimistic layout is too small: this run goes to the dump tile
+                    delta = r.dump;
+                }
+                s_delta[d] = delta;
             }
             ex += c[k];
         }
@@ -365,11 +374,6 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
                 Tup t = s_tup[i];
                 u32 d = digit<KIND>(t.val, a);
                 Tup *ob = (KIND == kDigitShard && !a.shard_local) ? a.peer_out[ri][d >> a.sub_bits] : r.out;
-                // the optimistic layout is too small: partition (segment group, digit) ends at (index + 1) * capacity
-                if (LIMIT && s_delta[d] + i >= ((u64) seg_group(r, seg) * a.ndig + d + 1) * r.limit_cap) {
-                    *a.overflow = 1;
-                    continue;
-                }
                 if (IO != kIoSoaOut) {
                     st_stream(ob + s_delta[d] + i, t);
                 } else {  // 12-byte SoA output; a row id that does not fit 32 bits is an error the host reports
@@ -681,10 +685,11 @@ struct FixedArgs {
     u32 *overflow;
     u32 rel_mask;         // bit r set: relation r uses the fixed-capacity layout (the other one has a histogram)
 };
+__device__ __forceinline__ u64 fixed_beg1(const FixedArgs &a, int ri, u32 d) { return (u64) d * a.cap[ri]; }
 __global__ void k_fixed_cursors(FixedArgs a) {
     const int ri = blockIdx.x;
     if (!((a.rel_mask >> ri) & 1u)) return;
-    for (u32 d = threadIdx.x; d < a.ndig; d += blockDim.x) a.cursor[ri][d] = (u64) d * a.cap[ri];
+    for (u32 d = threadIdx.x; d < a.ndig; d += blockDim.x) a.cursor[ri][d] = fixed_beg1(a, ri, d);
 }
 __global__ void __launch_bounds__(kMaxDigits) k_fixed_finish(FixedArgs a) {
     __shared__ u64 s_w[33];
@@ -693,11 +698,12 @@ __global__ void __launch_bounds__(kMaxDigits) k_fixed_finish(FixedArgs a) {
     const u32 tid = threadIdx.x;
     u64 beg = 0, cnt = 0;
     if (tid < a.ndig) {
-        beg = (u64) tid * a.cap[ri];
+        beg = fixed_beg1(a, ri, tid);
+        const u64 room = (u64) (tid + 1) * a.cap[ri] - beg;
         cnt = a.cursor[ri][tid] - beg;
-        if (cnt > a.cap[ri]) {
+        if (cnt > room) {
             *a.overflow = 1;
-            cnt = a.cap[ri];
+            cnt = room;
         }
     }
     u64 total, ttotal;
@@ -732,10 +738,13 @@ struct PlanFixedArgs {
     u32 *err;
     u32 *overflow;
 };
+// Region starts are multiples of 8 tuples (128-byte lines): measured 5 % faster in k_join than unaligned or
+// pseudo-randomly shifted starts (profiles/r01_tuning_notes.md).
+__device__ __forceinline__ u64 fixed_beg(const PlanFixedArgs &a, int ri, u32 p) { return (u64) p * a.cap[ri]; }
 __global__ void k_fixed_cursors2(PlanFixedArgs a) {
     const int ri = blockIdx.y;
     const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < a.nseg * a.ndig) a.end[ri][p] = (u64) p * a.cap[ri];
+    if (p < a.nseg * a.ndig) a.end[ri][p] = fixed_beg(a, ri, p);
 }
 __global__ void __launch_bounds__(kMaxDigits) k_plan_fixed(PlanFixedArgs a) {
     __shared__ u32 s_w32[32];
@@ -746,11 +755,11 @@ __global__ void __launch_bounds__(kMaxDigits) k_plan_fixed(PlanFixedArgs a) {
     if (tid < a.ndig) {
 #pragma unroll
         for (int ri = 0; ri < 2; ++ri) {
-            const u64 b = (u64) p * a.cap[ri];
+            const u64 b = fixed_beg(a, ri, p), room = (u64) (p + 1) * a.cap[ri] - b;
             u64 c = a.end[ri][p] - b;
-            if (c > a.cap[ri]) {
+            if (c > room) {
                 *a.overflow = 1;
-                c = a.cap[ri];
+                c = room;
                 a.end[ri][p] = b + c;
             }
             a.beg[ri][p] = b;
