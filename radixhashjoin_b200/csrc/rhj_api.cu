@@ -898,6 +898,7 @@ int rhj_create(int device, rhj_ctx **out) {
     if ((e = getenv("RHJ_NO_OPT"))) ctx->optimistic = atoi(e) == 0;
     if ((e = getenv("RHJ_FORCE_OPT"))) ctx->force_optimistic = atoi(e) != 0;
     if ((e = getenv("RHJ_NO_OPT2"))) ctx->optimistic2 = atoi(e) == 0;
+    if ((e = getenv("RHJ_NO_SHARD_OPT2"))) ctx->shard_optimistic2 = atoi(e) == 0;
     if ((e = getenv("RHJ_HOST_CHUNK"))) ctx->host_chunk = std::max<long long>(1, atoll(e));
     if ((e = getenv("RHJ_SHARD_SCATTER_MODE"))) ctx->shard_scatter_mode = atoi(e);
     if (cudaSetDevice(device) != cudaSuccess ||
@@ -1456,6 +1457,9 @@ int rhj_shardx_begin(rhj_ctx *ctx, const rhj_shard_plan *sp, void *stream) {
     if ((rc = slot_arrays(ctx, 1u << sp->bits_total, 2, s2))) return rc;
     CK(cudaMemsetAsync(s2.hist2, 0, ((size_t) 1 << sp->bits_total) * 8, st));
     ctx->shard_n[0] = ctx->shard_n[1] = ctx->shard_n[2] = 0;
+    ctx->shard_cap[0] = ctx->shard_cap[1] = ctx->shard_cap[2] = 0;
+    ctx->shard_poisson[0] = ctx->shard_poisson[1] = ctx->shard_poisson[2] = false;
+    ctx->shard_count = 0;
     return RHJ_OK;
 }
 
@@ -1546,10 +1550,23 @@ int rhj_shardx_layout_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rank, i
     CK(cudaGetLastError());
     ctx->info.kernel_launches++;
     const u32 W = sp->world, nd1 = 1u << sp->bits_pass1;
-    static thread_local u64 h_tot[kMaxPeers * kMaxPeers], h_loc[kMaxDigits + 1];
+    static thread_local u64 h_tot[kMaxPeers * kMaxPeers], h_loc[kMaxDigits + 1], h_off1[kMaxDigits + 1];
     CK(cudaMemcpyAsync(h_tot, sm.tot, (size_t) W * W * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(h_loc, sl.loc_off, ((size_t) (W << sp->bits_pass1) + 1) * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(h_off1, sl.off1, ((size_t) nd1 + 1) * 8, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    {
+        // Index of dispersion of the pass-1 partition sizes this rank receives (exact counts): 1 for hashed distinct keys,
+        // f for keys repeated f times.  Only Poisson-like data gets the histogram-free second pass.
+        double sum = 0, sq = 0;
+        for (u32 i = 0; i < nd1; ++i) {
+            const double c = (double) (h_off1[i + 1] - h_off1[i]);
+            sum += c;
+            sq += c * c;
+        }
+        const double mean = sum / nd1, var = sq / nd1 - mean * mean;
+        ctx->shard_poisson[rel] = nd1 >= 16 && mean >= 4096.0 && var <= 1.75 * mean;
+    }
     u64 total = 0;
     for (u32 d = 0; d < W; ++d) {
         send_off[d] = h_loc[(size_t) d * nd1];
@@ -1567,15 +1584,28 @@ int rhj_shardx_layout_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rank, i
 // Pass 2 of slot `rel` over what this rank received (d_recv[n_recv], world << bits_pass1 pieces):
 // histogram, per-partition offsets, scatter into the slot's final partition buffer.  Enqueues only.
 static int shardx_pass2_impl(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_recv,
-                             const uint64_t *d_recv_val, const uint32_t *d_recv_rid, uint64_t n_recv, void *stream) {
+                             const uint64_t *d_recv_val, const uint32_t *d_recv_rid, uint64_t n_recv, void *stream,
+                             bool allow_fixed = true) {
     if (!ctx || !sp || rel < 0 || rel > 2 || (n_recv && !d_recv && (!d_recv_val || !d_recv_rid))) return RHJ_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = pick(ctx, stream);
     SlotArrays sl;
     int rc;
-    if ((rc = slot_arrays(ctx, 1u << sp->bits_total, rel, sl))) return rc;
+    const u32 nparts = 1u << sp->bits_total;
+    if ((rc = slot_arrays(ctx, nparts, rel, sl))) return rc;
     ctx->shard_recv[rel] = (const Tup *) d_recv;
-    if ((rc = ensure(ctx, *sl.out, std::max<u64>(n_recv, 1) * sizeof(Tup)))) return rc;
+    ctx->shard_recv_val[rel] = (const u64 *) d_recv_val;
+    ctx->shard_recv_rid[rel] = d_recv_rid;
+    // histogram-free second pass (fixed-capacity final partitions) when the received sizes look Poisson
+    bool fixed = allow_fixed && ctx->optimistic && ctx->shard_optimistic2 && d_recv && sp->bits_pass2 > 0 && sp->bits_pass2 <= 9 &&
+                 n_recv >= ((u64) 1 << 16) && (ctx->shard_poisson[rel] || ctx->force_optimistic);
+    if (fixed && ctx->opt2_skip > 0 && !ctx->force_optimistic) {
+        ctx->opt2_skip--;
+        fixed = false;
+    }
+    const u64 cap = fixed ? fixed_cap2(n_recv, nparts) : 0;
+    ctx->shard_cap[rel] = cap;
+    if ((rc = ensure(ctx, *sl.out, (fixed ? (u64) nparts * cap + kTile : std::max<u64>(n_recv, 1)) * sizeof(Tup)))) return rc;
     const u32 nd1 = 1u << sp->bits_pass1, npieces = sp->world << sp->bits_pass1;
     PartArgs b{};
     // bits_pass2 == 0 (tiny relations): a one-digit pass that only merges the pieces of a partition
@@ -1590,6 +1620,24 @@ static int shardx_pass2_impl(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, co
         b.rel[0].in_rid = d_recv_rid;
     }
     if ((rc = build_tile_tables(ctx, st, b, 1, rel))) return rc;
+    if (fixed) {
+        Meta m;
+        if ((rc = layout_meta(ctx, nparts, m))) return rc;
+        b.overflow = (u32 *) (m.scalars + kScOverflow);
+        b.rel[0].limit_cap = cap;
+        b.rel[0].dump = (u64) nparts * cap;
+        PlanFixedArgs pf{};
+        pf.end[0] = sl.cur2;
+        pf.beg[0] = sl.off2;
+        pf.cap[0] = cap;
+        pf.nseg = nd1;
+        pf.ndig = b.ndig;
+        k_fixed_cursors2<<<dim3((nparts + 255) / 256, 1), 256, 0, st>>>(pf);
+        CK(cudaGetLastError());
+        ctx->info.kernel_launches++;
+        if (rel == 0) mark(ctx, st, RHJ_PHASE_SCATTER2);
+        return launch_scatter(ctx, st, b, kDigitHash, true, true);
+    }
     if (rel == 0) mark(ctx, st, RHJ_PHASE_HIST2);
     if ((rc = launch_hist(ctx, st, b, kDigitHash, true))) return rc;
     ScanPartsRelArgs sr{};
@@ -1635,48 +1683,73 @@ int rhj_shardx_join_slots_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int bui
     if ((rc = layout_meta(ctx, nparts, m))) return rc;
     if ((rc = slot_arrays(ctx, nparts, build_slot, sb))) return rc;
     if ((rc = slot_arrays(ctx, nparts, probe_slot, spb))) return rc;
-    // per-launch scalars start from zero; the output cursor only when a new result starts
-    CK(cudaMemsetAsync(m.scalars + kScWork0, 0, 8, st));
-    CK(cudaMemsetAsync(m.scalars + kScNItems, 0, 8, st));
-    if (first) CK(cudaMemsetAsync(m.scalars + kScCursor, 0, 8, st));
-    if (nB && nP) {
-        u64 cap64 = (u64) nparts + nP / kProbeChunk + 2;
-        if (cap64 > 0x7fffffffull) return fail(ctx, RHJ_ERR_ARG, "relation too large for the work-item table");
-        u32 item_cap = (u32) cap64;
-        if ((rc = ensure(ctx, ctx->items, (size_t) item_cap * sizeof(Item)))) return rc;
-        mark(ctx, st, RHJ_PHASE_PLAN);
-        PlanPartsArgs pa{};
-        pa.offB = sb.off2;
-        pa.offP = spb.off2;
-        pa.ndig = std::min<u32>(nparts, kMaxDigits);
-        pa.items = (Item *) ctx->items.p;
-        pa.item_cap = item_cap;
-        pa.nitems = (u32 *) (m.scalars + kScNItems);
-        pa.err = (u32 *) (m.scalars + kScErr);
-        k_plan_parts<<<nparts / pa.ndig, kMaxDigits, 0, st>>>(pa);
-        CK(cudaGetLastError());
-        ctx->info.kernel_launches++;
-        ctx->cur.valid = true;
-        ctx->cur.build = (const Tup *) sb.out->p;
-        ctx->cur.probe = (const Tup *) spb.out->p;
-        ctx->cur.offB = sb.off2;
-        ctx->cur.offP = spb.off2;
-        ctx->cur.endB = sb.off2 + 1;
-        ctx->cur.endP = spb.off2 + 1;
-        ctx->cur.nparts = nparts;
-        ctx->cur.item_cap = item_cap;
-        // slot 0 is R; slots 1 and 2 hold S tuples unless S is the (unsplit) build side
-        ctx->cur.build_is_S = build_slot != 0;
-        JoinArgs j = join_args(ctx, kScWork0);
-        j.out = (Pair *) d_out;
-        j.capacity = capacity;
-        mark(ctx, st, RHJ_PHASE_JOIN);
-        if ((rc = launch_join<kJoinFused>(ctx, st, j, item_cap))) return rc;
-        mark(ctx, st, -1);
+    if (first) ctx->shard_count = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {  // attempt 1 = after a fixed-capacity second pass overflowed
+        // per-launch scalars start from zero; the output cursor restarts where the previous join of this step ended
+        CK(cudaMemsetAsync(m.scalars + kScWork0, 0, 8, st));
+        CK(cudaMemsetAsync(m.scalars + kScNItems, 0, 8, st));
+        ctx->h_scalars[kScCursor] = ctx->shard_count;
+        CK(cudaMemcpyAsync(m.scalars + kScCursor, ctx->h_scalars + kScCursor, 8, cudaMemcpyHostToDevice, st));
+        if (nB && nP) {
+            u64 cap64 = (u64) nparts + nP / kProbeChunk + 2;
+            if (cap64 > 0x7fffffffull) return fail(ctx, RHJ_ERR_ARG, "relation too large for the work-item table");
+            u32 item_cap = (u32) cap64;
+            if ((rc = ensure(ctx, ctx->items, (size_t) item_cap * sizeof(Item)))) return rc;
+            mark(ctx, st, RHJ_PHASE_PLAN);
+            const u64 capB = ctx->shard_cap[build_slot], capP = ctx->shard_cap[probe_slot];
+            PlanPartsArgs pa{};
+            pa.offB = sb.off2;
+            pa.offP = spb.off2;
+            pa.endB = capB ? sb.cur2 : nullptr;
+            pa.endP = capP ? spb.cur2 : nullptr;
+            pa.capB = capB;
+            pa.capP = capP;
+            pa.ndig = std::min<u32>(nparts, kMaxDigits);
+            pa.items = (Item *) ctx->items.p;
+            pa.item_cap = item_cap;
+            pa.nitems = (u32 *) (m.scalars + kScNItems);
+            pa.err = (u32 *) (m.scalars + kScErr);
+            pa.overflow = (u32 *) (m.scalars + kScOverflow);
+            k_plan_parts<<<nparts / pa.ndig, kMaxDigits, 0, st>>>(pa);
+            CK(cudaGetLastError());
+            ctx->info.kernel_launches++;
+            ctx->cur.valid = true;
+            ctx->cur.build = (const Tup *) sb.out->p;
+            ctx->cur.probe = (const Tup *) spb.out->p;
+            ctx->cur.offB = sb.off2;
+            ctx->cur.offP = spb.off2;
+            ctx->cur.endB = capB ? sb.cur2 : sb.off2 + 1;
+            ctx->cur.endP = capP ? spb.cur2 : spb.off2 + 1;
+            ctx->cur.nparts = nparts;
+            ctx->cur.item_cap = item_cap;
+            // slot 0 is R; slots 1 and 2 hold S tuples unless S is the (unsplit) build side
+            ctx->cur.build_is_S = build_slot != 0;
+            ctx->info.optimistic_pass1 = (capB ? 4u : 0u) | (capP ? 8u : 0u);
+            JoinArgs j = join_args(ctx, kScWork0);
+            j.out = (Pair *) d_out;
+            j.capacity = capacity;
+            mark(ctx, st, RHJ_PHASE_JOIN);
+            if ((rc = launch_join<kJoinFused>(ctx, st, j, item_cap))) return rc;
+            mark(ctx, st, -1);
+        }
+        rc = read_scalars(ctx, st);
+        if (rc != kRetryExact || attempt == 1) break;
+        // A fixed-capacity region overflowed (duplicate-heavy data): redo the second pass of every slot that used one through
+        // the exact histogram path -- what they received is still in place -- and join again.
+        CK(cudaMemsetAsync(m.scalars + kScOverflow, 0, 8, st));
+        ctx->opt2_skip = 16;
+        for (int sl = 0; sl < 3; ++sl) {  // every slot partitioned so far: the flag does not say which one overflowed
+            if (!ctx->shard_cap[sl]) continue;
+            if ((rc = shardx_pass2_impl(ctx, sp, sl, (const rhj_tuple *) ctx->shard_recv[sl], (const uint64_t *) ctx->shard_recv_val[sl],
+                                        ctx->shard_recv_rid[sl], ctx->shard_n[sl], stream, false)))
+                return rc;
+        }
     }
-    if ((rc = read_scalars(ctx, st))) return rc;
+    if (rc == kRetryExact) return fail(ctx, RHJ_ERR_STATE, "sharded join: overflow flag set on the exact path");
+    if (rc) return rc;
     *count = ctx->h_scalars[kScCursor];
     if (*count > capacity) return fail(ctx, RHJ_ERR_CAPACITY, "output buffer too small for the fused emitter");
+    ctx->shard_count = *count;
     return RHJ_OK;
 }
 

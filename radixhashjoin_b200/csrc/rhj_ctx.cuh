@@ -88,6 +88,12 @@ struct rhj_ctx {
     rhj_plan_info info{};
     u64 shard_n[3] = {0, 0, 0};            // sharded join: tuples received per slot
     const Tup *shard_recv[3] = {nullptr, nullptr, nullptr};
+    const u64 *shard_recv_val[3] = {nullptr, nullptr, nullptr};   // 12-byte form of the same
+    const u32 *shard_recv_rid[3] = {nullptr, nullptr, nullptr};
+    bool shard_poisson[3] = {false, false, false};  // the received pass-1 partition sizes look like hashed distinct keys
+    u64 shard_cap[3] = {0, 0, 0};                   // > 0: the slot's final partitions lie in fixed-capacity regions of this size
+    u64 shard_count = 0;                            // pairs emitted by the joins of this sharded step so far
+    bool shard_optimistic2 = true;                  // RHJ_NO_SHARD_OPT2=1 disables the histogram-free second pass
 
     // optional per-phase timing (rhj_set_profiling)
     bool profiling = false;

@@ -744,7 +744,10 @@ __device__ __forceinline__ u64 fixed_beg(const PlanFixedArgs &a, int ri, u32 p) 
 __global__ void k_fixed_cursors2(PlanFixedArgs a) {
     const int ri = blockIdx.y;
     const u32 p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p < a.nseg * a.ndig) a.end[ri][p] = fixed_beg(a, ri, p);
+    if (p < a.nseg * a.ndig) {
+        a.end[ri][p] = fixed_beg(a, ri, p);
+        a.beg[ri][p] = fixed_beg(a, ri, p);
+    }
 }
 __global__ void __launch_bounds__(kMaxDigits) k_plan_fixed(PlanFixedArgs a) {
     __shared__ u32 s_w32[32];
@@ -810,14 +813,28 @@ __global__ void __launch_bounds__(kMaxDigits) k_scan_parts_rel(ScanPartsRelArgs 
 }
 // ... and the planning half: work items of every final partition from both relations' offsets
 struct PlanPartsArgs {
-    const u64 *offB;
+    const u64 *offB;   // [nparts (+1)] partition starts
     const u64 *offP;
+    u64 *endB;         // fixed-capacity layouts: [nparts] scatter cursors = partition ends (clamped here); null = packed, end = off[p + 1]
+    u64 *endP;
+    u64 capB, capP;    // region capacity of a fixed-capacity layout
     u32 ndig;  // partitions per CTA
     Item *items;
     u32 item_cap;
     u32 *nitems;
     u32 *err;
+    u32 *overflow;
 };
+__device__ __forceinline__ u64 part_size(const u64 *off, u64 *end, u64 cap, u32 p, u32 *overflow) {
+    if (!end) return off[p + 1] - off[p];
+    u64 c = end[p] - off[p];
+    if (c > cap) {  // an optimistic region overflowed: keep every range inside the buffer, the host re-runs the exact path
+        *overflow = 1;
+        c = cap;
+        end[p] = off[p] + c;
+    }
+    return c;
+}
 __global__ void __launch_bounds__(kMaxDigits) k_plan_parts(PlanPartsArgs a) {
     __shared__ u64 s_w[33];
     __shared__ u32 s_base;
@@ -825,7 +842,7 @@ __global__ void __launch_bounds__(kMaxDigits) k_plan_parts(PlanPartsArgs a) {
     const u32 p = blockIdx.x * a.ndig + tid;
     u64 k = 0;
     if (tid < a.ndig) {
-        u64 nb = a.offB[p + 1] - a.offB[p], np = a.offP[p + 1] - a.offP[p];
+        u64 nb = part_size(a.offB, a.endB, a.capB, p, a.overflow), np = part_size(a.offP, a.endP, a.capP, p, a.overflow);
         if (nb && np) k = (np + kProbeChunk - 1) / kProbeChunk;
     }
     u64 total;

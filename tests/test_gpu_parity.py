@@ -510,6 +510,61 @@ def test_dma_shard_join_compact_rowids_emulated_ranks(world, n_local, dom, id_ba
         e.close()
 
 
+@pytest.mark.parametrize("hot", [0, 200000])
+def test_dma_shard_join_histogram_free_second_pass(hot, monkeypatch):
+    """Received shards whose pass-1 partition sizes look Poisson take the histogram-free second pass (fixed-capacity
+    final partitions, plan bits 4 | 8).  With `hot` copies of one probe value forced through it, one region overflows:
+    that rank redoes its second passes through the exact path and still emits exactly the oracle's pairs."""
+    from radixhashjoin_b200 import RadixHashJoin
+    if hot:
+        monkeypatch.setenv("RHJ_FORCE_OPT", "1")
+    world, n_local = 2, 1 << 20
+    rng = np.random.default_rng(2024 + hot)
+    Rg, Sg = rand_rel(rng, world * n_local, 1 << 62), rand_rel(rng, world * n_local, 1 << 62, 1 << 34)
+    Sg["payload"][::2] = Rg["payload"][:n_local]                         # half of the probe side matches
+    if hot:
+        Sg["payload"][1:2 * hot:2] = np.uint64(12345)                     # one hot probe value (absent from R)
+    exp = O.pairs_digest(O.oracle_join(Rg, Sg))
+    engines = [RadixHashJoin(0) for _ in range(world)]
+    shards = [(to_dev(Rg[r * n_local:(r + 1) * n_local]), to_dev(Sg[r * n_local:(r + 1) * n_local])) for r in range(world)]
+    plan = engines[0].shard_plan(len(Rg), len(Sg), world)
+    ndig = world << plan.bits_pass1
+    stage = [[torch.empty((n_local, 2), dtype=torch.int64, device=DEV) for _ in range(2)] for _ in range(world)]
+    hist = [[torch.empty(ndig, dtype=torch.int64, device=DEV) for _ in range(2)] for _ in range(world)]
+    for r in range(world):
+        engines[r].shardx_begin(plan)
+        for rel in (0, 1):
+            engines[r].shardx_pass1(plan, rel, shards[r][rel], stage[r][rel], hist[r][rel])
+    lay = [[None, None] for _ in range(world)]
+    for rel in (0, 1):
+        all_hist = torch.stack([hist[r][rel] for r in range(world)])
+        for r in range(world):
+            lay[r][rel] = engines[r].shardx_layout(plan, r, rel, all_hist)
+    recv = [[torch.empty((max(lay[r][rel][3], 1), 2), dtype=torch.int64, device=DEV) for rel in (0, 1)] for r in range(world)]
+    for rel in (0, 1):
+        for r in range(world):
+            so, sc, do, _ = lay[r][rel]
+            for d in range(world):
+                recv[d][rel][do[d]:do[d] + sc[d]].copy_(stage[r][rel][so[d]:so[d] + sc[d]])
+    torch.cuda.synchronize()
+    total, ssum, sxor, bits = 0, 0, 0, []
+    for r in range(world):
+        for rel in (0, 1):
+            engines[r].shardx_pass2(plan, rel, recv[r][rel][:lay[r][rel][3]])
+        out = torch.empty((exp[0], 2), dtype=torch.int64, device=DEV)
+        pairs, n = engines[r].shardx_join(plan, out)
+        d = engines[r].pairs_digest(pairs)
+        total, ssum, sxor = total + n, (ssum + d[1]) % (1 << 64), sxor ^ d[2]
+        bits.append(engines[r].last_plan()["optimistic_pass1"])
+    assert (total, ssum, sxor) == exp
+    if hot:
+        assert sorted(bits) == [0, 12]        # the rank that got the hot value fell back, the other one did not
+    else:
+        assert bits == [12, 12]
+    for e in engines:
+        e.close()
+
+
 # ---- pipelined host join (large inputs: chunked probe side, H2D / compute / D2H overlapped) ----------------
 @pytest.mark.parametrize("nR,nS,dom", [(30000, 100000, 20000), (100000, 30000, 1 << 40), (4000, 50000, 700), (200000, 200000, 150000),
                                        (5000, 2001, 3)])
