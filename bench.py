@@ -178,6 +178,14 @@ def small_work_wall(with_reference=False):
         return res
 
 
+def _workload_name(log2n, world):
+    """config.workload of both arms: the single-GPU configuration, or the global relation pair sharded over N ranks"""
+    if world == 1:
+        return f"uniform_unique_2^{log2n}x2^{log2n}"
+    gbits = log2n + (world.bit_length() - 1)
+    return f"uniform_unique_global_2^{gbits}x2^{gbits}_sharded_over_{world}"
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -186,7 +194,7 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"uniform_unique_2^{args.log2n}x2^{args.log2n}", "tuples_per_gpu": 2 << args.log2n,
+            "config": {"workload": _workload_name(args.log2n, args.gpus), "tuples_per_gpu": 2 << args.log2n,
                        "tuple_bytes": 16,
                        "sample_per_step": f"2^{log2n} x 2^{log2n} tuples of the same generator (the reference's throughput is "
                                           "flat in size: BASELINE.md 2.2)"},
@@ -233,7 +241,7 @@ def run_b200(args, rank, world, local_rank):
         w = W.uniform_unique(log2n, dev, row_offset=rank * n_local, log2_global=gbits)
         R, S = w.R, w.S
         expected = None
-        wname = f"uniform_unique_global_2^{gbits}x2^{gbits}_sharded_over_{world}"
+        wname = _workload_name(log2n, world)
     nR, nS = R.shape[0], S.shape[0]
     n_in_local = nR + nS
     compact = False

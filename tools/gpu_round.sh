@@ -16,7 +16,7 @@ echo "== bench"
 timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench exit $?"
 cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
 if [ "${1:-}" != "quick" ]; then
-  for v in "RHJ_NO_DIG=1" "RHJ_SCATTER_MODE=1"; do
+  for v in "RHJ_NO_OPT2=1" "RHJ_NO_OPT=1" "RHJ_SCATTER_MODE=1"; do
     echo "== bench $v"
     env $v timeout 600 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu --no-small-work > gpurun_out/bench_$v.json 2> gpurun_out/bench_$v.err
     cat gpurun_out/bench_$v.json; tail -3 gpurun_out/bench_$v.err
