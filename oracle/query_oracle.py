@@ -149,16 +149,28 @@ def update_intermediate(inter, pairs, t1, t2):
     return new
 
 
-def execute(q, relations, join_fn, trace=None):
+def execute(q, relations, join_fn, trace=None, update_fn=None):
     """Query::execute (Query.cpp:204-211) + run_joins (164-201).  join_fn(R, S) -> PAIR array.
-    Returns the printed line (Query.cpp:226-235).  `trace` collects (nR, nS, count, R, S, pairs)."""
+    Returns the printed line (Query.cpp:226-235).  `trace` collects (R, S, pairs) per executed join.
+    `update_fn(inter, pairs, t1, t2)` replaces update_intermediate (the tests pass the CUDA one)."""
+    if update_fn is None:
+        update_fn = update_intermediate
     filtered_out, filtered = run_filters(q, relations)
     inter = [None] * len(q.table)
     if not filtered_out:
         for (t1, c1, t2, c2) in q.join:
             if t1 == t2:
-                raise NotImplementedError("same-binding predicate (parse_table, intermediate.cpp:11-44) "
-                                          "is not exercised by the pinned workload")
+                # parse_table (intermediate.cpp:11-44): a predicate between two columns of ONE binding.  Only its first
+                # branch is defined behaviour in the reference (the binding has not been joined yet: keep the filtered
+                # rows whose two values are equal, 18-26); the second branch dereferences end() (27-43).
+                if inter[t1] is not None:
+                    raise NotImplementedError("same-binding predicate on an already joined binding: undefined behaviour "
+                                              "in the reference (intermediate.cpp:27-43)")
+                cols = relations[q.table[t1]]
+                rows = filtered[t1]
+                keep = rows[cols[c1][rows.astype(np.int64)] == cols[c2][rows.astype(np.int64)]]
+                inter[t1] = keep if keep.size else None      # an empty vector reads as "not joined yet" (structs.cpp:230)
+                continue
             R = create_relation(relations[q.table[t1]][c1], filtered[t1], inter[t1])
             S = create_relation(relations[q.table[t2]][c2], filtered[t2], inter[t2])
             pairs = join_fn(R, S)
@@ -167,7 +179,7 @@ def execute(q, relations, join_fn, trace=None):
             if len(pairs) == 0:                      # Query.cpp:188-191
                 filtered_out = True
                 break
-            inter = update_intermediate(inter, pairs, t1, t2)
+            inter = update_fn(inter, pairs, t1, t2)
     if filtered_out:
         return " ".join("NULL" for _ in q.proj)
     sums = []

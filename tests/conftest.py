@@ -38,6 +38,27 @@ def small_joins_golden():
 
 
 @pytest.fixture(scope="session")
+def edge_dir(tmp_path_factory):
+    """The `edge` workload (tests/golden/make_edge.py): six synthetic relations + init/work and the result the
+    unmodified reference printed for them."""
+    d = tmp_path_factory.mktemp("edgework") / "edge"    # the init file names ./edge/rN
+    d.mkdir()
+    with tarfile.open(os.path.join(GOLDEN, "edge_relations.tar.xz")) as tf:
+        tf.extractall(d)
+    for name in ("edge.init", "edge.work", "edge.result"):
+        with open(os.path.join(GOLDEN, name), "rb") as src, open(os.path.join(d, name), "wb") as dst:
+            dst.write(src.read())
+    return str(d)
+
+
+@pytest.fixture(scope="session")
+def edge_joins_golden():
+    """per-join records the unmodified reference logged for edge.work (tests/golden/make_edge.py)."""
+    with open(os.path.join(GOLDEN, "edge_joins.txt")) as f:
+        return sorted(tuple(int(v) for v in line.split()) for line in f if line.strip())
+
+
+@pytest.fixture(scope="session")
 def engine():
     """One rhj context on cuda:0.  Fails loudly (no skip, no fallback) if the CUDA library or the GPU
     is missing -- `-m gpu` tests are only meaningful on the GPU box."""

@@ -300,12 +300,8 @@ def test_intermediate_filter_equals_oracle(engine, wide):
     assert np.array_equal(_rows(got), _rows([a[keep], b[keep], c[keep]]))
 
 
-def test_small_workload_with_gpu_intermediate(engine, small_dir):
-    """small.work with BOTH the join and update_intermediate on the GPU: all 50 checksum lines"""
-    rels = Q.load_workload(small_dir)
-    queries = Q.parse_work(os.path.join(small_dir, "small.work"))
-    expected = open(os.path.join(small_dir, "small.result")).read().split("\n")
-
+def _gpu_update_fn(engine):
+    """update_intermediate with cases 2 and 3 on the GPU (the Python twin of host/intermediate.cpp)"""
     def gpu_update(inter, pairs, t1, t2):
         e1, e2 = inter[t1] is None, inter[t2] is None
         if e1 and e2:
@@ -321,31 +317,34 @@ def test_small_workload_with_gpu_intermediate(engine, small_dir):
         for i, colv in zip(live, carried):
             new[i] = colv
         return new
+    return gpu_update
 
-    lines = [_execute_with(q, rels, engine, gpu_update) for q in queries]
+
+def test_small_workload_with_gpu_intermediate(engine, small_dir):
+    """small.work with BOTH the join and update_intermediate on the GPU: all 50 checksum lines"""
+    rels = Q.load_workload(small_dir)
+    queries = Q.parse_work(os.path.join(small_dir, "small.work"))
+    expected = open(os.path.join(small_dir, "small.result")).read().split("\n")
+    upd = _gpu_update_fn(engine)
+    lines = [Q.execute(q, rels, lambda R, S: engine.join_host(R, S), update_fn=upd) for q in queries]
     assert lines == expected[:50]
 
 
-def _execute_with(q, rels, engine, update_fn):
-    filtered_out, filtered = Q.run_filters(q, rels)
-    inter = [None] * len(q.table)
-    if not filtered_out:
-        for (t1, c1, t2, c2) in q.join:
-            R = Q.create_relation(rels[q.table[t1]][c1], filtered[t1], inter[t1])
-            S = Q.create_relation(rels[q.table[t2]][c2], filtered[t2], inter[t2])
-            pairs = engine.join_host(R, S)
-            if len(pairs) == 0:
-                filtered_out = True
-                break
-            inter = update_fn(inter, pairs, t1, t2)
-    if filtered_out:
-        return " ".join("NULL" for _ in q.proj)
-    out = []
-    for (b, col) in q.proj:
-        rows = inter[b]
-        with np.errstate(over="ignore"):
-            out.append(0 if rows is None else int(np.add.reduce(rels[q.table[b]][col][rows.astype(np.int64)], dtype=np.uint64)))
-    return " ".join(str(v) for v in out)
+def test_edge_workload_golden_through_gpu(engine, edge_dir, edge_joins_golden):
+    """edge.work (tests/golden/make_edge.py: one relation bound twice, a same-binding predicate, empty joins, a
+    one-row relation, a one-value join column, values >= 2^32, a 288000-row intermediate filtered by a third join)
+    with every join done by librhj.so -- all 13 lines the unmodified reference printed and its 14 per-join records --
+    and again with update_intermediate on the GPU as well."""
+    rels = Q.load_workload(edge_dir, "edge.init")
+    queries = Q.parse_work(os.path.join(edge_dir, "edge.work"))
+    expected = open(os.path.join(edge_dir, "edge.result")).read().split("\n")
+    trace = []
+    lines = [Q.execute(q, rels, lambda R, S: engine.join_host(R, S), trace) for q in queries]
+    assert lines == expected[:13]
+    assert sorted(Q.join_trace_record(*t) for t in trace) == edge_joins_golden
+    upd = _gpu_update_fn(engine)
+    lines = [Q.execute(q, rels, lambda R, S: engine.join_host(R, S), update_fn=upd) for q in queries]
+    assert lines == expected[:13]
 
 
 HOST_BIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "radixhashjoin_b200", "host", "_build")
@@ -362,6 +361,20 @@ def test_reference_program_with_dropin_translation_units(small_dir):
     out = subprocess.run([os.path.join(HOST_BIN, "join_b200_full")], input=data, cwd=cwd, capture_output=True, timeout=600)
     assert out.returncode == 0, out.stderr.decode()[-2000:]
     assert out.stdout.decode() == open(os.path.join(small_dir, "small.result")).read()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(HOST_BIN, "join_b200_full")),
+                    reason="drop-in binaries are built in the dev container (need the reference sources)")
+def test_reference_program_with_dropin_translation_units_edge_workload(edge_dir):
+    """the same program on edge.work: same-binding predicates go through host/intermediate.cpp's parse_table, the third
+    join of a query through rhj_intermediate_filter_host, a query without joins prints 0."""
+    import subprocess
+    cwd = os.path.dirname(edge_dir)
+    data = open(os.path.join(edge_dir, "edge.init"), "rb").read() + open(os.path.join(edge_dir, "edge.work"), "rb").read()
+    for binary in ("join_b200", "join_b200_full"):
+        out = subprocess.run([os.path.join(HOST_BIN, binary)], input=data, cwd=cwd, capture_output=True, timeout=600)
+        assert out.returncode == 0, out.stderr.decode()[-2000:]
+        assert out.stdout.decode() == open(os.path.join(edge_dir, "edge.result")).read()
 
 
 # ---- multi-GPU fused partition + shuffle, emulated on one GPU ---------------------------------------------

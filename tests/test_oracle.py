@@ -101,6 +101,23 @@ def test_small_workload_golden(small_dir, small_joins_golden):
     assert sorted(Q.join_trace_record(*t) for t in trace) == small_joins_golden
 
 
+def test_edge_workload_golden(edge_dir, edge_joins_golden):
+    """edge.work (what small.work never exercises: one relation bound twice, a same-binding predicate, an empty join,
+    a filter past the column range, two filters on one binding, values >= 2^32, a one-row relation, a one-value join
+    column, a query without joins, a join between two joined bindings over a 288000-row intermediate) through the query
+    oracle: every line the unmodified reference printed, and every per-join record it logged."""
+    rels = Q.load_workload(edge_dir, "edge.init")
+    queries = Q.parse_work(os.path.join(edge_dir, "edge.work"))
+    expected = open(os.path.join(edge_dir, "edge.result")).read().split("\n")
+    trace = []
+    lines = [Q.execute(q, rels, O.oracle_join, trace) for q in queries]
+    assert len(lines) == 13
+    assert lines == expected[:13]
+    assert lines[2] == "NULL NULL" and lines[3] == "NULL" and lines[10] == "0"
+    assert sorted(Q.join_trace_record(*t) for t in trace) == edge_joins_golden
+    assert len(edge_joins_golden) == 14
+
+
 def test_filter_gather_sum_oracles():
     rng = np.random.default_rng(11)
     col = rng.integers(0, 1000, 10000, dtype=np.uint64)
