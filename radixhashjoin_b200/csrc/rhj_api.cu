@@ -899,6 +899,7 @@ int rhj_create(int device, rhj_ctx **out) {
     if ((e = getenv("RHJ_FORCE_OPT"))) ctx->force_optimistic = atoi(e) != 0;
     if ((e = getenv("RHJ_NO_OPT2"))) ctx->optimistic2 = atoi(e) == 0;
     if ((e = getenv("RHJ_NO_SHARD_OPT2"))) ctx->shard_optimistic2 = atoi(e) == 0;
+    if ((e = getenv("RHJ_SHARD_OPT2_WORLD"))) ctx->shard_opt2_world = (u32) std::max(0, atoi(e));
     if ((e = getenv("RHJ_HOST_CHUNK"))) ctx->host_chunk = std::max<long long>(1, atoll(e));
     if ((e = getenv("RHJ_SHARD_SCATTER_MODE"))) ctx->shard_scatter_mode = atoi(e);
     if (cudaSetDevice(device) != cudaSuccess ||
@@ -1596,11 +1597,12 @@ static int shardx_pass2_impl(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, co
     ctx->shard_recv[rel] = (const Tup *) d_recv;
     ctx->shard_recv_val[rel] = (const u64 *) d_recv_val;
     ctx->shard_recv_rid[rel] = d_recv_rid;
-    // histogram-free second pass (fixed-capacity final partitions) when the received sizes look Poisson.  Limited to
-    // second passes of <= 8 bits: measured 8.29 -> 7.49 ms per join on 2 GPUs ([8, 8] bits), but 12.2 instead of 10.3-10.6 ms
-    // in the one run on 8 GPUs ([7, 9] bits) that the round's GPU budget allowed (profiles/r01_multi_gpu_notes.md).
-    bool fixed = allow_fixed && ctx->optimistic && ctx->shard_optimistic2 && d_recv && sp->bits_pass2 > 0 &&
-                 sp->bits_pass2 <= (ctx->force_optimistic ? 9u : 8u) &&
+    // histogram-free second pass (fixed-capacity final partitions) when the received sizes look Poisson.  On by default
+    // only where it was measured to help: 8.29 -> 7.49 ms per join on 2 GPUs; the one run on 8 GPUs that the round's GPU
+    // budget allowed gave 12.2 instead of 10.3-10.6 ms, 4 GPUs are unmeasured (profiles/r01_multi_gpu_notes.md).
+    // RHJ_SHARD_OPT2_WORLD=<n> raises the limit for measurements.
+    bool fixed = allow_fixed && ctx->optimistic && ctx->shard_optimistic2 && d_recv && sp->bits_pass2 > 0 && sp->bits_pass2 <= 9 &&
+                 (sp->world <= ctx->shard_opt2_world || ctx->force_optimistic) &&
                  n_recv >= ((u64) 1 << 16) && (ctx->shard_poisson[rel] || ctx->force_optimistic);
     if (fixed && ctx->opt2_skip > 0 && !ctx->force_optimistic) {
         ctx->opt2_skip--;

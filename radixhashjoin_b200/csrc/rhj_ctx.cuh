@@ -94,6 +94,7 @@ struct rhj_ctx {
     u64 shard_cap[3] = {0, 0, 0};                   // > 0: the slot's final partitions lie in fixed-capacity regions of this size
     u64 shard_count = 0;                            // pairs emitted by the joins of this sharded step so far
     bool shard_optimistic2 = true;                  // RHJ_NO_SHARD_OPT2=1 disables the histogram-free second pass
+    u32 shard_opt2_world = 2;                       // ... which is on by default up to this many ranks (RHJ_SHARD_OPT2_WORLD)
 
     // optional per-phase timing (rhj_set_profiling)
     bool profiling = false;
