@@ -1,6 +1,9 @@
 """Per-rank, per-step view of the DMA-shipped sharded join (torchrun, one process per GPU).
 
-    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 tools/diag_dma_steps.py [log2n=27] [steps=12]
+    torchrun --nproc-per-node 8 --master-addr 127.0.0.1 tools/diag_dma_steps.py [log2n=27] [steps=12] [free]
+
+With `free` the steps run back to back as in bench.py's timed loop (no barrier or synchronize between them; a step's time
+is the distance between the events recorded in front of consecutive steps).
 
 bench.py reports one average over the max of all ranks; this prints, for every rank, the device time of every step, the
 kernels the library launched in it (a fixed-capacity overflow shows up as extra launches: the second passes are redone)
@@ -33,18 +36,33 @@ def main():
     slack = int(n_local * 1.05) + 4096
     out = torch.empty((slack, 2), dtype=torch.int64, device=dev)
     dj = DmaShardedJoin(eng, world, rank, n_local * world, n_local * world, n_local, slack)
-    rows = []
+    free = len(sys.argv) > 3 and sys.argv[3] == "free"
+    rows, evs = [], []
+    dist.barrier()
+    torch.cuda.synchronize()
     for it in range(steps):
-        dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if not free:
+            dist.barrier()
+            torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True)
         e0.record()
+        evs.append(e0)
         pairs, count, (nB, nP) = dj.step(w.R, w.S, out)
-        e1.record()
-        torch.cuda.synchronize()
         plan = eng.last_plan()
-        rows.append({"step": it, "ms": round(e0.elapsed_time(e1), 3), "launches": plan["kernel_launches"],
-                     "bits": plan["optimistic_pass1"], "count": int(count), "recv": [int(nB), int(nP)]})
+        rows.append({"step": it, "launches": plan["kernel_launches"], "bits": plan["optimistic_pass1"], "count": int(count),
+                     "recv": [int(nB), int(nP)]})
+        if not free:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            torch.cuda.synchronize()
+            rows[-1]["ms"] = round(e0.elapsed_time(e1), 3)
+    e_end = torch.cuda.Event(enable_timing=True)
+    e_end.record()
+    evs.append(e_end)
+    torch.cuda.synchronize()
+    if free:
+        for it in range(steps):
+            rows[it]["ms"] = round(evs[it].elapsed_time(evs[it + 1]), 3)
     gathered = [None] * world
     dist.all_gather_object(gathered, rows)
     if rank == 0:
@@ -53,7 +71,7 @@ def main():
             cells = [gathered[r][it] for r in range(world)]
             print(f"{it:4d} " + " ".join(f"{c['ms']:6.2f}/{c['launches']:2d}/{c['bits']:<2d}".ljust(10) for c in cells) +
                   f"  {max(c['ms'] for c in cells):6.2f}")
-        print("cells: ms / kernel launches / plan bits; steps are separated by a barrier (no cross-step overlap)")
+        print("cells: ms / kernel launches / plan bits; " + ("steps back to back" if free else "steps separated by a barrier"))
         print(json.dumps({"world": world, "log2n": log2n, "per_rank": gathered}))
     dist.destroy_process_group()
 
