@@ -241,6 +241,10 @@ int second_pass_and_plan(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Me
     const u64 *offB, *offP, *endB = nullptr, *endP = nullptr;
     bool planned = false;
     u32 item_cap = 0;
+    const u64 cap[2] = {fixed_cap2(pl.nB, pl.nparts), fixed_cap2(pl.nP, pl.nparts)};
+    const size_t regB = (size_t) pl.nparts * cap[0], regP = (size_t) pl.nparts * cap[1];
+    // the padded layout needs ~1.4x the memory of the packed one: when that does not fit, pack (histogram path)
+    if (fixed2 && pl.b2 > 0 && ensure(ctx, ctx->bufB, (regB + regP + kTile) * sizeof(Tup)) != RHJ_OK) fixed2 = false;
     if (pl.b2 == 0) {
         finB = inX[0];
         finP = inX[1];
@@ -248,9 +252,6 @@ int second_pass_and_plan(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Me
         offP = off1X[1];
     } else if (fixed2) {
         // ---- optimistic pass 2: no histogram; final partition p scatters into the fixed region [p * cap, (p + 1) * cap) ----
-        const u64 cap[2] = {fixed_cap2(pl.nB, pl.nparts), fixed_cap2(pl.nP, pl.nparts)};
-        const size_t regB = (size_t) pl.nparts * cap[0], regP = (size_t) pl.nparts * cap[1];
-        if ((rc = ensure(ctx, ctx->bufB, (regB + regP + kTile) * sizeof(Tup)))) return rc;
         Tup *B = (Tup *) ctx->bufB.p;
         PartArgs b{};
         b.shift = 32 - pl.bits;
