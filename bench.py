@@ -255,12 +255,28 @@ def run_b200(args, rank, world, local_rank):
             return eng.join_device(R, S, out=out, emit=emit)
     else:
         slack = int(n_local * 1.05) + 4096
-        recvR = torch.empty((slack, 2), dtype=torch.int64, device=dev)
-        recvS = torch.empty((slack, 2), dtype=torch.int64, device=dev)
         out = torch.empty((slack, 2), dtype=torch.int64, device=dev)
-        eng.reserve(slack, slack)
-        from radixhashjoin_b200.distributed import DmaShardedJoin, FusedShardedJoin, ShardedJoin
-        if args.shuffle == "dma":
+        from radixhashjoin_b200.distributed import DmaShardedJoin, FusedShardedJoin, PipeShardedJoin, ShardedJoin
+        if args.shuffle != "pipe":
+            recvR = torch.empty((slack, 2), dtype=torch.int64, device=dev)
+            recvS = torch.empty((slack, 2), dtype=torch.int64, device=dev)
+            eng.reserve(slack, slack)
+        if args.shuffle == "pipe":
+            # histogram-free chunked pass 1 -> hand-written TMA copy kernel over NVLink -> appended pass 2 -> join;
+            # no collective call and one host synchronisation per step (radixhashjoin_b200/distributed.py)
+            pj = PipeShardedJoin(eng, world, rank, n_local * world, n_local * world, n_local, n_local, chunks=args.chunks,
+                                 exact_recv_capacity=slack)
+
+            def step():
+                pairs, count, _ = pj.step(R, S, out)
+                return pairs, count
+
+            def timeline():
+                marks = []
+                pj.step(R, S, out, marks)
+                torch.cuda.synchronize()
+                return pj.timeline(marks)
+        elif args.shuffle == "dma":
             # pass 1 partitions on (rank | sub-digit) into staging; the copy engines ship one chunk per peer
             # while the SMs partition the other relation; pass 2 runs on the received (source, partition) pieces
             # 12-byte shipping when every row id fits 32 bits (checked here once, and by the kernels every step)
@@ -345,7 +361,7 @@ def run_b200(args, rank, world, local_rank):
     m_local = count
 
     shard_timeline = None
-    if world > 1 and args.shuffle == "dma":
+    if world > 1 and args.shuffle in ("dma", "pipe"):
         shard_timeline = timeline()
     # ---- per-phase device times -> roofline of the dominant kernel (separate, untimed passes) ----
     eng.set_profiling(True)
@@ -429,6 +445,10 @@ def run_b200(args, rank, world, local_rank):
                                     % (nR * 16 / 2**30),
                            "radix_bits": [plan["bits_pass1"], plan["bits_pass2"]],
                            "parallelism": "1 GPU" if world == 1 else (
+                               f"{world} ranks: {args.chunks} row chunks per relation; histogram-free pass 1 on (rank | sub-digit) into "
+                               "fixed-capacity regions, TMA copy kernel ships them over NVLink while the next chunk is partitioned, "
+                               "pass 2 appends each arrived chunk to fixed-capacity final partitions, one join; no collective in the "
+                               f"step (exact-path steps among the timed ones: {pj.exact_steps})" if args.shuffle == "pipe" else
                                f"{world} ranks: pass 1 partitions on (rank | sub-digit), copy engines ship one chunk per peer "
                                f"({12 if compact else 16} B per tuple) over "
                                "NVLink overlapped with the other relation's passes, then local pass 2 + join" if args.shuffle == "dma" else
@@ -463,9 +483,11 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-log2n", type=int, default=26, help="cpu_baseline sample size (2^k x 2^k)")
     ap.add_argument("--ref-log2n", type=int, default=24, help="--impl reference: sample per step")
-    ap.add_argument("--shuffle", default="dma", choices=["dma", "stores", "nccl"],
-                    help="multi-GPU exchange: pass-1 chunks shipped by the copy engines (default), pass-1 scatter storing "
-                         "straight into peer memory, or rank partition + NCCL all-to-all")
+    ap.add_argument("--shuffle", default="pipe", choices=["pipe", "dma", "stores", "nccl"],
+                    help="multi-GPU exchange: pipelined histogram-free chunks shipped by our copy kernel (default), pass-1 chunks "
+                         "shipped by the copy engines after exact histograms, pass-1 scatter storing straight into peer memory, "
+                         "or rank partition + NCCL all-to-all")
+    ap.add_argument("--chunks", type=int, default=4, help="pipe shuffle: row chunks per relation")
     ap.add_argument("--ship-bytes", type=int, default=16, choices=[12, 16],
                     help="dma shuffle: bytes per tuple on the wire; 12 = {u64 value, u32 row id}, used when row ids fit 32 bits")
     ap.add_argument("--split-probe", action="store_true", help="dma shuffle: ship the probe relation in two halves (measured slower)")

@@ -235,6 +235,39 @@ int rhj_shardx_pass2_soa_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int re
 int rhj_shardx_join_slots_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int build_slot, int probe_slot, int first,
                                  rhj_pair *d_out, uint64_t capacity, uint64_t *count, void *stream);
 
+/* Pipelined exchange (the default of bench.py at N > 1): histogram-free, chunked, no host synchronisation and
+ * no collective call inside a step.  Every rank cuts each local relation into `chunks` row chunks; pass 1 of a
+ * chunk scatters on (destination rank | sub-digit) into fixed-capacity regions; a hand-written copy kernel
+ * (TMA bulk copies through a shared-memory ring, peer stores over NVLink / NVSwitch) ships the filled part of
+ * every region into the same region of the destination's receive buffer while the SMs partition the next chunk;
+ * the destination appends each chunk, as soon as its flags have arrived, to fixed-capacity final partitions;
+ * one build/probe/emit pass follows.  Receive buffers, region ends and flags live in one SYMMETRIC block per
+ * rank (rhj_pipe_sym_bytes bytes, zero-filled once, mapped into every peer: CUDA IPC / symmetric memory) and
+ * are double-buffered by step parity.  Per step, on every rank, with the same epoch = 1, 2, 3, ...:
+ *   rhj_pipe_begin -> for rel, chunk: rhj_pipe_pass1_device (compute stream), rhj_pipe_ship_device (copy stream,
+ *   behind an event) -> for rel, chunk: rhj_pipe_pass2_device -> rhj_pipe_post_device -> rhj_pipe_join_device.
+ * A region that overflows anywhere (skewed or duplicate-heavy data) reaches every rank as RHJ_PIPE_OVERFLOW in
+ * *status: all ranks then redo the step through the exact exchange (rhj_shardx_*). */
+#define RHJ_MAX_PEERS 16
+#define RHJ_PIPE_OVERFLOW 1u   /* a fixed-capacity region overflowed somewhere: redo through rhj_shardx_*   */
+#define RHJ_PIPE_TIMEOUT 2u    /* a peer's flag did not arrive within 4 s                                   */
+#define RHJ_PIPE_BAD 4u        /* a received region end was out of range                                    */
+typedef struct rhj_pipe_cfg {
+    uint32_t world, rank;
+    uint32_t chunks;                       /* row chunks per relation, 1..8                                  */
+    uint32_t ship_ctas;                    /* CTAs of the copy kernel (0 = default 48)                       */
+    uint64_t nR_local_max, nS_local_max;   /* rows per rank (upper bound over ranks) of R and S              */
+    void *sym[RHJ_MAX_PEERS];              /* base of every rank's symmetric block, valid in this process    */
+} rhj_pipe_cfg;
+uint64_t rhj_pipe_sym_bytes(const rhj_shard_plan *plan, const rhj_pipe_cfg *cfg);
+int rhj_pipe_open(rhj_ctx *ctx, const rhj_shard_plan *plan, const rhj_pipe_cfg *cfg);
+int rhj_pipe_begin(rhj_ctx *ctx, uint64_t epoch, void *stream);
+int rhj_pipe_pass1_device(rhj_ctx *ctx, int rel, int chunk, const rhj_tuple *d_rows, uint64_t n, void *stream);
+int rhj_pipe_ship_device(rhj_ctx *ctx, int rel, int chunk, void *stream);
+int rhj_pipe_pass2_device(rhj_ctx *ctx, int rel, int chunk, void *stream);
+int rhj_pipe_post_device(rhj_ctx *ctx, void *stream);
+int rhj_pipe_join_device(rhj_ctx *ctx, rhj_pair *d_out, uint64_t capacity, uint64_t *count, uint32_t *status, void *stream);
+
 /* ---- introspection for benchmarks ------------------------------------------------------------ */
 
 typedef struct rhj_plan_info {

@@ -28,6 +28,13 @@ class ShardPlan(ctypes.Structure):
                 ("bits_pass1", ctypes.c_uint32), ("bits_pass2", ctypes.c_uint32), ("build_is_S", ctypes.c_uint32)]
 
 
+class PipeCfg(ctypes.Structure):
+    """struct rhj_pipe_cfg (include/rhj.h)."""
+    _fields_ = [("world", ctypes.c_uint32), ("rank", ctypes.c_uint32), ("chunks", ctypes.c_uint32),
+                ("ship_ctas", ctypes.c_uint32), ("nR_local_max", ctypes.c_uint64), ("nS_local_max", ctypes.c_uint64),
+                ("sym", ctypes.c_void_p * 16)]
+
+
 # name -> (restype, argtypes): every symbol include/rhj.h declares
 SIGNATURES = {
     "rhj_version": (ctypes.c_char_p, []),
@@ -69,6 +76,14 @@ SIGNATURES = {
     "rhj_shardx_join_slots_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                     c_vp, c_u64, c_u64p, c_vp]),
     "rhj_shardx_join_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), c_vp, c_u64, c_u64p, c_vp]),
+    "rhj_pipe_sym_bytes": (c_u64, [ctypes.POINTER(ShardPlan), ctypes.POINTER(PipeCfg)]),
+    "rhj_pipe_open": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.POINTER(PipeCfg)]),
+    "rhj_pipe_begin": (ctypes.c_int, [c_vp, c_u64, c_vp]),
+    "rhj_pipe_pass1_device": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp, c_u64, c_vp]),
+    "rhj_pipe_ship_device": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp]),
+    "rhj_pipe_pass2_device": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int, c_vp]),
+    "rhj_pipe_post_device": (ctypes.c_int, [c_vp, c_vp]),
+    "rhj_pipe_join_device": (ctypes.c_int, [c_vp, c_vp, c_u64, c_u64p, ctypes.POINTER(ctypes.c_uint32), c_vp]),
     "rhj_last_plan": (ctypes.c_int, [c_vp, ctypes.POINTER(PlanInfo)]),
     "rhj_set_profiling": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "rhj_last_phase_ms": (ctypes.c_int, [c_vp, ctypes.POINTER(ctypes.c_float)]),

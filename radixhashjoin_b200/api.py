@@ -306,6 +306,52 @@ class RadixHashJoin:
         self._ck(rc)
         return out[:cnt.value], int(cnt.value)
 
+    # ---- multi-GPU: pipelined exchange (include/rhj.h, rhj_pipe_*) --------------------------------
+    def pipe_cfg(self, plan, rank, chunks, nR_local_max, nS_local_max, sym_ptrs=None, ship_ctas=0):
+        cfg = _lib.PipeCfg()
+        cfg.world, cfg.rank, cfg.chunks, cfg.ship_ctas = plan.world, rank, chunks, ship_ctas
+        cfg.nR_local_max, cfg.nS_local_max = nR_local_max, nS_local_max
+        for i, p in enumerate(sym_ptrs or []):
+            cfg.sym[i] = p
+        return cfg
+
+    def pipe_sym_bytes(self, plan, cfg):
+        n = int(self._lib.rhj_pipe_sym_bytes(ctypes.byref(plan), ctypes.byref(cfg)))
+        if n == 0:
+            raise RhjError(2, "rhj_pipe_sym_bytes: bad plan / configuration")
+        return n
+
+    def pipe_open(self, plan, cfg):
+        self._ck(self._lib.rhj_pipe_open(self._ctx, ctypes.byref(plan), ctypes.byref(cfg)))
+
+    def pipe_begin(self, epoch, stream=None):
+        self._ck(self._lib.rhj_pipe_begin(self._ctx, epoch, self._stream(stream)))
+
+    def pipe_pass1(self, rel, chunk, rows, stream=None):
+        n = _check_rel(rows)
+        self._ck(self._lib.rhj_pipe_pass1_device(self._ctx, rel, chunk, _ptr(rows), n, self._stream(stream)))
+
+    def pipe_ship(self, rel, chunk, stream=None):
+        self._ck(self._lib.rhj_pipe_ship_device(self._ctx, rel, chunk, self._stream(stream)))
+
+    def pipe_pass2(self, rel, chunk, stream=None):
+        self._ck(self._lib.rhj_pipe_pass2_device(self._ctx, rel, chunk, self._stream(stream)))
+
+    def pipe_post(self, stream=None):
+        self._ck(self._lib.rhj_pipe_post_device(self._ctx, self._stream(stream)))
+
+    def pipe_join(self, out, stream=None):
+        """(pairs, count, status): status != 0 (RHJ_PIPE_* bits) means the step must be redone exactly"""
+        cnt, status = ctypes.c_uint64(), ctypes.c_uint32()
+        rc = self._lib.rhj_pipe_join_device(self._ctx, _ptr(out), out.shape[0], ctypes.byref(cnt), ctypes.byref(status),
+                                            self._stream(stream))
+        if rc == 4:
+            e = RhjError(rc, self._lib.rhj_last_error(self._ctx).decode())
+            e.needed = int(cnt.value)
+            raise e
+        self._ck(rc)
+        return out[:cnt.value], int(cnt.value), int(status.value)
+
     # ---- neighbours on the query path ----------------------------------------------------------
     def filter(self, col, op, constant, rowids=None, stream=None):
         """Query::run_filters predicate (Query.cpp:94-146): surviving row ids, input order kept."""

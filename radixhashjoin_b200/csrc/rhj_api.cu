@@ -91,6 +91,19 @@ cudaError_t launch_scatter_t(cudaStream_t st, const PartArgs &a, u32 grid) {
 int launch_scatter(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, bool seg, bool limit = false) {
     u32 grid = a.rel[0].ntiles + a.rel[1].ntiles;
     if (!grid) return RHJ_OK;
+    if (limit && kind == kDigitShard) {  // pipelined exchange, pass 1: (rank | sub-digit) regions of fixed capacity, per-digit output base
+        if (seg || a.shard_local) return fail(ctx, RHJ_ERR_STATE, "bounds-checked shard scatter: unsegmented, peer_out bases");
+        if (a.ndig > 512) {
+            CK(set_smem(k_scatter<kDigitShard, false, kWriteStaged, kMaxDigits, true>, kScatterSmem));
+            k_scatter<kDigitShard, false, kWriteStaged, kMaxDigits, true><<<grid, kPartThreads, kScatterSmem, st>>>(a);
+        } else {
+            CK(set_smem(k_scatter<kDigitShard, false, kWriteStaged, 512, true>, kScatterSmem));
+            k_scatter<kDigitShard, false, kWriteStaged, 512, true><<<grid, kPartThreads, kScatterSmem, st>>>(a);
+        }
+        CK(cudaGetLastError());
+        ctx->info.kernel_launches++;
+        return RHJ_OK;
+    }
     if (limit) {  // optimistic passes: fixed-capacity regions, bounds-checked staged stores
         if (kind != kDigitHash || a.ndig > 512) return fail(ctx, RHJ_ERR_STATE, "bounds-checked scatter: hash digits, <= 512 per pass");
         if (seg) {
@@ -1768,3 +1781,5 @@ int rhj_shardx_join_device(rhj_ctx *ctx, const rhj_shard_plan *sp, rhj_pair *d_o
 }
 
 }  // extern "C"
+
+#include "rhj_pipe.cuh"

@@ -34,6 +34,8 @@ enum Scalar {
     kScFilt = 8,
     kScOverflow = 9,  // optimistic pass 1: a partition outgrew its fixed-capacity region
     kScWideKey = 10,  // 12-byte shipping: a row id did not fit 32 bits
+    kScPipeStatus = 11,  // pipelined exchange: RHJ_PIPE_* bits of this step, own and received
+    kScPipeDone = 12,    // pipelined exchange: CTA arrival counter of the copy kernel (returns to 0)
     kScCount = 16
 };
 
@@ -96,6 +98,25 @@ struct rhj_ctx {
     bool shard_optimistic2 = true;                  // RHJ_NO_SHARD_OPT2=1 disables the histogram-free second pass
     u32 shard_opt2_world = 2;                       // ... which is on by default up to this many ranks (RHJ_SHARD_OPT2_WORLD)
 
+    // pipelined exchange (rhj_pipe_*): wiring + layout of the symmetric blocks, fixed at rhj_pipe_open
+    struct PipeState {
+        bool open = false;
+        rhj_shard_plan plan{};
+        u32 world = 1, rank = 0, chunks = 1, ship_ctas = 48;
+        u64 nmax[2] = {0, 0};          // rows per rank (upper bound) of R / S
+        u64 chunk_rows[2] = {0, 0};    // rows per chunk
+        u64 cap1[2] = {0, 0};          // capacity of one (chunk, destination, sub-digit) region, tuples
+        u64 cap2[2] = {0, 0};          // capacity of one final partition, tuples
+        void *sym[16] = {};            // every rank's symmetric block (sym[rank] = the own one)
+        u64 off_recv[2][2] = {}, off_end[2][2] = {}, off_flag = 0, off_status = 0, sym_bytes = 0;  // byte offsets
+        DevBuf stage[2];               // local staging of R / S: chunks * ndig * cap1 tuples + one dump tile
+        DevBuf cursors;                // [2][chunks * ndig] pass-1 cursors
+        DevBuf segs;                   // [2][chunks] segment tables of what arrived
+        DevBuf done;                   // arrival counter of the copy kernel (lives outside the per-step zero block)
+        u64 epoch = 0;
+        bool ship_smem_set = false;
+    } pipe;
+
     // optional per-phase timing (rhj_set_profiling)
     bool profiling = false;
     static constexpr int kMaxMarks = 24;
@@ -109,7 +130,8 @@ inline void for_each_buf(rhj_ctx *c, F f) {
     DevBuf *bufs[] = {&c->bufA, &c->bufB, &c->tiles, &c->sample, &c->bufB2, &c->bufB3, &c->shard_meta2, &c->shard_meta, &c->zero, &c->meta, &c->items, &c->item_cnt, &c->item_off, &c->filt_cnt,
                       &c->filt_off, &c->filt_tmp, &c->inR, &c->inS, &c->outP, &c->pin[0], &c->pin[1], &c->pout[0], &c->pout[1],
                       &c->pA, &c->pB, &c->iu_col, &c->iu_pairs, &c->iu_A,
-                      &c->iu_B, &c->iu_ep, &c->iu_out};
+                      &c->iu_B, &c->iu_ep, &c->iu_out, &c->pipe.stage[0], &c->pipe.stage[1], &c->pipe.cursors, &c->pipe.segs,
+                      &c->pipe.done};
     for (DevBuf *b : bufs) f(*b);
 }
 

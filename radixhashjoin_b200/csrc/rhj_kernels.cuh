@@ -62,6 +62,7 @@ struct PartRel {
     // k_scatter<LIMIT>: a run that does not fit its partition's region is written to the kTile tuples at out[dump..]
     // instead (nothing out of bounds, no per-tuple check); the overflow flag makes the host discard the attempt.
     u64 dump;
+    Tup *dump_ptr;         // same, as an absolute address, for scatters whose output base depends on the digit (peer_out)
 };
 // tuple idx of a relation in either form
 // How a partitioning kernel reads / writes tuples: 16-byte AoS both ways (everything single-GPU), or the
@@ -342,6 +343,7 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
                 if (LIMIT && c[k] && g[k] + c[k] > ((u64) seg_group(r, seg) * a.ndig + d + 1) * r.limit_cap) {
                     *a.overflow = 1;  // the optimistic layout is too small: this run goes to the dump tile
                     delta = r.dump;
+                    if (KIND == kDigitShard && !a.shard_local) delta = (u64) (r.dump_ptr - a.peer_out[ri][d >> a.sub_bits]);
                 }
                 s_delta[d] = delta;
             }

@@ -148,6 +148,128 @@ class FusedShardedJoin:
         return pairs, count, (nR, nS)
 
 
+class PipeShardedJoin:
+    """Multi-GPU join over the pipelined exchange (rhj_pipe_* in include/rhj.h): the default at N > 1.
+
+    Every rank cuts each local relation into `chunks` row chunks.  Pass 1 of a chunk scatters on
+    (destination rank | sub-digit) into fixed-capacity regions -- no histogram, no all-gather, no host
+    round trip; a hand-written copy kernel on a second, high-priority stream ships the filled part of every
+    region into the same region of the destination's symmetric receive buffer (TMA bulk copies through a
+    shared-memory ring, peer stores over NVLink / NVSwitch) while the SMs partition the next chunk; the
+    destination appends a chunk to its fixed-capacity final partitions as soon as the chunk's flags have
+    arrived from all ranks (a device-side wait in front of pass 2); one build/probe/emit pass follows.
+    A step is ~40 kernel launches on two streams, one host synchronisation (the result count) and no
+    collective call; torch.distributed only provides the symmetric-memory rendezvous at construction.
+
+    Skewed or duplicate-heavy inputs overflow a region somewhere; every rank learns it through the flags
+    and all ranks redo the step through the exact (histogram) exchange, DmaShardedJoin, and stay on it for
+    the next 16 steps.
+    """
+
+    OVERFLOW, TIMEOUT, BAD = 1, 2, 4
+
+    def __init__(self, engine, world, rank, nR_global, nS_global, nR_local_max, nS_local_max, chunks=4, group=None,
+                 ship_ctas=0, exact_recv_capacity=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.torch, self.dist = torch, dist
+        self.engine, self.world, self.rank = engine, world, rank
+        self.group = group if group is not None else dist.group.WORLD
+        self.plan = engine.shard_plan(nR_global, nS_global, world)
+        self.build_rel = 1 if self.plan.build_is_S else 0
+        self.order = (self.build_rel, 1 - self.build_rel)
+        self.chunks = int(chunks)
+        self.nmax = (int(nR_local_max), int(nS_local_max))
+        self.chunk_rows = tuple((n + self.chunks - 1) // self.chunks for n in self.nmax)
+        self._globals = (nR_global, nS_global)
+        self._exact_cap = exact_recv_capacity
+        dev = torch.device("cuda", engine.device)
+        cfg = engine.pipe_cfg(self.plan, rank, self.chunks, self.nmax[0], self.nmax[1], ship_ctas=ship_ctas)
+        self.sym_bytes = engine.pipe_sym_bytes(self.plan, cfg)
+        self.sym = symm_mem.empty((self.sym_bytes // 8,), dtype=torch.int64, device=dev)
+        self.sym.zero_()
+        self.hdl = symm_mem.rendezvous(self.sym, self.group)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        engine.pipe_open(self.plan, engine.pipe_cfg(self.plan, rank, self.chunks, self.nmax[0], self.nmax[1], ptrs, ship_ctas))
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=self.group)       # every block is zero before anyone ships into it
+        self.copy_stream = torch.cuda.Stream(device=dev, priority=-1)   # the copy kernel's CTAs go first when an SM frees up
+        self.epoch = 0
+        self.exact_left = 0
+        self.exact_steps = 0
+        self._exact = None
+
+    def _mark(self, stream=None):
+        ev = self.torch.cuda.Event(enable_timing=True)
+        ev.record(stream if stream is not None else self.torch.cuda.current_stream())
+        return ev
+
+    def _exact_step(self, R_local, S_local, out):
+        if self._exact is None:
+            n_local_max = max(self.nmax)
+            cap = self._exact_cap or int(n_local_max * 1.3) + 8192
+            self._exact = DmaShardedJoin(self.engine, self.world, self.rank, self._globals[0], self._globals[1], n_local_max,
+                                         cap, group=self.group)
+        self.exact_steps += 1
+        return self._exact.step(R_local, S_local, out)
+
+    def step(self, R_local, S_local, out, marks=None):
+        """One sharded join; returns (pairs, count, None).  `marks` (a list) collects (label, CUDA event)
+        pairs for a timeline of the step."""
+        torch, eng = self.torch, self.engine
+        if self.exact_left > 0:
+            self.exact_left -= 1
+            return self._exact_step(R_local, S_local, out)
+        rels = (R_local, S_local)
+        for rel in (0, 1):
+            if rels[rel].shape[0] > self.nmax[rel]:
+                raise ValueError("local shard larger than the nR_local_max / nS_local_max given at construction")
+        self.epoch += 1
+        cur = torch.cuda.current_stream()
+        cs = self.copy_stream
+        if marks is not None:
+            marks.append(("start", self._mark()))
+        eng.pipe_begin(self.epoch)
+        for rel in self.order:
+            T, rows = rels[rel], self.chunk_rows[rel]
+            n = T.shape[0]
+            for c in range(self.chunks):
+                lo = min(n, c * rows)
+                hi = min(n, lo + rows)
+                eng.pipe_pass1(rel, c, T[lo:hi])
+                ev = torch.cuda.Event(enable_timing=marks is not None)
+                ev.record(cur)
+                if marks is not None:
+                    marks.append((f"pass1_{rel}.{c}_done", ev))
+                cs.wait_event(ev)
+                eng.pipe_ship(rel, c, stream=cs)
+                if marks is not None:
+                    marks.append((f"ship_{rel}.{c}_sent", self._mark(cs)))
+        for rel in self.order:
+            for c in range(self.chunks):
+                eng.pipe_pass2(rel, c)
+                if marks is not None:
+                    marks.append((f"pass2_{rel}.{c}_done", self._mark()))
+        eng.pipe_post()
+        pairs, count, status = eng.pipe_join(out)
+        if marks is not None:
+            marks.append(("join_done", self._mark()))
+        cur.wait_stream(cs)
+        if status & (self.TIMEOUT | self.BAD):
+            raise RuntimeError(f"rank {self.rank}: pipelined exchange failed (status {status}: "
+                               f"{'timeout ' if status & self.TIMEOUT else ''}{'bad region end' if status & self.BAD else ''})")
+        if status & self.OVERFLOW:
+            self.exact_left = 16
+            return self._exact_step(R_local, S_local, out)
+        return pairs, count, None
+
+    @staticmethod
+    def timeline(marks):
+        t0 = marks[0][1]
+        return [(name, round(t0.elapsed_time(ev), 3)) for name, ev in marks]
+
+
 class DmaShardedJoin:
     """Multi-GPU join, DMA-shipped (rhj_shardx_* in include/rhj.h): the default at N > 1.
 

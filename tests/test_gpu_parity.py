@@ -726,3 +726,88 @@ def test_dma_shard_join_split_probe_emulated_ranks(world, nR, nS, dom):
     assert np.array_equal(O.sort_pairs(got), expect)
     for e in engines:
         e.close()
+
+
+# ---- multi-GPU, pipelined exchange (rhj_pipe_*): emulated ranks on one GPU -------------------------------
+def _pipe_emulated_steps(world, n_local, chunks, make_data, steps=3):
+    """Drives rhj_pipe_* for `world` contexts on one GPU.  Plain tensors stand in for the symmetric blocks (every
+    context sees every block); the phases run rank after rank, so every device-side wait finds its flag already set
+    (kernels that wait on one another must not share a GPU).  Yields (expected sorted pairs, [per-rank (pairs, status)])
+    per step; consecutive steps alternate the parity of the double-buffered receive side."""
+    from radixhashjoin_b200 import RadixHashJoin
+    engines = [RadixHashJoin(0) for _ in range(world)]
+    try:
+        plan = engines[0].shard_plan(world * n_local, world * n_local, world)
+        nbytes = engines[0].pipe_sym_bytes(plan, engines[0].pipe_cfg(plan, 0, chunks, n_local, n_local))
+        syms = [torch.zeros(nbytes // 8, dtype=torch.int64, device=DEV) for _ in range(world)]
+        ptrs = [s.data_ptr() for s in syms]
+        for r in range(world):
+            engines[r].pipe_open(plan, engines[r].pipe_cfg(plan, r, chunks, n_local, n_local, ptrs))
+        rows = (n_local + chunks - 1) // chunks
+        for step in range(1, steps + 1):
+            Rg, Sg = make_data(step)
+            expect = O.sort_pairs(O.oracle_join(Rg, Sg))
+            shards = [(to_dev(Rg[r * n_local:(r + 1) * n_local]), to_dev(Sg[r * n_local:(r + 1) * n_local])) for r in range(world)]
+            for r in range(world):
+                engines[r].pipe_begin(step)
+                for rel in (0, 1):
+                    for c in range(chunks):
+                        engines[r].pipe_pass1(rel, c, shards[r][rel][c * rows:(c + 1) * rows])
+            for r in range(world):
+                for rel in (0, 1):
+                    for c in range(chunks):
+                        engines[r].pipe_ship(rel, c)
+            for r in range(world):
+                for rel in (1, 0):
+                    for c in range(chunks):
+                        engines[r].pipe_pass2(rel, c)
+                engines[r].pipe_post()
+            res = []
+            for r in range(world):
+                out = torch.empty((max(len(expect), 1), 2), dtype=torch.int64, device=DEV)
+                pairs, n, status = engines[r].pipe_join(out)
+                res.append((pairs_np(pairs), status))
+            yield expect, res
+    finally:
+        for e in engines:
+            e.close()
+
+
+@pytest.mark.parametrize("world,n_local,dom,chunks", [(1, 50000, 20000, 2), (2, 60000, 1 << 40, 4), (4, 40000, 1 << 40, 3),
+                                                      (8, 300000, 1 << 30, 4), (4, 500, 1 << 20, 1), (2, 3001, 1 << 33, 8),
+                                                      (8, 70000, 300000, 2)])
+def test_pipe_shard_join_emulated_ranks(world, n_local, dom, chunks):
+    """rhj_pipe_*: histogram-free chunked pass 1 into fixed-capacity regions, the copy kernel, device-side
+    arrival + appended pass 2, join.  Union over ranks == oracle, three steps in a row (both parities)."""
+    rng = np.random.default_rng(world * 131 + n_local)
+
+    def make(step):
+        return rand_rel(rng, world * n_local, dom), rand_rel(rng, world * n_local, dom, 1 << 35)
+
+    for expect, res in _pipe_emulated_steps(world, n_local, chunks, make):
+        assert all(st == 0 for _, st in res), [st for _, st in res]
+        got = np.concatenate([p for p, _ in res])
+        assert len(got) == len(expect)
+        assert np.array_equal(O.sort_pairs(got), expect)
+
+
+def test_pipe_shard_join_overflow_reaches_every_rank():
+    """A single hot value overflows one (destination, sub-digit) region on every sender: every rank must see
+    RHJ_PIPE_OVERFLOW (so that all ranks redo the step exactly), and the next, benign step must be clean."""
+    world, n_local = 4, 50000
+    rng = np.random.default_rng(5)
+
+    def make(step):
+        if step == 2:
+            R = rand_rel(rng, world * n_local, 1 << 40)
+            S = O.as_tuples(np.arange(world * n_local, dtype=np.uint64), np.full(world * n_local, 12345, dtype=np.uint64))
+            return R, S
+        return rand_rel(rng, world * n_local, 1 << 40), rand_rel(rng, world * n_local, 1 << 40, 1 << 35)
+
+    for step, (expect, res) in enumerate(_pipe_emulated_steps(world, n_local, 2, make), start=1):
+        if step == 2:
+            assert all(st == 1 for _, st in res), [st for _, st in res]
+        else:
+            assert all(st == 0 for _, st in res), [st for _, st in res]
+            got = np.concatenate([p for p, _ in res])
+            assert np.array_equal(O.sort_pairs(got), expect)
