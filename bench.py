@@ -229,22 +229,33 @@ def run_b200(args, rank, world, local_rank):
         elif args.workload == "zipf":
             w = W.zipf_probe(log2n, dev)
         elif args.workload == "fk":
-            w = W.foreign_key(args.fk_build_log2, log2n, dev)
+            w = W.foreign_key(args.fk_build_log2, args.fk_probe_log2 or log2n, dev)
         else:
             raise SystemExit("unknown workload")
         R, S, expected = w.R, w.S, w.expected
         wname = w.name
     else:
-        assert args.workload == "uniform", "multi-GPU bench runs the uniform workload (config 5 shape)"
-        gbits = log2n + (world.bit_length() - 1)
-        assert (1 << (world.bit_length() - 1)) == world, "world size must be a power of two"
-        w = W.uniform_unique(log2n, dev, row_offset=rank * n_local, log2_global=gbits)
+        lw = world.bit_length() - 1
+        assert (1 << lw) == world, "world size must be a power of two"
+        gbits = log2n + lw
+        if args.workload == "uniform":   # weak scaling: 2^log2n + 2^log2n tuples per GPU of a global 2^gbits pair (config 5 shape)
+            w = W.uniform_unique(log2n, dev, row_offset=rank * n_local, log2_global=gbits)
+            expected = W.uniform_unique_global_digest(gbits, dev, lo=rank * n_local, hi=(rank + 1) * n_local)
+            wname = _workload_name(log2n, world)
+        elif args.workload == "zipf":    # weak scaling: rank's rows of a global Zipf 2^gbits pair (config 4 shape)
+            w = W.zipf_probe(gbits, dev, rank=rank, world=world)
+            expected = w.expected
+            wname = f"zipf_global_2^{gbits}x2^{gbits}_sharded_over_{world}"
+        else:                            # fk, STRONG scaling: the global sizes of config 3 are fixed, every rank owns 1 / world
+            pbits = args.fk_probe_log2 if args.fk_probe_log2 else gbits
+            w = W.foreign_key(args.fk_build_log2, pbits, dev, rank=rank, world=world)
+            expected = w.expected
+            wname = f"fk_2^{args.fk_build_log2}x2^{pbits}_sharded_over_{world}"
         R, S = w.R, w.S
-        expected = None
-        wname = _workload_name(log2n, world)
     nR, nS = R.shape[0], S.shape[0]
     n_in_local = nR + nS
     compact = False
+    strategy = None
 
     if world == 1:
         cap = nS if args.workload != "dup" else nS
@@ -254,17 +265,31 @@ def run_b200(args, rank, world, local_rank):
         def step():
             return eng.join_device(R, S, out=out, emit=emit)
     else:
-        slack = int(n_local * 1.05) + 4096
+        from radixhashjoin_b200.distributed import (BroadcastShardedJoin, DmaShardedJoin, FusedShardedJoin, PipeShardedJoin,
+                                                    ShardedJoin, broadcast_is_cheaper)
+        n_max = max(nR, nS)
+        # what a rank receives / emits: ~ its share for hashed distinct keys; the rank that owns the hot Zipf keys gets more
+        slack = int(n_max * (2.0 if args.workload == "zipf" else 1.05)) + 4096
         out = torch.empty((slack, 2), dtype=torch.int64, device=dev)
-        from radixhashjoin_b200.distributed import DmaShardedJoin, FusedShardedJoin, PipeShardedJoin, ShardedJoin
-        if args.shuffle != "pipe":
+        strategy = args.shuffle
+        if broadcast_is_cheaper(nR * world, nS * world, world) and args.shuffle == "pipe":
+            strategy = "broadcast"
+        if strategy not in ("pipe", "broadcast"):
             recvR = torch.empty((slack, 2), dtype=torch.int64, device=dev)
             recvS = torch.empty((slack, 2), dtype=torch.int64, device=dev)
             eng.reserve(slack, slack)
-        if args.shuffle == "pipe":
+        if strategy == "broadcast":
+            # small build side (foreign-key join): all-gather it, never shuffle the probe side, join locally
+            bj = BroadcastShardedJoin(eng, world, rank, nR * world, nS * world, min(nR, nS))
+            eng.reserve(nR * world if nR < nS else nR, nS * world if nS <= nR else nS)
+
+            def step():
+                pairs, count, _ = bj.step(R, S, out)
+                return pairs, count
+        elif strategy == "pipe":
             # histogram-free chunked pass 1 -> hand-written TMA copy kernel over NVLink -> appended pass 2 -> join;
             # no collective call and one host synchronisation per step (radixhashjoin_b200/distributed.py)
-            pj = PipeShardedJoin(eng, world, rank, n_local * world, n_local * world, n_local, n_local, chunks=args.chunks,
+            pj = PipeShardedJoin(eng, world, rank, nR * world, nS * world, nR, nS, chunks=args.chunks,
                                  exact_recv_capacity=slack)
 
             def step():
@@ -276,14 +301,14 @@ def run_b200(args, rank, world, local_rank):
                 pj.step(R, S, out, marks)
                 torch.cuda.synchronize()
                 return pj.timeline(marks)
-        elif args.shuffle == "dma":
+        elif strategy == "dma":
             # pass 1 partitions on (rank | sub-digit) into staging; the copy engines ship one chunk per peer
             # while the SMs partition the other relation; pass 2 runs on the received (source, partition) pieces
             # 12-byte shipping when every row id fits 32 bits (checked here once, and by the kernels every step)
             mx = torch.stack([R[:, 0].max(), S[:, 0].max()]).max()
             dist.all_reduce(mx, op=dist.ReduceOp.MAX)
             compact = args.ship_bytes == 12 and int(mx.item()) < (1 << 32)
-            dj = DmaShardedJoin(eng, world, rank, n_local * world, n_local * world, n_local, slack,
+            dj = DmaShardedJoin(eng, world, rank, nR * world, nS * world, n_max, slack,
                                 split_probe=args.split_probe, compact_rowids=compact)
             del recvR, recvS
 
@@ -296,9 +321,9 @@ def run_b200(args, rank, world, local_rank):
                 dj.step(R, S, out, marks)
                 torch.cuda.synchronize()
                 return dj.timeline(marks)
-        elif args.shuffle == "stores":
+        elif strategy == "stores":
             # pass 1 of the join IS the shuffle: runs are stored straight into the peers' receive buffers
-            fj = FusedShardedJoin(eng, world, rank, n_local * world, n_local * world, slack)
+            fj = FusedShardedJoin(eng, world, rank, nR * world, nS * world, slack)
             del recvR, recvS
 
             def step():
@@ -333,7 +358,7 @@ def run_b200(args, rank, world, local_rank):
     clocks = sampler.stop()
     ms_total = ev0.elapsed_time(ev1)
     plan = eng.last_plan()
-    launches_per_step = plan["kernel_launches"] + (0 if world == 1 else (6 if args.shuffle == "nccl" else 0))
+    launches_per_step = plan["kernel_launches"] + (0 if world == 1 else (6 if strategy == "nccl" else 0))
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -346,22 +371,23 @@ def run_b200(args, rank, world, local_rank):
     if world == 1:
         verified = tuple(dig) == tuple(expected)
     else:
-        tot = torch.tensor([dig[0], dig[1] - (1 << 64) if dig[1] >= (1 << 63) else dig[1]], dtype=torch.int64, device=dev)
+        def _i64(v):
+            return v - (1 << 64) if v >= (1 << 63) else v
+        # every rank knows the closed-form digest of what ITS probe rows must produce; digests add up (count, sum) / xor
+        tot = torch.tensor([dig[0], _i64(dig[1]), expected[0], _i64(expected[1])], dtype=torch.int64, device=dev)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         xr = [None] * world
-        dist.all_gather_object(xr, dig[2])
-        x = 0
-        for v in xr:
-            x ^= v
-        verified = None
-        if rank == 0:
-            gbits = log2n + (world.bit_length() - 1)
-            exp = W.uniform_unique_global_digest(gbits, dev)
-            verified = (int(tot[0].item()), int(tot[1].item()) & ((1 << 64) - 1), x) == tuple(exp)
+        dist.all_gather_object(xr, (dig[2], expected[2]))
+        x = e = 0
+        for a, b in xr:
+            x ^= a
+            e ^= b
+        m64 = (1 << 64) - 1
+        verified = (int(tot[0].item()), int(tot[1].item()) & m64, x) == (int(tot[2].item()), int(tot[3].item()) & m64, e)
     m_local = count
 
     shard_timeline = None
-    if world > 1 and args.shuffle in ("dma", "pipe"):
+    if world > 1 and strategy in ("dma", "pipe"):
         shard_timeline = timeline()
     # ---- per-phase device times -> roofline of the dominant kernel (separate, untimed passes) ----
     eng.set_profiling(True)
@@ -373,6 +399,21 @@ def run_b200(args, rank, world, local_rank):
         for k, v in eng.last_phase_ms().items():
             acc[k] = acc.get(k, 0.0) + v / reps
     eng.set_profiling(False)
+    nvlink = None
+    if shard_timeline and strategy == "pipe" and any(k == "join_done" for k, _ in shard_timeline):
+        # the pipelined exchange has no library phase marks: the join kernel is what runs between the last pass 2 and the
+        # end of the step; the wire is busy from the first chunk's pass 1 to the last chunk's copy kernel
+        tl = dict(shard_timeline)
+        p2 = [v for k, v in shard_timeline if k.startswith("pass2_")]
+        p1 = [v for k, v in shard_timeline if k.startswith("pass1_")]
+        sent = [v for k, v in shard_timeline if k.startswith("ship_")]
+        acc = {"join": tl["join_done"] - max(p2), "scatter1": max(p1) - tl["start"]}
+        wire_ms = max(sent) - min(p1)
+        out_bytes = 16 * n_in_local * (world - 1) / world
+        nvlink = {"bytes_out_per_gpu": out_bytes, "wire_busy_ms": wire_ms, "achieved_GBps_per_direction": out_bytes / wire_ms / 1e6,
+                  "peak_GBps_per_direction": 770.0, "peak_source": "B200_PROFILING.md measured peer copy",
+                  "frac": out_bytes / wire_ms / 1e6 / 770.0,
+                  "note": "copy kernel (k_pipe_ship) running next to the partitioning kernels, one profiled step, this rank"}
     n_join = n_in_local  # at N > 1: ~ balanced, what this rank joins after the exchange
     alg_bytes = {"hist1": 16 * n_join, "scatter1": 32 * n_join, "hist2": 16 * n_join, "scatter2": 32 * n_join,
                  "join": 16 * n_join + 16 * m_local, "join_write": 16 * n_join + 16 * m_local}
@@ -437,7 +478,8 @@ def run_b200(args, rank, world, local_rank):
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "strong" if world > 1 and args.workload == "fk" else "weak",
                 "vs_baseline": None, "dtype": "u64", "data": "synthetic",
                 "config": {"workload": wname, "tuples_per_gpu": n_in_local, "tuple_bytes": 16,
                            "matches_per_gpu": int(m_local), "emitter": args.emit,
@@ -445,15 +487,17 @@ def run_b200(args, rank, world, local_rank):
                                     % (nR * 16 / 2**30),
                            "radix_bits": [plan["bits_pass1"], plan["bits_pass2"]],
                            "parallelism": "1 GPU" if world == 1 else (
+                               f"{world} ranks: the build side is all-gathered ({min(nR, nS) * world} tuples), the probe side is never "
+                               "shuffled, every rank joins its probe shard locally" if strategy == "broadcast" else
                                f"{world} ranks: {args.chunks} row chunks per relation; histogram-free pass 1 on (rank | sub-digit) into "
                                "fixed-capacity regions, TMA copy kernel ships them over NVLink while the next chunk is partitioned, "
                                "pass 2 appends each arrived chunk to fixed-capacity final partitions, one join; no collective in the "
-                               f"step (exact-path steps among the timed ones: {pj.exact_steps})" if args.shuffle == "pipe" else
+                               f"step (exact-path steps among the timed ones: {pj.exact_steps})" if strategy == "pipe" else
                                f"{world} ranks: pass 1 partitions on (rank | sub-digit), copy engines ship one chunk per peer "
                                f"({12 if compact else 16} B per tuple) over "
-                               "NVLink overlapped with the other relation's passes, then local pass 2 + join" if args.shuffle == "dma" else
+                               "NVLink overlapped with the other relation's passes, then local pass 2 + join" if strategy == "dma" else
                                f"{world} ranks: pass-1 scatter stores into peer receive buffers over NVLink (fused partition+shuffle), "
-                               "then local pass 2 + join" if args.shuffle == "stores" else
+                               "then local pass 2 + join" if strategy == "stores" else
                                f"{world} ranks: rank-radix partition + NCCL all-to-all + local join")},
                 "verified": verified, "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
                 "phase_ms": {k: round(v, 4) for k, v in acc.items() if v > 0},
@@ -463,6 +507,8 @@ def run_b200(args, rank, world, local_rank):
                 "e2e": e2e, "cpu_baseline": cpu}
         if shard_timeline:
             line["shard_timeline_ms"] = shard_timeline
+        if nvlink:
+            line["nvlink"] = nvlink
         if world == 1 and not args.no_small_work:
             line["small_work"] = small_work_wall(args.small_work_ref)
         print(json.dumps(line), flush=True)
@@ -479,6 +525,7 @@ def main():
     ap.add_argument("--log2n", type=int, default=27, help="tuples per relation per GPU = 2^log2n")
     ap.add_argument("--workload", default="uniform", choices=["uniform", "zipf", "fk"])
     ap.add_argument("--fk-build-log2", type=int, default=24)
+    ap.add_argument("--fk-probe-log2", type=int, default=0, help="fk: GLOBAL probe size (default: 2^log2n per GPU)")
     ap.add_argument("--emit", default="fused", choices=["fused", "count_then_write"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-log2n", type=int, default=26, help="cpu_baseline sample size (2^k x 2^k)")

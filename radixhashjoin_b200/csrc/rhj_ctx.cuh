@@ -35,7 +35,6 @@ enum Scalar {
     kScOverflow = 9,  // optimistic pass 1: a partition outgrew its fixed-capacity region
     kScWideKey = 10,  // 12-byte shipping: a row id did not fit 32 bits
     kScPipeStatus = 11,  // pipelined exchange: RHJ_PIPE_* bits of this step, own and received
-    kScPipeDone = 12,    // pipelined exchange: CTA arrival counter of the copy kernel (returns to 0)
     kScCount = 16
 };
 
@@ -102,7 +101,7 @@ struct rhj_ctx {
     struct PipeState {
         bool open = false;
         rhj_shard_plan plan{};
-        u32 world = 1, rank = 0, chunks = 1, ship_ctas = 48;
+        u32 world = 1, rank = 0, chunks = 1, ship_ctas = 48, stages = 8, stage_bytes = 8192;
         u64 nmax[2] = {0, 0};          // rows per rank (upper bound) of R / S
         u64 chunk_rows[2] = {0, 0};    // rows per chunk
         u64 cap1[2] = {0, 0};          // capacity of one (chunk, destination, sub-digit) region, tuples

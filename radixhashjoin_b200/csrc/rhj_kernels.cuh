@@ -27,6 +27,9 @@ namespace rhj {
 #ifndef RHJ_PART_MINBLOCKS
 #define RHJ_PART_MINBLOCKS 2
 #endif
+#ifndef RHJ_SCATTER_MAXNREG
+#define RHJ_SCATTER_MAXNREG 56
+#endif
 constexpr int kPartThreads = RHJ_PART_THREADS;  // threads per partition CTA
 constexpr int kPartItems = RHJ_PART_ITEMS;      // tuples per thread
 constexpr int kTile = kPartThreads * kPartItems;  // 4096 tuples = 64 KiB staged per CTA
@@ -273,7 +276,13 @@ __global__ void __launch_bounds__(kMaxDigits) k_scan_digits(ScanDigitsArgs a) {
 // Algorithmic bytes: 16 read + 16 written per tuple.
 enum ScatterWrite { kWriteStaged = 0, kWriteBulk = 1 };
 template <int KIND, bool SEG, int WMODE, int MAXD, bool LIMIT = false, int IO = kIoAos>
+#if RHJ_SCATTER_MAXNREG
+// 56 registers (0-48 bytes of spills) instead of the 62-64 two 512-thread CTAs per SM would allow: leaves room in the
+// register file for a CTA of the multi-GPU copy kernel next to two scatter CTAs (rhj_pipe_kernels.cuh)
+__global__ void __maxnreg__(RHJ_SCATTER_MAXNREG) k_scatter(PartArgs a) {
+#else
 __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(PartArgs a) {
+#endif
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     Tup *s_tup = reinterpret_cast<Tup *>(dyn_smem);
     __shared__ u32 s_cnt[MAXD];
@@ -339,11 +348,15 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
             if (d < a.ndig) {
                 s_off[d] = ex;
                 u64 delta = g[k] - ex;
+                // per-destination output bases: folded into the digit's delta here, once per digit, as an offset from
+                // peer_out[ri][0] -- indexing the parameter bank by the digit in the write-out loop would serialise a
+                // warp over its distinct destinations
+                if (KIND == kDigitShard && !a.shard_local) delta += (u64) (a.peer_out[ri][d >> a.sub_bits] - a.peer_out[ri][0]);
                 // (the reservation's result is first looked at here, after the scan, so its latency stays hidden)
                 if (LIMIT && c[k] && g[k] + c[k] > ((u64) seg_group(r, seg) * a.ndig + d + 1) * r.limit_cap) {
                     *a.overflow = 1;  // the optimistic layout is too small: this run goes to the dump tile
                     delta = r.dump;
-                    if (KIND == kDigitShard && !a.shard_local) delta = (u64) (r.dump_ptr - a.peer_out[ri][d >> a.sub_bits]);
+                    if (KIND == kDigitShard && !a.shard_local) delta = (u64) (r.dump_ptr - a.peer_out[ri][0]);
                 }
                 s_delta[d] = delta;
             }
@@ -362,7 +375,7 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
         __syncthreads();
         for (u32 d = tid; d < a.ndig; d += kPartThreads) {
             u32 cd = s_cnt[d];
-            Tup *ob = (KIND == kDigitShard && !a.shard_local) ? a.peer_out[ri][d >> a.sub_bits] : r.out;
+            Tup *ob = (KIND == kDigitShard && !a.shard_local) ? a.peer_out[ri][0] : r.out;
             if (cd) bulk_s2g(ob + s_delta[d] + s_off[d], s_tup + s_off[d], cd * (u32) sizeof(Tup));
         }
         bulk_commit();
@@ -375,7 +388,7 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
             if (i < ntile) {
                 Tup t = s_tup[i];
                 u32 d = digit<KIND>(t.val, a);
-                Tup *ob = (KIND == kDigitShard && !a.shard_local) ? a.peer_out[ri][d >> a.sub_bits] : r.out;
+                Tup *ob = (KIND == kDigitShard && !a.shard_local) ? a.peer_out[ri][0] : r.out;
                 if (IO != kIoSoaOut) {
                     st_stream(ob + s_delta[d] + i, t);
                 } else {  // 12-byte SoA output; a row id that does not fit 32 bits is an error the host reports

@@ -129,7 +129,12 @@ int rhj_pipe_open(rhj_ctx *ctx, const rhj_shard_plan *sp, const rhj_pipe_cfg *cf
     if ((rc = ensure(ctx, ctx->items, ((u64) nparts + np_bound / kProbeChunk + 2) * sizeof(Item)))) return rc;
     const u64 tiles_bound = (u64) ndig * std::max(P.cap1[0], P.cap1[1]) / kTile + ndig + 2;
     if ((rc = ensure(ctx, ctx->tiles, 3 * (tiles_bound + 1) * sizeof(TileDesc)))) return rc;
-    CK(cudaFuncSetAttribute(k_pipe_ship, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kPipeRingBytes));
+    P.stage_bytes = 8192;
+    P.stages = 8;
+    if (const char *e = getenv("RHJ_PIPE_STAGE_KB")) P.stage_bytes = (u32) std::max(1, std::min(64, atoi(e))) * 1024;
+    if (const char *e = getenv("RHJ_PIPE_STAGES")) P.stages = (u32) std::max(2, std::min((int) kPipeMaxStages, atoi(e)));
+    if ((u64) P.stages * P.stage_bytes > 200 * 1024) return fail(ctx, RHJ_ERR_ARG, "rhj_pipe_open: copy-kernel ring larger than 200 KiB");
+    CK(cudaFuncSetAttribute(k_pipe_ship, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (P.stages * P.stage_bytes)));
     P.epoch = 0;
     P.open = true;
     return RHJ_OK;
@@ -237,7 +242,9 @@ int rhj_pipe_ship_device(rhj_ctx *ctx, int rel, int chunk, void *stream) {
     a.overflow = (u32 *) (m.scalars + kScOverflow);
     const u32 nremote = (P.world - 1) << sp->bits_pass1;
     const u32 grid = std::max<u32>(1, std::min<u32>(P.ship_ctas, std::max<u32>(nremote, 1)));
-    k_pipe_ship<<<grid, kPipeShipThreads, kPipeRingBytes, st>>>(a);
+    a.stages = P.stages;
+    a.stage_bytes = P.stage_bytes;
+    k_pipe_ship<<<grid, kPipeShipThreads, (size_t) P.stages * P.stage_bytes, st>>>(a);
     CK(cudaGetLastError());
     ctx->info.kernel_launches++;
     return RHJ_OK;
@@ -271,9 +278,6 @@ int rhj_pipe_pass2_device(rhj_ctx *ctx, int rel, int chunk, void *stream) {
     ar.seg_end = sg.seg_end;
     ar.seg_tile0 = sg.seg_tile0;
     ar.status = m.scalars + kScPipeStatus;
-    k_pipe_arrive<<<1, 1024, 0, st>>>(ar);
-    CK(cudaGetLastError());
-    ctx->info.kernel_launches++;
 
     PartArgs b{};
     b.shift = std::min(31, 32 - (int) sp->bits_total);
@@ -287,7 +291,15 @@ int rhj_pipe_pass2_device(rhj_ctx *ctx, int rel, int chunk, void *stream) {
     b.rel[0].seg_end = sg.seg_end;
     b.rel[0].limit_cap = P.cap2[rel];
     b.rel[0].dump = (u64) nparts * P.cap2[rel];
-    if ((rc = build_tile_tables(ctx, st, b, 1, rel))) return rc;
+    // the tile table of what arrived is written by the arrival kernel itself (one launch instead of two)
+    const size_t need = ((size_t) tiles_bound + 1) * sizeof(TileDesc);
+    if (2 * need > ctx->tiles.cap) return fail(ctx, RHJ_ERR_STATE, "rhj_pipe_pass2_device: tile table smaller than sized at rhj_pipe_open");
+    ar.tiles = (TileDesc *) ((char *) ctx->tiles.p + (size_t) rel * need);
+    ar.ntiles = tiles_bound;
+    b.rel[0].tiles = ar.tiles;
+    k_pipe_arrive<<<1, 1024, 0, st>>>(ar);
+    CK(cudaGetLastError());
+    ctx->info.kernel_launches++;
     return launch_scatter(ctx, st, b, kDigitHash, true, true);
 }
 

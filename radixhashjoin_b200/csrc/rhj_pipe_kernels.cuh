@@ -25,9 +25,8 @@ namespace rhj {
 
 constexpr int kPipeMaxChunks = 8;
 constexpr u32 kPipeShipThreads = 64;
-constexpr u32 kPipeStageBytes = 8192;             // bytes per ring stage (512 tuples)
-constexpr u32 kPipeStages = 8;                    // 64 KiB ring per CTA: fits next to two k_scatter CTAs on an SM
-constexpr u32 kPipeRingBytes = kPipeStageBytes * kPipeStages;
+constexpr u32 kPipeMaxStages = 32;                // ring = stages x stage_bytes of dynamic shared memory, chosen at rhj_pipe_open:
+                                                  // default 8 x 8 KiB = 64 KiB per CTA, which fits next to two k_scatter CTAs on an SM
 constexpr u64 kPipeSpinNs = 4000000000ull;        // a wait gives up after 4 s and reports RHJ_PIPE_TIMEOUT
 
 // status bits (low 8 bits of a flag / status word; the rest is the epoch)
@@ -80,16 +79,17 @@ struct PipeShipArgs {
     u64 epoch;
     u32 *done;                   // CTA arrival counter (returns to 0)
     u32 *overflow;               // the local overflow flag (set by pass 1 or here)
+    u32 stages, stage_bytes;     // shared-memory ring
 };
 
 __global__ void __launch_bounds__(kPipeShipThreads) k_pipe_ship(PipeShipArgs a) {
     extern __shared__ __align__(128) unsigned char ring[];
-    __shared__ __align__(8) u64 s_full[kPipeStages];
+    __shared__ __align__(8) u64 s_full[kPipeMaxStages];
     __shared__ u32 s_last;
     const u32 tid = threadIdx.x;
     const u32 nd1 = 1u << a.sub_bits;
     if (tid == 0)
-        for (u32 s = 0; s < kPipeStages; ++s) mbar_init(&s_full[s], 1);
+        for (u32 s = 0; s < a.stages; ++s) mbar_init(&s_full[s], 1);
     __syncthreads();
 
     // region ends, one thread per region of this CTA's share: region (dest, p1) of this chunk lands in the
@@ -130,7 +130,7 @@ __global__ void __launch_bounds__(kPipeShipThreads) k_pipe_ship(PipeShipArgs a) 
                 if (c.off < c.cnt) {
                     g = c.g;
                     off = c.off;
-                    n = (u32) min((u64) (kPipeStageBytes / sizeof(Tup)), c.cnt - c.off);
+                    n = (u32) min((u64) (a.stage_bytes / sizeof(Tup)), c.cnt - c.off);
                     c.off += n;
                     return true;
                 }
@@ -144,17 +144,17 @@ __global__ void __launch_bounds__(kPipeShipThreads) k_pipe_ship(PipeShipArgs a) 
         u32 g, n;
         u64 off;
         // prime the ring
-        while (issued < kPipeStages - 1 && next_block(ld, g, off, n)) {
-            const u32 s = issued % kPipeStages;
+        while (issued < a.stages - 1 && next_block(ld, g, off, n)) {
+            const u32 s = issued % a.stages;
             mbar_expect_tx(&s_full[s], n * (u32) sizeof(Tup));
-            bulk_g2s(ring + (size_t) s * kPipeStageBytes, a.stage + (u64) g * a.cap1 + off, n * (u32) sizeof(Tup), &s_full[s]);
+            bulk_g2s(ring + (size_t) s * a.stage_bytes, a.stage + (u64) g * a.cap1 + off, n * (u32) sizeof(Tup), &s_full[s]);
             ++issued;
         }
         while (next_block(stc, g, off, n)) {
-            const u32 s = stored % kPipeStages;
-            mbar_wait(&s_full[s], (stored / kPipeStages) & 1);
+            const u32 s = stored % a.stages;
+            mbar_wait(&s_full[s], (stored / a.stages) & 1);
             const u32 dest = g >> a.sub_bits, p1 = g & (nd1 - 1);
-            bulk_s2g(a.peer_recv[dest] + (a.region0 + p1) * a.cap1 + off, ring + (size_t) s * kPipeStageBytes, n * (u32) sizeof(Tup));
+            bulk_s2g(a.peer_recv[dest] + (a.region0 + p1) * a.cap1 + off, ring + (size_t) s * a.stage_bytes, n * (u32) sizeof(Tup));
             bulk_commit();
             ++stored;
             // refill the stage the PREVIOUS store read from (its read-out is done once at most one group is pending)
@@ -162,9 +162,9 @@ __global__ void __launch_bounds__(kPipeShipThreads) k_pipe_ship(PipeShipArgs a) 
             u64 off2;
             if (next_block(ld, g2, off2, n2)) {
                 bulk_wait_read(1);
-                const u32 s2 = issued % kPipeStages;
+                const u32 s2 = issued % a.stages;
                 mbar_expect_tx(&s_full[s2], n2 * (u32) sizeof(Tup));
-                bulk_g2s(ring + (size_t) s2 * kPipeStageBytes, a.stage + (u64) g2 * a.cap1 + off2, n2 * (u32) sizeof(Tup), &s_full[s2]);
+                bulk_g2s(ring + (size_t) s2 * a.stage_bytes, a.stage + (u64) g2 * a.cap1 + off2, n2 * (u32) sizeof(Tup), &s_full[s2]);
                 ++issued;
             }
         }
@@ -196,6 +196,8 @@ struct PipeArriveArgs {
     u64 *seg_off;          // [nseg + 1]
     u64 *seg_end;          // [nseg]
     u32 *seg_tile0;        // [nseg + 1]
+    TileDesc *tiles;       // [ntiles] one descriptor per pass-2 tile (what k_tile_table builds on the other paths)
+    u32 ntiles;            // host-side bound; entries behind the last tile get len 0
     u64 *status;           // local status word (kPipe* bits are OR-ed in)
 };
 __global__ void __launch_bounds__(1024) k_pipe_arrive(PipeArriveArgs a) {
@@ -236,7 +238,12 @@ __global__ void __launch_bounds__(1024) k_pipe_arrive(PipeArriveArgs a) {
             a.seg_off[a.nseg] = beg + cnt;
             a.seg_tile0[a.nseg] = (u32) ttotal;
         }
+        for (u32 t = 0; t < (u32) tl; ++t) {
+            const u64 tb = beg + (u64) t * kTile;
+            a.tiles[tex + t] = TileDesc{tb, (u32) min((u64) kTile, beg + cnt - tb), tid};
+        }
     }
+    for (u32 t = (u32) ttotal + tid; t < a.ntiles; t += blockDim.x) a.tiles[t] = TileDesc{0, 0, 0};
 }
 
 // After the last pass 2: tell every rank whether anything overflowed here (sender or receiver side).

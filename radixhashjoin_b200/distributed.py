@@ -148,6 +148,40 @@ class FusedShardedJoin:
         return pairs, count, (nR, nS)
 
 
+def broadcast_is_cheaper(nR_global, nS_global, world):
+    """Exchange strategy of a sharded join (skew / small-build caveat): replicating the build side
+    costs every rank nB * (world - 1) / world tuples in, shuffling both sides (nB + nP) * (world - 1) / world^2;
+    with the redundant build-side partitioning on top, broadcasting pays once nB * world <= nP."""
+    nB, nP = min(nR_global, nS_global), max(nR_global, nS_global)
+    return world > 1 and nB * world <= nP
+
+
+class BroadcastShardedJoin:
+    """Multi-GPU join for a small build side (foreign-key joins, BASELINE config 3): every rank gathers the
+    whole build relation (one all-gather of nB tuples; the probe relation is never shuffled) and joins it with
+    its local probe shard through the single-GPU path.  Results stay sharded by probe row."""
+
+    def __init__(self, engine, world, rank, nR_global, nS_global, n_build_local, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.engine, self.world, self.rank = engine, world, rank
+        self.group = group if group is not None else dist.group.WORLD
+        self.build_is_S = nS_global < nR_global
+        dev = torch.device("cuda", engine.device)
+        self.n_build_local = int(n_build_local)   # equal on every rank (the all-gather is unpadded)
+        self.full = torch.empty((world * self.n_build_local, 2), dtype=torch.int64, device=dev)
+
+    def step(self, R_local, S_local, out, marks=None):
+        B, P = (S_local, R_local) if self.build_is_S else (R_local, S_local)
+        if B.shape[0] != self.n_build_local:
+            raise ValueError("the build shards must have the size given at construction on every rank")
+        self.dist.all_gather_into_tensor(self.full, B, group=self.group)
+        R, S = (P, self.full) if self.build_is_S else (self.full, P)
+        pairs, count = self.engine.join_device(R, S, out=out)
+        return pairs, count, None
+
+
 class PipeShardedJoin:
     """Multi-GPU join over the pipelined exchange (rhj_pipe_* in include/rhj.h): the default at N > 1.
 
@@ -205,14 +239,16 @@ class PipeShardedJoin:
         ev.record(stream if stream is not None else self.torch.cuda.current_stream())
         return ev
 
-    def _exact_step(self, R_local, S_local, out):
+    def _exact_step(self, R_local, S_local, out, marks=None):
         if self._exact is None:
             n_local_max = max(self.nmax)
             cap = self._exact_cap or int(n_local_max * 1.3) + 8192
             self._exact = DmaShardedJoin(self.engine, self.world, self.rank, self._globals[0], self._globals[1], n_local_max,
                                          cap, group=self.group)
         self.exact_steps += 1
-        return self._exact.step(R_local, S_local, out)
+        if marks is not None:
+            del marks[:]   # the timeline of a redone step is the exact exchange's
+        return self._exact.step(R_local, S_local, out, marks)
 
     def step(self, R_local, S_local, out, marks=None):
         """One sharded join; returns (pairs, count, None).  `marks` (a list) collects (label, CUDA event)
@@ -220,7 +256,7 @@ class PipeShardedJoin:
         torch, eng = self.torch, self.engine
         if self.exact_left > 0:
             self.exact_left -= 1
-            return self._exact_step(R_local, S_local, out)
+            return self._exact_step(R_local, S_local, out, marks)
         rels = (R_local, S_local)
         for rel in (0, 1):
             if rels[rel].shape[0] > self.nmax[rel]:
@@ -261,7 +297,7 @@ class PipeShardedJoin:
                                f"{'timeout ' if status & self.TIMEOUT else ''}{'bad region end' if status & self.BAD else ''})")
         if status & self.OVERFLOW:
             self.exact_left = 16
-            return self._exact_step(R_local, S_local, out)
+            return self._exact_step(R_local, S_local, out, marks)
         return pairs, count, None
 
     @staticmethod

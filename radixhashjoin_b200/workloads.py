@@ -43,15 +43,22 @@ def pair_hash(r, s):
     return mix64(r * _s64(0x100000001b3) + s)
 
 
-def _fill(n, device, fn):
-    """out[(n,2)] with out[i] = (i, fn(i)) and the digest pieces of fn's expected partner, chunked."""
+def _fill(n, device, fn, first=0):
+    """out[(n,2)] with out[i] = (first + i, fn(first + i)), chunked."""
     out = torch.empty((n, 2), dtype=torch.int64, device=device)
     for lo in range(0, n, _CHUNK):
         hi = min(n, lo + _CHUNK)
-        idx = torch.arange(lo, hi, dtype=torch.int64, device=device)
+        idx = torch.arange(first + lo, first + hi, dtype=torch.int64, device=device)
         out[lo:hi, 0] = idx
         out[lo:hi, 1] = fn(idx)
     return out
+
+
+def _shard(n, rank, world):
+    """rows [lo, hi) of an n-row relation that rank `rank` of `world` owns before the join"""
+    per = (n + world - 1) // world
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
 
 
 def _xor_reduce(h):
@@ -121,25 +128,30 @@ def uniform_unique_global_digest(log2_global, device="cpu", lo=0, hi=None):
     return _digest_range(lo, hi, device, lambda j: (j * a + b) & (n - 1))
 
 
-def foreign_key(log2_build, log2_probe, device="cpu", seed=SEED):
+def foreign_key(log2_build, log2_probe, device="cpu", seed=SEED, rank=0, world=1):
     """Config 3: unique build keys, every probe tuple references one build row.
-    S[j] = (j, mix64(row(j)+seed)), row(j) = (mix64(j ^ 0xabcdef) >> 1) mod N_R."""
+    S[j] = (j, mix64(row(j)+seed)), row(j) = (mix64(j ^ 0xabcdef) >> 1) mod N_R.
+    With world > 1 the call returns rank `rank`'s row ranges of both relations and the digest of what ITS probe
+    rows produce (the global expectation is the (sum, sum, xor) of the ranks' digests)."""
     nR, nS = 1 << log2_build, 1 << log2_probe
 
     def row(j):
         return lsr(mix64(j ^ 0xabcdef), 1) & (nR - 1)
 
-    R = _fill(nR, device, lambda i: mix64(i + seed))
-    S = _fill(nS, device, lambda j: mix64(row(j) + seed))
-    return Workload(f"fk_2^{log2_build}x2^{log2_probe}", R, S, _digest_of(nS, device, row),
+    r0, r1 = _shard(nR, rank, world)
+    s0, s1 = _shard(nS, rank, world)
+    R = _fill(r1 - r0, device, lambda i: mix64(i + seed), r0)
+    S = _fill(s1 - s0, device, lambda j: mix64(row(j) + seed), s0)
+    return Workload(f"fk_2^{log2_build}x2^{log2_probe}", R, S, _digest_range(s0, s1, device, row),
                     "foreign-key join, unique build keys (BASELINE config 3)")
 
 
-def zipf_probe(log2n, device="cpu", seed=SEED):
+def zipf_probe(log2n, device="cpu", seed=SEED, rank=0, world=1):
     """Config 4: unique build keys, probe keys ~ Zipf(theta = 1) by an integer-only inverse CDF:
     k = (mix64(j^0x5151) >> 8) mod log2n, rank r = 2^k + (mix64(j^0x7171) & (2^k - 1)) in [1, N-1]
     => P(r) = 1 / (log2n * 2^floor(log2 r)) ~ 1/r; the hottest key draws 1/log2n of the probe side.
-    build row = ((r-1) * A) mod N."""
+    build row = ((r-1) * A) mod N.  log2n is the GLOBAL size; world > 1 returns rank `rank`'s row ranges
+    and the digest of what its probe rows produce."""
     n = 1 << log2n
     a = _s64(A_MUL)
 
@@ -148,9 +160,10 @@ def zipf_probe(log2n, device="cpu", seed=SEED):
         r = (1 << k) + (mix64(j ^ 0x7171) & ((1 << k) - 1))
         return ((r - 1) * a) & (n - 1)
 
-    R = _fill(n, device, lambda i: mix64(i + seed))
-    S = _fill(n, device, lambda j: mix64(row(j) + seed))
-    return Workload(f"zipf_2^{log2n}x2^{log2n}", R, S, _digest_of(n, device, row),
+    lo, hi = _shard(n, rank, world)
+    R = _fill(hi - lo, device, lambda i: mix64(i + seed), lo)
+    S = _fill(hi - lo, device, lambda j: mix64(row(j) + seed), lo)
+    return Workload(f"zipf_2^{log2n}x2^{log2n}", R, S, _digest_range(lo, hi, device, row),
                     "Zipf(1.0) probe keys over unique build keys (BASELINE config 4)")
 
 

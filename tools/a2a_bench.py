@@ -17,30 +17,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--log2n", type=int, default=27)
-    ap.add_argument("--chunks", type=int, default=4)
-    ap.add_argument("--ctas", type=int, default=0)
-    ap.add_argument("--reps", type=int, default=5)
-    args = ap.parse_args()
-    import torch
-    import torch.distributed as dist
-    from radixhashjoin_b200 import RadixHashJoin
-    from radixhashjoin_b200 import workloads as W
+def one(args, torch, dist, eng, R, S, out, rank, world, dev, n, ctas, stage_kb, stages):
     from radixhashjoin_b200.distributed import PipeShardedJoin
-
-    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local_rank)
-    dev = f"cuda:{local_rank}"
-    dist.init_process_group("nccl", device_id=torch.device(dev))
-    eng = RadixHashJoin(local_rank)
-    n = 1 << args.log2n
-    gbits = args.log2n + (world.bit_length() - 1)
-    w = W.uniform_unique(args.log2n, dev, row_offset=rank * n, log2_global=gbits)
-    R, S = w.R, w.S
-    out = torch.empty((int(n * 1.05) + 4096, 2), dtype=torch.int64, device=dev)
-    pj = PipeShardedJoin(eng, world, rank, n * world, n * world, n, n, chunks=args.chunks, ship_ctas=args.ctas)
+    pj = PipeShardedJoin(eng, world, rank, n * world, n * world, n, n, chunks=args.chunks)
     rels = (R, S)
     times = []
     for rep in range(args.reps + 2):
@@ -77,9 +56,41 @@ def main():
         sent = 2 * n * 16 * (world - 1) / world
         ms = sorted(times)[len(times) // 2]
         print(json.dumps({"bench": "k_pipe_ship all-to-all", "n_gpus": world, "tuples_per_relation_per_gpu": n, "chunks": args.chunks,
-                          "ship_ctas": eng._lib and (args.ctas or 48), "remote_bytes_sent_per_gpu": sent, "ms_median": ms,
+                          "ship_ctas": ctas, "stage_kb": stage_kb, "stages": stages, "remote_bytes_sent_per_gpu": sent, "ms_median": ms,
                           "ms_all": [round(x, 3) for x in times], "GBps_per_gpu_per_direction": sent / ms / 1e6,
                           "total_pairs": int(cnt.item()), "expected_pairs": n * world}), flush=True)
+    del pj
+    torch.cuda.empty_cache()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--log2n", type=int, default=27)
+    ap.add_argument("--chunks", type=int, default=4)
+    ap.add_argument("--ctas", type=int, default=0)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--sweep", default="", help="comma list of ctas:stage_kb:stages to run one after the other")
+    args = ap.parse_args()
+    import torch
+    import torch.distributed as dist
+    from radixhashjoin_b200 import RadixHashJoin
+    from radixhashjoin_b200 import workloads as W
+    from radixhashjoin_b200.distributed import PipeShardedJoin
+
+    rank, world, local_rank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    dist.init_process_group("nccl", device_id=torch.device(dev))
+    eng = RadixHashJoin(local_rank)
+    n = 1 << args.log2n
+    gbits = args.log2n + (world.bit_length() - 1)
+    w = W.uniform_unique(args.log2n, dev, row_offset=rank * n, log2_global=gbits)
+    R, S = w.R, w.S
+    out = torch.empty((int(n * 1.05) + 4096, 2), dtype=torch.int64, device=dev)
+    configs = [tuple(int(x) for x in c.split(":")) for c in args.sweep.split(",") if c] or [(args.ctas or 48, 8, 8)]
+    for ctas, stage_kb, stages in configs:
+        os.environ["RHJ_PIPE_SHIP_CTAS"], os.environ["RHJ_PIPE_STAGE_KB"], os.environ["RHJ_PIPE_STAGES"] = str(ctas), str(stage_kb), str(stages)
+        one(args, torch, dist, eng, R, S, out, rank, world, dev, n, ctas, stage_kb, stages)
     dist.destroy_process_group()
 
 
