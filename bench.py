@@ -102,10 +102,12 @@ def measured_hbm_peak():
 # ------------------------------------------------------------------------------------------------
 # the reference arm / cpu_baseline: the reference's own multiRadixHashJoin on the host cores
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_run(log2n, steps, warmup):
+def cpu_reference_run(log2n, steps, warmup, budget_s=None):
     """Times oracle/_ref (the unmodified reference, NUM_OF_THREADS pthread workers) -- or, if that
-    build is absent, the single-threaded C port -- on a 2^log2n x 2^log2n sample of the uniform
-    workload.  Returns (tuples_per_s, seconds_per_step, info)."""
+    build is absent, the single-threaded C port -- on the 2^log2n x 2^log2n uniform workload.
+    With budget_s the loop stops early (after at least one timed step) once that many seconds of joins have
+    run, so that a 6-second-per-join configuration still ends within a few minutes.
+    Returns (tuples_per_s, seconds_per_step, info, timed_steps)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import _oracle as O
     from radixhashjoin_b200 import workloads as W
@@ -113,27 +115,37 @@ def cpu_reference_run(log2n, steps, warmup):
     R, S = W.to_numpy_tuples(w.R), W.to_numpy_tuples(w.S)
     n_in = len(R) + len(S)
     times = []
+    spent = 0.0
     if O.have_ref():
         kind, cores = "reference", O.libref().ref_num_threads()
-        for i in range(warmup + steps):
+
+        def one():
             cnt, sec = O.reference_join(R, S, want_pairs=False)
             assert cnt == len(S)
-            if i >= warmup:
-                times.append(sec)
+            return sec
     else:
         kind, cores = "port", 1
-        for i in range(warmup + steps):
+
+        def one():
             t0 = time.perf_counter()
             p = O.oracle_join(R, S)
             sec = time.perf_counter() - t0
             assert len(p) == len(S)
-            if i >= warmup:
-                times.append(sec)
+            return sec
+    for i in range(warmup + steps):
+        sec = one()
+        spent += sec
+        if i >= warmup:
+            times.append(sec)
+        elif budget_s is not None and spent > budget_s / 4:
+            warmup = i + 1   # the warm-up already used its share: the next runs are timed ones
+        if budget_s is not None and times and spent > budget_s:
+            break
     sec = sum(times) / len(times)
     info = {"kind": kind, "cores": cores, "host_cpus": os.cpu_count(),
             "sample": f"uniform_unique 2^{log2n} x 2^{log2n} (same generator as the GPU workload), "
-                      f"{steps} timed run(s) of Result::multiRadixHashJoin alone, inputs in host RAM"}
-    return n_in / sec, sec, info
+                      f"{len(times)} timed run(s) of Result::multiRadixHashJoin alone, inputs in host RAM"}
+    return n_in / sec, sec, info, len(times)
 
 
 def small_work_wall(with_reference=False):
@@ -178,6 +190,52 @@ def small_work_wall(with_reference=False):
         return res
 
 
+def bytes_moved(nR, nS, m, plan):
+    """HBM bytes one join actually moves: two scatters (32 B per tuple each), the join's read, the pairs,
+    plus the histograms that RAN -- plan['optimistic_pass1'] bit 0 / 1: the build / probe relation skipped its pass-1
+    histogram, bit 2: both skipped the pass-2 one.  The canonical 96n + 16m of SURVEY 8d counts one histogram read
+    (16n) regardless."""
+    nB, nP = min(nR, nS), max(nR, nS)
+    n = nB + nP
+    o = plan["optimistic_pass1"]
+    passes = (1 if plan["bits_pass1"] else 0) + (1 if plan["bits_pass2"] else 0)
+    b = 32 * n * passes + 16 * n + 16 * m
+    if plan["bits_pass1"]:
+        b += (0 if o & 1 else 16 * nB) + (0 if o & 2 else 16 * nP)
+    if plan["bits_pass2"] and not o & 4:
+        b += 16 * n
+    return b
+
+
+def target_2p28(eng, dev, emit, peak):
+    """The size the north star quotes its bar for (2^28 x 2^28 uniform, >= 50 % of the HBM roofline on one B200),
+    measured like the headline: inputs resident, CUDA events around 5 joins after 3 warm-ups, count + digest checked."""
+    import torch
+    from radixhashjoin_b200 import workloads as W
+    w = W.uniform_unique(28, dev)
+    n = w.R.shape[0]
+    out = torch.empty((n, 2), dtype=torch.int64, device=dev)
+    eng.reserve(n, n)
+    for _ in range(3):
+        pairs, count = eng.join_device(w.R, w.S, out=out, emit=emit)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        pairs, count = eng.join_device(w.R, w.S, out=out, emit=emit)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    plan = eng.last_plan()
+    ok = tuple(eng.pairs_digest(pairs)) == tuple(w.expected)
+    canon, moved = 96 * 2 * n + 16 * count, bytes_moved(n, n, count, plan)
+    return {"workload": w.name, "ms_per_step": ms, "steps": 5, "warmup": 3, "value": 2 * n / (ms * 1e-3), "unit": UNIT,
+            "verified": ok, "radix_bits": [plan["bits_pass1"], plan["bits_pass2"]], "optimistic_mask": plan["optimistic_pass1"],
+            "canonical_bytes": canon, "frac_canonical_of_measured_hbm": canon / (ms * 1e-3) / 1e9 / peak,
+            "bytes_moved": moved, "frac_moved_of_measured_hbm": moved / (ms * 1e-3) / 1e9 / peak,
+            "workspace_GiB": round(eng.workspace_bytes() / 2**30, 2)}
+
+
 def _workload_name(log2n, world):
     """config.workload of both arms: the single-GPU configuration, or the global relation pair sharded over N ranks"""
     if world == 1:
@@ -187,17 +245,24 @@ def _workload_name(log2n, world):
 
 
 def run_reference(args, rank):
+    """The reference's own CPU path on the stated configuration: at N = 1 every step is one complete
+    2^log2n x 2^log2n join (BASELINE configs[1] by default: 2^27 x 2^27, ~6 s per join, ~14 GiB of host RAM); the
+    number of timed steps is capped by --ref-budget-s.  At N > 1 (config = a global relation pair sharded over N GPUs,
+    which does not fit one host's reference run) rank 0 times the per-GPU share, 2^log2n x 2^log2n, and says so."""
     if rank != 0:
         return
-    log2n = args.ref_log2n
-    val, sec, info = cpu_reference_run(log2n, args.steps, args.warmup)
+    log2n = args.ref_log2n if args.ref_log2n else args.log2n
+    val, sec, info, timed = cpu_reference_run(log2n, args.steps, min(args.warmup, 1), budget_s=args.ref_budget_s)
+    same = args.gpus == 1 and log2n == args.log2n
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "steps": timed, "steps_requested": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
             "config": {"workload": _workload_name(args.log2n, args.gpus), "tuples_per_gpu": 2 << args.log2n,
                        "tuple_bytes": 16,
-                       "sample_per_step": f"2^{log2n} x 2^{log2n} tuples of the same generator (the reference's throughput is "
-                                          "flat in size: BASELINE.md 2.2)"},
+                       "sample_per_step": (f"the whole configuration: one 2^{log2n} x 2^{log2n} join per step" if same else
+                                           f"2^{log2n} x 2^{log2n} tuples of the same generator per step (one GPU's share of the "
+                                           "sharded configuration; the reference is a single-process program)"),
+                       "timed_steps_cap": f"{args.ref_budget_s} s of joins (--ref-budget-s)"},
             "cpu_baseline": dict(info, value=val, unit=UNIT),
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -436,6 +501,7 @@ def run_b200(args, rank, world, local_rank):
                     "algorithmic_bytes_per_launch": alg_bytes[dom]}
     b_alg_step = 96 * n_join + 16 * m_local     # canonical 2-pass plan
     step_gbs = b_alg_step / (ms_step * 1e-3) / 1e9
+    moved_step = bytes_moved(nR, nS, m_local, plan) if world == 1 else None
 
     # ---- end to end through the host entry point (pinned host buffers, H2D + D2H inside) ----
     e2e = None
@@ -463,7 +529,23 @@ def run_b200(args, rank, world, local_rank):
                "d2h_bytes_per_step": 16 * cnt, "ms_per_step": dt * 1e3, "steps": k, "verified": e2e_ok,
                "api": "rhj_join_host (count-then-write emitter, pinned host inputs, pinned host result; probe side streamed in "
                       "2^24-tuple chunks so H2D, compute and D2H overlap)"}
+        # the same call with the arrays the drop-in host/Result.cpp passes: the reference's relation::tuples are
+        # `new tuple[]` (structs.cpp:217-243), i.e. PAGEABLE host memory
+        pR, pS = hR.numpy().copy(), hS.numpy().copy()
         del hR, hS
+        for _ in range(1):
+            view, cnt = eng.join_host_view(pR, pS)
+        t0 = time.perf_counter()
+        kp = max(1, min(3, k))
+        for _ in range(kp):
+            view, cnt = eng.join_host_view(pR, pS)
+            first = int(view["keyR"][0])
+        dtp = (time.perf_counter() - t0) / kp
+        dres = torch.from_numpy(view.view(np.int64).reshape(-1, 2)).to(dev)
+        ok_p = (cnt,) + tuple(eng.pairs_digest(dres)[1:]) == tuple(expected) if expected else None
+        del dres, pR, pS
+        e2e["pageable"] = {"value": n_in_local / dtp, "unit": UNIT, "ms_per_step": dtp * 1e3, "steps": kp, "verified": ok_p,
+                           "note": "inputs in pageable (malloc'd) host arrays, as host/Result.cpp passes them"}
     elif world > 1:
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "note": "multi-GPU run keeps shards device-resident; e2e is reported at N=1"}
@@ -473,8 +555,17 @@ def run_b200(args, rank, world, local_rank):
     if world == 1 and rank == 0 and not args.no_cpu:
         del out
         torch.cuda.empty_cache()
-        v, sec, info = cpu_reference_run(args.cpu_log2n, 1, 0)
+        v, sec, info, _ = cpu_reference_run(args.cpu_log2n, 1, 0)
         cpu = dict(info, value=v, unit=UNIT, seconds=sec)
+
+    target = None
+    if world == 1 and rank == 0 and args.workload == "uniform" and log2n == 27 and not args.no_target:
+        try:
+            del R, S, w
+            torch.cuda.empty_cache()
+            target = target_2p28(eng, dev, emit, peak)
+        except Exception as ex:  # never lose the headline line to the extra block
+            target = {"unavailable": repr(ex)[:200]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -503,8 +594,14 @@ def run_b200(args, rank, world, local_rank):
                 "phase_ms": {k: round(v, 4) for k, v in acc.items() if v > 0},
                 "roofline": roofline,
                 "step_roofline": {"algorithmic_bytes": b_alg_step, "formula": "96*n + 16*m (SURVEY 8d)",
-                                  "achieved_GBps": step_gbs, "frac_of_measured_hbm": step_gbs / peak},
+                                  "achieved_GBps": step_gbs, "frac_of_measured_hbm": step_gbs / peak,
+                                  "bytes_moved": moved_step,
+                                  "frac_moved_of_measured_hbm": moved_step / (ms_step * 1e-3) / 1e9 / peak if moved_step else None,
+                                  "note": "canonical bytes credit the histograms the histogram-free passes skip; bytes_moved "
+                                          "counts only what ran (plan optimistic mask %d)" % plan["optimistic_pass1"]},
                 "e2e": e2e, "cpu_baseline": cpu}
+        if target:
+            line["target_2p28"] = target
         if shard_timeline:
             line["shard_timeline_ms"] = shard_timeline
         if nvlink:
@@ -529,7 +626,8 @@ def main():
     ap.add_argument("--emit", default="fused", choices=["fused", "count_then_write"])
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-log2n", type=int, default=26, help="cpu_baseline sample size (2^k x 2^k)")
-    ap.add_argument("--ref-log2n", type=int, default=24, help="--impl reference: sample per step")
+    ap.add_argument("--ref-log2n", type=int, default=0, help="--impl reference: 2^k x 2^k per step (default: --log2n, the stated config)")
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: stop timing after this many seconds of joins")
     ap.add_argument("--shuffle", default="pipe", choices=["pipe", "dma", "stores", "nccl"],
                     help="multi-GPU exchange: pipelined histogram-free chunks shipped by our copy kernel (default), pass-1 chunks "
                          "shipped by the copy engines after exact histograms, pass-1 scatter storing straight into peer memory, "
@@ -542,6 +640,7 @@ def main():
     ap.add_argument("--small-work-ref", action="store_true", help="also time the unmodified reference program (minutes)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-target", action="store_true", help="skip the extra 2^28 x 2^28 block of the N=1 line")
     args = ap.parse_args()
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if args.impl == "reference":

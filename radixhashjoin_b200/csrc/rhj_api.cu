@@ -105,8 +105,12 @@ int launch_scatter(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, b
         return RHJ_OK;
     }
     if (limit) {  // optimistic passes: fixed-capacity regions, bounds-checked staged stores
-        if (kind != kDigitHash || a.ndig > 512) return fail(ctx, RHJ_ERR_STATE, "bounds-checked scatter: hash digits, <= 512 per pass");
-        if (seg) {
+        if (kind != kDigitHash) return fail(ctx, RHJ_ERR_STATE, "bounds-checked scatter: hash digits only");
+        if (a.ndig > 512) {  // 1024-digit second pass: only the sharded plans of very large relations (2^28 tuples per rank) need it
+            if (!seg) return fail(ctx, RHJ_ERR_STATE, "bounds-checked scatter: > 512 digits only in the segmented pass");
+            CK(set_smem(k_scatter<kDigitHash, true, kWriteStaged, kMaxDigits, true>, kScatterSmem));
+            k_scatter<kDigitHash, true, kWriteStaged, kMaxDigits, true><<<grid, kPartThreads, kScatterSmem, st>>>(a);
+        } else if (seg) {
             CK(set_smem(k_scatter<kDigitHash, true, kWriteStaged, 512, true>, kScatterSmem));
             k_scatter<kDigitHash, true, kWriteStaged, 512, true><<<grid, kPartThreads, kScatterSmem, st>>>(a);
         } else {
@@ -257,7 +261,10 @@ int second_pass_and_plan(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Me
     const u64 cap[2] = {fixed_cap2(pl.nB, pl.nparts), fixed_cap2(pl.nP, pl.nparts)};
     const size_t regB = (size_t) pl.nparts * cap[0], regP = (size_t) pl.nparts * cap[1];
     // the padded layout needs ~1.4x the memory of the packed one: when that does not fit, pack (histogram path)
-    if (fixed2 && pl.b2 > 0 && ensure(ctx, ctx->bufB, (regB + regP + kTile) * sizeof(Tup)) != RHJ_OK) fixed2 = false;
+    if (fixed2 && pl.b2 > 0 && ensure(ctx, ctx->bufB, (regB + regP + kTile) * sizeof(Tup)) != RHJ_OK) {
+        fixed2 = false;
+        ctx->err.clear();  // not an error: the packed layout is tried next
+    }
     if (pl.b2 == 0) {
         finB = inX[0];
         finP = inX[1];
@@ -502,11 +509,21 @@ int partition_and_plan(rhj_ctx *ctx, cudaStream_t st, const Tup *dR, u64 nR, con
         }
         if (opt[0] || opt[1]) {
             const u32 nd1 = 1u << pl.b1;
+            const size_t regB = opt[0] ? (size_t) nd1 * fixed_cap(pl.nB, nd1) : pl.nB;
+            const size_t regP = opt[1] ? (size_t) nd1 * fixed_cap(pl.nP, nd1) : pl.nP;
+            if (ensure(ctx, ctx->bufA, (regB + regP + kTile) * sizeof(Tup)) != RHJ_OK) {
+                // the padded layout does not fit where the packed one might: take the histogram path for both relations
+                ctx->err.clear();
+                opt[0] = opt[1] = false;
+                fixed2 = false;
+            }
+        }
+        if (opt[0] || opt[1]) {
+            const u32 nd1 = 1u << pl.b1;
             const u64 cap[2] = {fixed_cap(pl.nB, nd1), fixed_cap(pl.nP, nd1)};
             const u64 nX[2] = {pl.nB, pl.nP};
             const Tup *inX0[2] = {inB, inP};
             const size_t regB = opt[0] ? (size_t) nd1 * cap[0] : pl.nB, regP = opt[1] ? (size_t) nd1 * cap[1] : pl.nP;
-            if ((rc = ensure(ctx, ctx->bufA, (regB + regP + kTile) * sizeof(Tup)))) return rc;
             Tup *A = (Tup *) ctx->bufA.p;
             Tup *outX[2] = {A, A + regB};
             PartArgs a{};
@@ -661,6 +678,8 @@ int write_phase(rhj_ctx *ctx, cudaStream_t st, Pair *d_out, u64 capacity) {
     if (capacity < ctx->cur.count) return fail(ctx, RHJ_ERR_CAPACITY, "output buffer smaller than the counted result");
     if (ctx->cur.count == 0) return RHJ_OK;
     JoinArgs j = join_args(ctx, kScWork1);
+    // a second write pass after one count (a retry into another buffer) must not find every item already taken
+    CK(cudaMemsetAsync(scalars_of(ctx, ctx->cur.nparts) + kScWork1, 0, 8, st));
     j.item_off = (const u64 *) ctx->item_off.p;
     j.out = d_out;
     j.capacity = capacity;
@@ -1126,7 +1145,15 @@ void *rhj_pairs_to_pages(const rhj_pair *pairs, uint64_t count, uint64_t *head_s
     for (uint64_t at = 0; at < count; at += cap) {
         uint64_t k = std::min(cap, count - at);
         char *page = (char *) malloc(page_bytes);
-        if (!page) abort();
+        if (!page) {  // out of host memory: free what was built and report it (count > 0 with a NULL head and *head_size == 0)
+            while (head) {
+                void *next = *(void **) head;
+                free(head);
+                head = next;
+            }
+            if (head_size) *head_size = 0;
+            return nullptr;
+        }
         *(void **) page = head;
         memcpy(page + sizeof(void *), pairs + at, k * sizeof(rhj_pair));
         head = page;
@@ -1141,6 +1168,8 @@ int rhj_histogram_device(rhj_ctx *ctx, const rhj_tuple *d_in, uint64_t n, int bi
                          uint64_t *d_hist, void *stream) {
     if (!ctx || !d_hist || bits < 0 || bits > kPlanBitsPerPass || shift < 0 || shift > 63) return RHJ_ERR_ARG;
     if (digit_kind != RHJ_DIGIT_RAW && digit_kind != RHJ_DIGIT_HASH) return RHJ_ERR_ARG;
+    // the hashed digit is taken from a 32-bit word, the raw one from the 64-bit value
+    if (shift + bits > (digit_kind == RHJ_DIGIT_HASH ? 32 : 64)) return RHJ_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = pick(ctx, stream);
     u32 ndig = 1u << bits;
@@ -1190,6 +1219,7 @@ int rhj_partition_device(rhj_ctx *ctx, const rhj_tuple *d_in, uint64_t n, int bi
                          rhj_tuple *d_out, uint64_t *d_offsets, void *stream) {
     if (!ctx || bits < 0 || bits > kPlanBitsPerPass || shift < 0 || shift > 63) return RHJ_ERR_ARG;
     if (digit_kind != RHJ_DIGIT_RAW && digit_kind != RHJ_DIGIT_HASH) return RHJ_ERR_ARG;
+    if (shift + bits > (digit_kind == RHJ_DIGIT_HASH ? 32 : 64)) return RHJ_ERR_ARG;
     if (n && (!d_in || !d_out)) return fail(ctx, RHJ_ERR_ARG, "null pointer");
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = pick(ctx, stream);
