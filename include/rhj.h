@@ -110,7 +110,8 @@ int rhj_join_host(rhj_ctx *ctx, const rhj_tuple *R, uint64_t nR, const rhj_tuple
 /* Materialises pairs[count] as the reference's page list (Result.cpp:21-35): malloc'd 128 KiB
  * pages [next*][8191 x key_tuple], newest page first; *head_size = pairs in the head page
  * (Result.size), every other page is full.  The pages are free()'d by ~Result (Result.cpp:127-133).
- * Returns the head page (NULL when count == 0). */
+ * Returns the head page (NULL when count == 0; NULL with *head_size == 0 when a page could not be allocated --
+ * nothing is leaked in that case). */
 void *rhj_pairs_to_pages(const rhj_pair *pairs, uint64_t count, uint64_t *head_size);
 
 /* ---- the steps, individually callable (parity tests compare each with the reference) -------- */

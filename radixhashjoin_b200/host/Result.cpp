@@ -72,6 +72,10 @@ void Result::multiRadixHashJoin(JobScheduler &, relation &relR, relation &relS) 
     rhj_host::check(rc, "rhj_join_host");
     uint64_t head_size = capacity;
     head = (bucket_info *) rhj_pairs_to_pages(pairs, count, &head_size);
+    if (count && head == nullptr) {  // the page list could not be allocated (the reference's add_result would have crashed)
+        fprintf(stderr, "Result::multiRadixHashJoin: out of host memory for %llu result pairs\n", (unsigned long long) count);
+        exit(EXIT_FAILURE);
+    }
     size = head_size;
 }
 
