@@ -354,8 +354,14 @@ def run_b200(args, rank, world, local_rank):
         elif strategy == "pipe":
             # histogram-free chunked pass 1 -> hand-written TMA copy kernel over NVLink -> appended pass 2 -> join;
             # no collective call and one host synchronisation per step (radixhashjoin_b200/distributed.py)
+            # 12-byte records on the wire when every row id fits 32 bits (checked once here, and by the copy kernel in every
+            # step) and the exchange is wire-bound (4+ ranks); 16-byte tuples otherwise
+            mx = torch.stack([R[:, 0].max(), S[:, 0].max()]).max()
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            wire = args.wire_bytes or (12 if world >= 4 and int(mx.item()) < (1 << 32) else 16)
+            compact = wire == 12
             pj = PipeShardedJoin(eng, world, rank, nR * world, nS * world, nR, nS, chunks=args.chunks,
-                                 exact_recv_capacity=slack)
+                                 exact_recv_capacity=slack, wire_bytes=wire)
 
             def step():
                 pairs, count, _ = pj.step(R, S, out)
@@ -474,7 +480,7 @@ def run_b200(args, rank, world, local_rank):
         sent = [v for k, v in shard_timeline if k.startswith("ship_")]
         acc = {"join": tl["join_done"] - max(p2), "scatter1": max(p1) - tl["start"]}
         wire_ms = max(sent) - min(p1)
-        out_bytes = 16 * n_in_local * (world - 1) / world
+        out_bytes = (12 if compact else 16) * n_in_local * (world - 1) / world
         nvlink = {"bytes_out_per_gpu": out_bytes, "wire_busy_ms": wire_ms, "achieved_GBps_per_direction": out_bytes / wire_ms / 1e6,
                   "peak_GBps_per_direction": 770.0, "peak_source": "B200_PROFILING.md measured peer copy",
                   "frac": out_bytes / wire_ms / 1e6 / 770.0,
@@ -581,7 +587,8 @@ def run_b200(args, rank, world, local_rank):
                                f"{world} ranks: the build side is all-gathered ({min(nR, nS) * world} tuples), the probe side is never "
                                "shuffled, every rank joins its probe shard locally" if strategy == "broadcast" else
                                f"{world} ranks: {args.chunks} row chunks per relation; histogram-free pass 1 on (rank | sub-digit) into "
-                               "fixed-capacity regions, TMA copy kernel ships them over NVLink while the next chunk is partitioned, "
+                               f"fixed-capacity regions, TMA copy kernel ships them ({12 if compact else 16} B per tuple) over NVLink while "
+                               "the next chunk is partitioned, "
                                "pass 2 appends each arrived chunk to fixed-capacity final partitions, one join; no collective in the "
                                f"step (exact-path steps among the timed ones: {pj.exact_steps})" if strategy == "pipe" else
                                f"{world} ranks: pass 1 partitions on (rank | sub-digit), copy engines ship one chunk per peer "
@@ -633,6 +640,8 @@ def main():
                          "shipped by the copy engines after exact histograms, pass-1 scatter storing straight into peer memory, "
                          "or rank partition + NCCL all-to-all")
     ap.add_argument("--chunks", type=int, default=4, help="pipe shuffle: row chunks per relation")
+    ap.add_argument("--wire-bytes", type=int, default=0, choices=[0, 12, 16],
+                    help="pipe shuffle: bytes per tuple on the wire (0 = 12 when row ids fit 32 bits and N >= 4, else 16)")
     ap.add_argument("--ship-bytes", type=int, default=16, choices=[12, 16],
                     help="dma shuffle: bytes per tuple on the wire; 12 = {u64 value, u32 row id}, used when row ids fit 32 bits")
     ap.add_argument("--split-probe", action="store_true", help="dma shuffle: ship the probe relation in two halves (measured slower)")

@@ -253,10 +253,15 @@ int rhj_shardx_join_slots_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int b
 #define RHJ_PIPE_OVERFLOW 1u   /* a fixed-capacity region overflowed somewhere: redo through rhj_shardx_*   */
 #define RHJ_PIPE_TIMEOUT 2u    /* a peer's flag did not arrive within 4 s                                   */
 #define RHJ_PIPE_BAD 4u        /* a received region end was out of range                                    */
+#define RHJ_PIPE_WIDE 8u       /* 12-byte wire format: a row id did not fit 32 bits (use wire_bytes = 16)   */
 typedef struct rhj_pipe_cfg {
     uint32_t world, rank;
     uint32_t chunks;                       /* row chunks per relation, 1..8                                  */
     uint32_t ship_ctas;                    /* CTAs of the copy kernel (0 = default 48)                       */
+    uint32_t wire_bytes;                   /* bytes per tuple on the wire: 16 (0 = default), or 12 = {u64 value, u32 row
+                                              id} records repacked by the copy kernel -- the caller promises that row ids
+                                              fit 32 bits, a wider one is reported as RHJ_PIPE_WIDE                      */
+    uint32_t reserved0;
     uint64_t nR_local_max, nS_local_max;   /* rows per rank (upper bound over ranks) of R and S              */
     void *sym[RHJ_MAX_PEERS];              /* base of every rank's symmetric block, valid in this process    */
 } rhj_pipe_cfg;

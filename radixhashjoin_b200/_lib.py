@@ -31,7 +31,8 @@ class ShardPlan(ctypes.Structure):
 class PipeCfg(ctypes.Structure):
     """struct rhj_pipe_cfg (include/rhj.h)."""
     _fields_ = [("world", ctypes.c_uint32), ("rank", ctypes.c_uint32), ("chunks", ctypes.c_uint32),
-                ("ship_ctas", ctypes.c_uint32), ("nR_local_max", ctypes.c_uint64), ("nS_local_max", ctypes.c_uint64),
+                ("ship_ctas", ctypes.c_uint32), ("wire_bytes", ctypes.c_uint32), ("reserved0", ctypes.c_uint32),
+                ("nR_local_max", ctypes.c_uint64), ("nS_local_max", ctypes.c_uint64),
                 ("sym", ctypes.c_void_p * 16)]
 
 

@@ -307,9 +307,9 @@ class RadixHashJoin:
         return out[:cnt.value], int(cnt.value)
 
     # ---- multi-GPU: pipelined exchange (include/rhj.h, rhj_pipe_*) --------------------------------
-    def pipe_cfg(self, plan, rank, chunks, nR_local_max, nS_local_max, sym_ptrs=None, ship_ctas=0):
+    def pipe_cfg(self, plan, rank, chunks, nR_local_max, nS_local_max, sym_ptrs=None, ship_ctas=0, wire_bytes=16):
         cfg = _lib.PipeCfg()
-        cfg.world, cfg.rank, cfg.chunks, cfg.ship_ctas = plan.world, rank, chunks, ship_ctas
+        cfg.world, cfg.rank, cfg.chunks, cfg.ship_ctas, cfg.wire_bytes = plan.world, rank, chunks, ship_ctas, wire_bytes
         cfg.nR_local_max, cfg.nS_local_max = nR_local_max, nS_local_max
         for i, p in enumerate(sym_ptrs or []):
             cfg.sym[i] = p

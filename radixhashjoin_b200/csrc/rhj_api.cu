@@ -106,6 +106,19 @@ int launch_scatter(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, b
     }
     if (limit) {  // optimistic passes: fixed-capacity regions, bounds-checked staged stores
         if (kind != kDigitHash) return fail(ctx, RHJ_ERR_STATE, "bounds-checked scatter: hash digits only");
+        if (!a.rel[0].in && a.rel[0].in_packed) {  // packed 12-byte records in (pipelined exchange, pass 2), 16-byte tuples out
+            if (!seg) return fail(ctx, RHJ_ERR_STATE, "packed input is only wired for the segmented pass");
+            if (a.ndig > 512) {
+                CK(set_smem(k_scatter<kDigitHash, true, kWriteStaged, kMaxDigits, true, kIoPacked12In>, kScatterSmem));
+                k_scatter<kDigitHash, true, kWriteStaged, kMaxDigits, true, kIoPacked12In><<<grid, kPartThreads, kScatterSmem, st>>>(a);
+            } else {
+                CK(set_smem(k_scatter<kDigitHash, true, kWriteStaged, 512, true, kIoPacked12In>, kScatterSmem));
+                k_scatter<kDigitHash, true, kWriteStaged, 512, true, kIoPacked12In><<<grid, kPartThreads, kScatterSmem, st>>>(a);
+            }
+            CK(cudaGetLastError());
+            ctx->info.kernel_launches++;
+            return RHJ_OK;
+        }
         if (a.ndig > 512) {  // 1024-digit second pass: only the sharded plans of very large relations (2^28 tuples per rank) need it
             if (!seg) return fail(ctx, RHJ_ERR_STATE, "bounds-checked scatter: > 512 digits only in the segmented pass");
             CK(set_smem(k_scatter<kDigitHash, true, kWriteStaged, kMaxDigits, true>, kScatterSmem));

@@ -101,7 +101,7 @@ struct rhj_ctx {
     struct PipeState {
         bool open = false;
         rhj_shard_plan plan{};
-        u32 world = 1, rank = 0, chunks = 1, ship_ctas = 48, stages = 8, stage_bytes = 8192;
+        u32 world = 1, rank = 0, chunks = 1, ship_ctas = 48, stages = 8, stage_bytes = 8192, wire = 16;
         u64 nmax[2] = {0, 0};          // rows per rank (upper bound) of R / S
         u64 chunk_rows[2] = {0, 0};    // rows per chunk
         u64 cap1[2] = {0, 0};          // capacity of one (chunk, destination, sub-digit) region, tuples

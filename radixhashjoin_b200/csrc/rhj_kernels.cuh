@@ -62,6 +62,7 @@ struct PartRel {
     const u32 *in_rid;
     u64 *out_val;          // output when `out` is null (non-peer scatter only)
     u32 *out_rid;
+    const unsigned char *in_packed;  // kIoPacked12In: record i at byte 12 * i
     // k_scatter<LIMIT>: a run that does not fit its partition's region is written to the kTile tuples at out[dump..]
     // instead (nothing out of bounds, no per-tuple check); the overflow flag makes the host discard the attempt.
     u64 dump;
@@ -70,7 +71,9 @@ struct PartRel {
 // tuple idx of a relation in either form
 // How a partitioning kernel reads / writes tuples: 16-byte AoS both ways (everything single-GPU), or the
 // 12-byte form the DMA-shipped sharded join puts on the wire ({u64 value}[n] + {u32 row id}[n]) on one side.
-enum TupleIo { kIoAos = 0, kIoSoaIn = 1, kIoSoaOut = 2 };
+// kIoPacked12In: packed 12-byte records {u64 value, u32 row id} -- the wire format of the pipelined exchange
+// (rhj_pipe_kernels.cuh); a tile is fetched with one TMA bulk copy and unpacked from shared memory.
+enum TupleIo { kIoAos = 0, kIoSoaIn = 1, kIoSoaOut = 2, kIoPacked12In = 3 };
 template <int IO>
 __device__ __forceinline__ Tup ld_tuple(const PartRel &r, u64 idx) {
     if (IO != kIoSoaIn) return ld_stream(r.in + idx);
@@ -301,10 +304,33 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
     for (u32 d = tid; d < a.ndig; d += kPartThreads) s_cnt[d] = 0;
     Tup v[kPartItems];
     u32 dr[kPartItems];  // digit << 16 | rank   (digit < 1024, rank < 4096)
+    if (IO == kIoPacked12In) {
+        // one TMA bulk copy brings the tile's 12-byte records into the staging area (which the sorted tile reuses later);
+        // every thread then unpacks its 8 records with conflict-free 4-byte shared-memory loads (stride 3 words)
+        __shared__ __align__(8) u64 s_bar;
+        if (tid == 0) {
+            mbar_init(&s_bar, 1);
+            const u32 bytes = (ntile * 12 + 15) & ~15u;  // the region capacity is a multiple of 16 bytes: the slack is readable
+            mbar_expect_tx(&s_bar, bytes);
+            bulk_g2s(dyn_smem, r.in_packed + beg * 12, bytes, &s_bar);
+        }
+        __syncthreads();
+        mbar_wait(&s_bar, 0);
+        const u32 *w = reinterpret_cast<const u32 *>(dyn_smem);
 #pragma unroll
-    for (int j = 0; j < kPartItems; ++j) {
-        u32 i = j * kPartThreads + tid;
-        if (i < ntile) v[j] = ld_tuple<IO>(r, beg + i);
+        for (int j = 0; j < kPartItems; ++j) {
+            u32 i = j * kPartThreads + tid;
+            if (i < ntile) {
+                v[j].val = (u64) w[3 * i] | ((u64) w[3 * i + 1] << 32);
+                v[j].key = w[3 * i + 2];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kPartItems; ++j) {
+            u32 i = j * kPartThreads + tid;
+            if (i < ntile) v[j] = ld_tuple<IO>(r, beg + i);
+        }
     }
     __syncthreads();
 #pragma unroll

@@ -15,6 +15,7 @@ inline u64 pipe_cap1(u64 rows, u32 ndig) {
 struct PipeLayout {
     u64 chunk_rows[2], cap1[2];
     u64 off_recv[2][2], off_end[2][2], off_flag, off_status, bytes;
+    u32 wire;
 };
 
 // The same arithmetic on every rank: where everything lies inside a rank's symmetric block.
@@ -23,6 +24,8 @@ int pipe_layout(const rhj_shard_plan *sp, const rhj_pipe_cfg *cfg, PipeLayout &L
         return RHJ_ERR_ARG;
     const u32 W = sp->world, ndig = W << sp->bits_pass1, C = cfg->chunks;
     if (ndig > (u32) kMaxDigits) return RHJ_ERR_ARG;
+    L.wire = cfg->wire_bytes ? cfg->wire_bytes : 16;
+    if (L.wire != 12 && L.wire != 16) return RHJ_ERR_ARG;
     const u64 nmax[2] = {cfg->nR_local_max, cfg->nS_local_max};
     u64 at = 0;
     auto take = [&at](u64 bytes) {
@@ -34,7 +37,7 @@ int pipe_layout(const rhj_shard_plan *sp, const rhj_pipe_cfg *cfg, PipeLayout &L
         L.chunk_rows[rel] = (nmax[rel] + C - 1) / C;
         L.cap1[rel] = pipe_cap1(L.chunk_rows[rel], ndig);
         for (int q = 0; q < 2; ++q) {
-            L.off_recv[rel][q] = take((u64) C * ndig * L.cap1[rel] * sizeof(Tup));
+            L.off_recv[rel][q] = take((u64) C * ndig * L.cap1[rel] * L.wire);
             L.off_end[rel][q] = take((u64) C * ndig * 8);
         }
     }
@@ -50,7 +53,7 @@ inline u64 *pipe_flag(const rhj_ctx *ctx, u32 r, u32 q, int rel, int chunk) {
 inline u64 *pipe_status(const rhj_ctx *ctx, u32 r, u32 q) {
     return (u64 *) ((char *) ctx->pipe.sym[r] + ctx->pipe.off_status) + (u64) q * kMaxPeers;
 }
-inline Tup *pipe_recv(const rhj_ctx *ctx, u32 r, int rel, u32 q) {
+inline Tup *pipe_recv(const rhj_ctx *ctx, u32 r, int rel, u32 q) {  // 16-byte tuples or packed 12-byte records (pipe.wire)
     return (Tup *) ((char *) ctx->pipe.sym[r] + ctx->pipe.off_recv[rel][q]);
 }
 inline u64 *pipe_end(const rhj_ctx *ctx, u32 r, int rel, u32 q) {
@@ -89,8 +92,11 @@ int rhj_pipe_open(rhj_ctx *ctx, const rhj_shard_plan *sp, const rhj_pipe_cfg *cf
     P.world = cfg->world;
     P.rank = cfg->rank;
     P.chunks = cfg->chunks;
-    P.ship_ctas = cfg->ship_ctas ? cfg->ship_ctas : 48;
+    // the plain copy kernel saturates the link with 48 single-thread CTAs; the repacking one is bound by its ring depth
+    // (4 x 8 KiB in flight per CTA) and wants one CTA on almost every SM
+    P.ship_ctas = cfg->ship_ctas ? cfg->ship_ctas : (L.wire == 12 ? 128 : 48);
     if (const char *e = getenv("RHJ_PIPE_SHIP_CTAS")) P.ship_ctas = (u32) std::max(1, atoi(e));
+    P.wire = L.wire;
     P.nmax[0] = cfg->nR_local_max;
     P.nmax[1] = cfg->nS_local_max;
     for (u32 r = 0; r < P.world; ++r) {
@@ -135,6 +141,7 @@ int rhj_pipe_open(rhj_ctx *ctx, const rhj_shard_plan *sp, const rhj_pipe_cfg *cf
     if (const char *e = getenv("RHJ_PIPE_STAGES")) P.stages = (u32) std::max(2, std::min((int) kPipeMaxStages, atoi(e)));
     if ((u64) P.stages * P.stage_bytes > 200 * 1024) return fail(ctx, RHJ_ERR_ARG, "rhj_pipe_open: copy-kernel ring larger than 200 KiB");
     CK(cudaFuncSetAttribute(k_pipe_ship, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (P.stages * P.stage_bytes)));
+    CK(cudaFuncSetAttribute(k_pipe_ship12, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (kPipe12Stages * kPipe12Block * 28)));
     P.epoch = 0;
     P.open = true;
     return RHJ_OK;
@@ -206,7 +213,8 @@ int rhj_pipe_pass1_device(rhj_ctx *ctx, int rel, int chunk, const rhj_tuple *d_r
     // region (chunk, source = rank, p1) of the own receive buffer
     Tup *self = pipe_recv(ctx, P.rank, rel, q) + (((u64) chunk * P.world + P.rank) * nd1) * P.cap1[rel] -
                 ((u64) P.rank << sp->bits_pass1) * P.cap1[rel];
-    for (u32 d = 0; d < P.world; ++d) a.peer_out[0][d] = d == P.rank ? self : stage_c;
+    // (12-byte wire format: the own digits are staged as well and repacked by the copy kernel like everybody else's)
+    for (u32 d = 0; d < P.world; ++d) a.peer_out[0][d] = (d == P.rank && P.wire == 16) ? self : stage_c;
     return launch_scatter(ctx, st, a, kDigitShard, false, true);
 }
 
@@ -244,7 +252,10 @@ int rhj_pipe_ship_device(rhj_ctx *ctx, int rel, int chunk, void *stream) {
     const u32 grid = std::max<u32>(1, std::min<u32>(P.ship_ctas, std::max<u32>(nremote, 1)));
     a.stages = P.stages;
     a.stage_bytes = P.stage_bytes;
-    k_pipe_ship<<<grid, kPipeShipThreads, (size_t) P.stages * P.stage_bytes, st>>>(a);
+    if (P.wire == 12)
+        k_pipe_ship12<<<std::max<u32>(1, std::min<u32>(P.ship_ctas, ndig)), kPipeShip12Threads, (size_t) kPipe12Stages * kPipe12Block * 28, st>>>(a);
+    else
+        k_pipe_ship<<<grid, kPipeShipThreads, (size_t) P.stages * P.stage_bytes, st>>>(a);
     CK(cudaGetLastError());
     ctx->info.kernel_launches++;
     return RHJ_OK;
@@ -288,6 +299,10 @@ int rhj_pipe_pass2_device(rhj_ctx *ctx, int rel, int chunk, void *stream) {
     b.rel[0] = PartRel{pipe_recv(ctx, P.rank, rel, q), (Tup *) sl.out->p, (u64) nseg * P.cap1[rel], sl.hist2, sl.cur2, sg.seg_off,
                        sg.seg_tile0, nseg, tiles_bound, nd1 - 1};
     if (nd1 == 1) b.rel[0].group_mask = 0x80000000u;  // every segment is partition 0
+    if (P.wire == 12) {
+        b.rel[0].in = nullptr;
+        b.rel[0].in_packed = (const unsigned char *) pipe_recv(ctx, P.rank, rel, q);
+    }
     b.rel[0].seg_end = sg.seg_end;
     b.rel[0].limit_cap = P.cap2[rel];
     b.rel[0].dump = (u64) nparts * P.cap2[rel];
@@ -395,7 +410,8 @@ int rhj_pipe_join_device(rhj_ctx *ctx, rhj_pair *d_out, uint64_t capacity, uint6
     CK(cudaStreamSynchronize(st));
     ctx->cur.valid = false;
     u64 bits = ctx->h_scalars[kScPipeStatus] & 0xff;
-    if (ctx->h_scalars[kScOverflow]) bits |= kPipeOvf;
+    if (ctx->h_scalars[kScOverflow] & 1) bits |= kPipeOvf;
+    if (ctx->h_scalars[kScOverflow] & 2) bits |= kPipeWide;
     *status = (uint32_t) bits;
     if (bits) return RHJ_OK;  // the caller redoes the step (or reports the timeout)
     if (ctx->h_scalars[kScErr]) return fail(ctx, RHJ_ERR_STATE, "device-side planning error (work-item table overflow)");

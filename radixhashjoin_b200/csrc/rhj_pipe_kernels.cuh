@@ -33,6 +33,10 @@ constexpr u64 kPipeSpinNs = 4000000000ull;        // a wait gives up after 4 s a
 constexpr u64 kPipeOvf = 1;      // a fixed-capacity region overflowed: redo the step through the exact exchange
 constexpr u64 kPipeTimeout = 2;  // a flag did not arrive in time
 constexpr u64 kPipeBad = 4;      // a received region end was out of range
+constexpr u64 kPipeWide = 8;     // 12-byte wire format: a row id did not fit 32 bits
+constexpr u32 kPipeShip12Threads = 128;   // the repacking copy kernel: 4 tuples (64 B -> 48 B) per thread and block of 512 tuples
+constexpr u32 kPipe12Block = 512;         // tuples per ring stage of the repacking copy kernel (8 KiB in, 6 KiB out)
+constexpr u32 kPipe12Stages = 4;          // 4 x (8 + 6) KiB = 56 KiB of shared memory per CTA
 
 __device__ __forceinline__ void st_release_sys(u64 *p, u64 v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -184,6 +188,129 @@ __global__ void __launch_bounds__(kPipeShipThreads) k_pipe_ship(PipeShipArgs a) 
     }
 }
 
+// The copy kernel of one (relation, chunk) for the 12-BYTE WIRE FORMAT: same job as k_pipe_ship, but every block of 512
+// tuples is repacked on its way through shared memory from 16-byte {row id, value} tuples to 12-byte {value, u32 row id}
+// records (4 tuples = 64 B -> 48 B = three 16-byte words), so a quarter fewer bytes cross NVLink and a quarter fewer land
+// in the destination's HBM.  Thread 0 drives the TMA bulk copies (global -> in-ring, out-ring -> peer global), all 128
+// threads repack.  The rank's own regions take the same route (a local repacking copy), so that a receive buffer holds
+// one format.  A row id that does not fit 32 bits sets kPipeWide.
+__global__ void __launch_bounds__(kPipeShip12Threads) k_pipe_ship12(PipeShipArgs a) {
+    extern __shared__ __align__(128) unsigned char ring[];
+    unsigned char *in_ring = ring;
+    unsigned char *out_ring = ring + (size_t) kPipe12Stages * kPipe12Block * 16;
+    __shared__ __align__(8) u64 s_full[kPipe12Stages];
+    __shared__ u32 s_g[kPipe12Stages], s_n[kPipe12Stages];
+    __shared__ u64 s_off[kPipe12Stages];
+    __shared__ u32 s_last, s_wide;
+    const u32 tid = threadIdx.x;
+    const u32 nd1 = 1u << a.sub_bits;
+    if (tid == 0) {
+        for (u32 s = 0; s < kPipe12Stages; ++s) mbar_init(&s_full[s], 1);
+        s_wide = 0;
+    }
+    __syncthreads();
+    for (u32 g = blockIdx.x * blockDim.x + tid; g < a.ndig; g += gridDim.x * blockDim.x) {
+        const u32 dest = g >> a.sub_bits, p1 = g & (nd1 - 1);
+        u64 cnt = a.cursor[g] - (u64) g * a.cap1;
+        if (cnt > a.cap1) {
+            cnt = a.cap1;
+            *a.overflow = 1;
+        }
+        a.peer_end[dest][a.region0 + p1] = (a.region0 + p1) * a.cap1 + cnt;
+        __threadfence_system();
+    }
+    // thread 0's view of the CTA's block sequence: every gridDim.x-th region (ALL destinations, the own rank included),
+    // consecutive regions going to consecutive destinations starting behind the own rank
+    struct Cur {
+        u32 k;
+        u64 off, cnt;
+        u32 g;
+    };
+    Cur ld{0, 0, 0, 0};
+    auto next_block = [&](u32 &g, u64 &off, u32 &n) -> bool {
+        while (true) {
+            if (ld.off < ld.cnt) {
+                g = ld.g;
+                off = ld.off;
+                n = (u32) min((u64) kPipe12Block, ld.cnt - ld.off);
+                ld.off += n;
+                return true;
+            }
+            const u32 r = blockIdx.x + ld.k * gridDim.x;
+            if (r >= a.ndig) return false;
+            const u32 dest = (a.rank + 1 + r % a.world) % a.world;
+            ld.g = (dest << a.sub_bits) | (r / a.world);
+            ld.cnt = min(a.cursor[ld.g] - (u64) ld.g * a.cap1, a.cap1);
+            ld.k++;
+            ld.off = 0;
+        }
+    };
+    auto issue = [&](u32 s) {  // thread 0: the next block into in-stage s, or the end-of-stream sentinel
+        u32 g, n;
+        u64 off;
+        if (next_block(g, off, n)) {
+            s_g[s] = g;
+            s_n[s] = n;
+            s_off[s] = off;
+            const u32 bytes = ((n + 3) & ~3u) * 16;  // whole groups of 4 tuples; the tail reads a few tuples of slack
+            mbar_expect_tx(&s_full[s], bytes);
+            bulk_g2s(in_ring + (size_t) s * kPipe12Block * 16, a.stage + (u64) g * a.cap1 + off, bytes, &s_full[s]);
+        } else {
+            s_n[s] = 0;
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&s_full[s])) : "memory");
+        }
+    };
+    if (tid == 0)
+        for (u32 s = 0; s < kPipe12Stages; ++s) issue(s);
+    u32 wide = 0;
+    for (u32 j = 0;; ++j) {
+        const u32 s = j % kPipe12Stages;
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPipe12Stages - 1) : "memory");  // out-stage s is free
+        __syncthreads();
+        mbar_wait(&s_full[s], (j / kPipe12Stages) & 1);
+        const u32 n = s_n[s];
+        if (n == 0) break;
+        const u32 g = s_g[s];
+        const u64 off = s_off[s];
+        const uint4 *in = reinterpret_cast<const uint4 *>(in_ring + (size_t) s * kPipe12Block * 16);
+        uint4 *out = reinterpret_cast<uint4 *>(out_ring + (size_t) s * kPipe12Block * 12);
+        const u32 groups = (n + 3) / 4;
+        if (tid < groups) {
+            const uint4 t0 = in[4 * tid], t1 = in[4 * tid + 1], t2 = in[4 * tid + 2], t3 = in[4 * tid + 3];  // {key.lo, key.hi, val.lo, val.hi}
+            const u32 left = n - 4 * tid;
+            if (t0.y | (left > 1 ? t1.y : 0) | (left > 2 ? t2.y : 0) | (left > 3 ? t3.y : 0)) wide = 1;
+            out[3 * tid] = make_uint4(t0.z, t0.w, t0.x, t1.z);
+            out[3 * tid + 1] = make_uint4(t1.w, t1.x, t2.z, t2.w);
+            out[3 * tid + 2] = make_uint4(t2.x, t3.z, t3.w, t3.x);
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            const u32 dest = g >> a.sub_bits, p1 = g & (nd1 - 1);
+            unsigned char *dst = reinterpret_cast<unsigned char *>(a.peer_recv[dest]) + ((a.region0 + p1) * a.cap1 + off) * 12;
+            bulk_s2g(dst, out, groups * 48);
+            bulk_commit();
+            issue(s);  // in-stage s has been consumed
+        }
+    }
+    if (wide) s_wide = 1;
+    if (tid == 0) bulk_wait_all();
+    __syncthreads();
+    if (tid == 0) {
+        if (s_wide) atomicOr(a.overflow, 2u);
+        __threadfence_system();
+        s_last = atomicAdd(a.done, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        const u32 o = *a.overflow;
+        const u64 v = (a.epoch << 8) | (o & 1 ? kPipeOvf : 0) | (o & 2 ? kPipeWide : 0);
+        if (tid < a.world) st_release_sys(a.peer_flag[tid] + a.rank, v);
+        if (tid == 0) *a.done = 0;
+    }
+}
+
 // Destination side of one (relation, chunk): wait for the flags of all sources, then build the segment table
 // of what arrived.  Segment s = source * nd1 + p1 is region (chunk, source, p1) of the receive buffer.
 struct PipeArriveArgs {
@@ -257,7 +384,8 @@ struct PipePostArgs {
 __global__ void k_pipe_post(PipePostArgs a) {
     const u32 tid = threadIdx.x;
     if (tid < a.world) {
-        const u64 bits = (*a.overflow ? kPipeOvf : 0) | (*a.status & 0xff);
+        const u32 o = *a.overflow;
+        const u64 bits = (o & 1 ? kPipeOvf : 0) | (o & 2 ? kPipeWide : 0) | (*a.status & 0xff);
         __threadfence_system();
         st_release_sys(a.peer_status[tid] + a.rank, (a.epoch << 8) | bits);
     }

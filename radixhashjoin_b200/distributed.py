@@ -200,10 +200,10 @@ class PipeShardedJoin:
     the next 16 steps.
     """
 
-    OVERFLOW, TIMEOUT, BAD = 1, 2, 4
+    OVERFLOW, TIMEOUT, BAD, WIDE = 1, 2, 4, 8
 
     def __init__(self, engine, world, rank, nR_global, nS_global, nR_local_max, nS_local_max, chunks=4, group=None,
-                 ship_ctas=0, exact_recv_capacity=None):
+                 ship_ctas=0, exact_recv_capacity=None, wire_bytes=16):
         import torch
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm_mem
@@ -219,13 +219,16 @@ class PipeShardedJoin:
         self._globals = (nR_global, nS_global)
         self._exact_cap = exact_recv_capacity
         dev = torch.device("cuda", engine.device)
-        cfg = engine.pipe_cfg(self.plan, rank, self.chunks, self.nmax[0], self.nmax[1], ship_ctas=ship_ctas)
+        self.wire_bytes = int(wire_bytes)   # 12: the copy kernel repacks to {u64 value, u32 row id}; row ids must fit 32 bits
+        cfg = engine.pipe_cfg(self.plan, rank, self.chunks, self.nmax[0], self.nmax[1], ship_ctas=ship_ctas,
+                              wire_bytes=self.wire_bytes)
         self.sym_bytes = engine.pipe_sym_bytes(self.plan, cfg)
         self.sym = symm_mem.empty((self.sym_bytes // 8,), dtype=torch.int64, device=dev)
         self.sym.zero_()
         self.hdl = symm_mem.rendezvous(self.sym, self.group)
         ptrs = [int(p) for p in self.hdl.buffer_ptrs]
-        engine.pipe_open(self.plan, engine.pipe_cfg(self.plan, rank, self.chunks, self.nmax[0], self.nmax[1], ptrs, ship_ctas))
+        engine.pipe_open(self.plan, engine.pipe_cfg(self.plan, rank, self.chunks, self.nmax[0], self.nmax[1], ptrs, ship_ctas,
+                                                    self.wire_bytes))
         torch.cuda.synchronize(dev)
         dist.barrier(group=self.group)       # every block is zero before anyone ships into it
         self.copy_stream = torch.cuda.Stream(device=dev, priority=-1)   # the copy kernel's CTAs go first when an SM frees up
@@ -292,6 +295,8 @@ class PipeShardedJoin:
         if marks is not None:
             marks.append(("join_done", self._mark()))
         cur.wait_stream(cs)
+        if status & self.WIDE:
+            raise RuntimeError(f"rank {self.rank}: a row id does not fit 32 bits -- construct PipeShardedJoin with wire_bytes=16")
         if status & (self.TIMEOUT | self.BAD):
             raise RuntimeError(f"rank {self.rank}: pipelined exchange failed (status {status}: "
                                f"{'timeout ' if status & self.TIMEOUT else ''}{'bad region end' if status & self.BAD else ''})")

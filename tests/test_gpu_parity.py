@@ -729,7 +729,7 @@ def test_dma_shard_join_split_probe_emulated_ranks(world, nR, nS, dom):
 
 
 # ---- multi-GPU, pipelined exchange (rhj_pipe_*): emulated ranks on one GPU -------------------------------
-def _pipe_emulated_steps(world, n_local, chunks, make_data, steps=3):
+def _pipe_emulated_steps(world, n_local, chunks, make_data, steps=3, wire_bytes=16):
     """Drives rhj_pipe_* for `world` contexts on one GPU.  Plain tensors stand in for the symmetric blocks (every
     context sees every block); the phases run rank after rank, so every device-side wait finds its flag already set
     (kernels that wait on one another must not share a GPU).  Yields (expected sorted pairs, [per-rank (pairs, status)])
@@ -738,11 +738,11 @@ def _pipe_emulated_steps(world, n_local, chunks, make_data, steps=3):
     engines = [RadixHashJoin(0) for _ in range(world)]
     try:
         plan = engines[0].shard_plan(world * n_local, world * n_local, world)
-        nbytes = engines[0].pipe_sym_bytes(plan, engines[0].pipe_cfg(plan, 0, chunks, n_local, n_local))
+        nbytes = engines[0].pipe_sym_bytes(plan, engines[0].pipe_cfg(plan, 0, chunks, n_local, n_local, wire_bytes=wire_bytes))
         syms = [torch.zeros(nbytes // 8, dtype=torch.int64, device=DEV) for _ in range(world)]
         ptrs = [s.data_ptr() for s in syms]
         for r in range(world):
-            engines[r].pipe_open(plan, engines[r].pipe_cfg(plan, r, chunks, n_local, n_local, ptrs))
+            engines[r].pipe_open(plan, engines[r].pipe_cfg(plan, r, chunks, n_local, n_local, ptrs, wire_bytes=wire_bytes))
         rows = (n_local + chunks - 1) // chunks
         for step in range(1, steps + 1):
             Rg, Sg = make_data(step)
@@ -776,15 +776,18 @@ def _pipe_emulated_steps(world, n_local, chunks, make_data, steps=3):
 @pytest.mark.parametrize("world,n_local,dom,chunks", [(1, 50000, 20000, 2), (2, 60000, 1 << 40, 4), (4, 40000, 1 << 40, 3),
                                                       (8, 300000, 1 << 30, 4), (4, 500, 1 << 20, 1), (2, 3001, 1 << 33, 8),
                                                       (8, 70000, 300000, 2)])
-def test_pipe_shard_join_emulated_ranks(world, n_local, dom, chunks):
-    """rhj_pipe_*: histogram-free chunked pass 1 into fixed-capacity regions, the copy kernel, device-side
-    arrival + appended pass 2, join.  Union over ranks == oracle, three steps in a row (both parities)."""
+@pytest.mark.parametrize("wire_bytes", [16, 12])
+def test_pipe_shard_join_emulated_ranks(world, n_local, dom, chunks, wire_bytes):
+    """rhj_pipe_*: histogram-free chunked pass 1 into fixed-capacity regions, the copy kernel (plain, or repacking to
+    12-byte {value, u32 row id} records), device-side arrival + appended pass 2, join.  Union over ranks == oracle,
+    three steps in a row (both parities).  Row ids reach 2^32 - 1 in the 12-byte runs."""
     rng = np.random.default_rng(world * 131 + n_local)
+    base = (1 << 35) if wire_bytes == 16 else (1 << 32) - world * n_local
 
     def make(step):
-        return rand_rel(rng, world * n_local, dom), rand_rel(rng, world * n_local, dom, 1 << 35)
+        return rand_rel(rng, world * n_local, dom), rand_rel(rng, world * n_local, dom, base)
 
-    for expect, res in _pipe_emulated_steps(world, n_local, chunks, make):
+    for expect, res in _pipe_emulated_steps(world, n_local, chunks, make, wire_bytes=wire_bytes):
         assert all(st == 0 for _, st in res), [st for _, st in res]
         got = np.concatenate([p for p, _ in res])
         assert len(got) == len(expect)
@@ -811,3 +814,15 @@ def test_pipe_shard_join_overflow_reaches_every_rank():
             assert all(st == 0 for _, st in res), [st for _, st in res]
             got = np.concatenate([p for p, _ in res])
             assert np.array_equal(O.sort_pairs(got), expect)
+
+
+def test_pipe_shard_join_12_byte_wire_reports_wide_row_ids():
+    """Row ids >= 2^32 cannot travel as 12-byte records: every rank must see RHJ_PIPE_WIDE (8)."""
+    world, n_local = 2, 30000
+    rng = np.random.default_rng(9)
+
+    def make(step):
+        return rand_rel(rng, world * n_local, 1 << 40), rand_rel(rng, world * n_local, 1 << 40, (1 << 32) - 5)
+
+    for expect, res in _pipe_emulated_steps(world, n_local, 2, make, steps=1, wire_bytes=12):
+        assert all(st & 8 for _, st in res), [st for _, st in res]
