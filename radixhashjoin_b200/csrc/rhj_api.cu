@@ -94,8 +94,14 @@ int launch_scatter(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, b
     if (limit && kind == kDigitShard) {  // pipelined exchange, pass 1: (rank | sub-digit) regions of fixed capacity, per-digit output base
         if (seg || a.shard_local) return fail(ctx, RHJ_ERR_STATE, "bounds-checked shard scatter: unsegmented, peer_out bases");
         if (a.ndig > 512) {
-            CK(set_smem(k_scatter<kDigitShard, false, kWriteStaged, kMaxDigits, true>, kScatterSmem));
-            k_scatter<kDigitShard, false, kWriteStaged, kMaxDigits, true><<<grid, kPartThreads, kScatterSmem, st>>>(a);
+            // 1024 digits: 1024 threads on 8192-tuple tiles, one CTA per SM (see k_scatter); one relation per launch
+            if (a.rel[1].ntiles) return fail(ctx, RHJ_ERR_STATE, "bounds-checked 1024-digit shard scatter: one relation per launch");
+            constexpr int kBigThreads = 1024, kBigTile = kBigThreads * kPartItems;
+            PartArgs b = a;
+            b.rel[0].ntiles = (u32) ((a.rel[0].n + kBigTile - 1) / kBigTile);
+            auto kern = k_scatter<kDigitShard, false, kWriteStaged, kMaxDigits, true, kIoAos, kBigThreads>;
+            CK(set_smem(kern, (size_t) kBigTile * sizeof(Tup)));
+            kern<<<b.rel[0].ntiles, kBigThreads, (size_t) kBigTile * sizeof(Tup), st>>>(b);
         } else {
             CK(set_smem(k_scatter<kDigitShard, false, kWriteStaged, 512, true>, kScatterSmem));
             k_scatter<kDigitShard, false, kWriteStaged, 512, true><<<grid, kPartThreads, kScatterSmem, st>>>(a);

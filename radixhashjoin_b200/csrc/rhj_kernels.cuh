@@ -278,13 +278,16 @@ __global__ void __launch_bounds__(kMaxDigits) k_scan_digits(ScanDigitsArgs a) {
 //   or, with BULK, by one TMA bulk store (cp.async.bulk shared->global) per run.
 // Algorithmic bytes: 16 read + 16 written per tuple.
 enum ScatterWrite { kWriteStaged = 0, kWriteBulk = 1 };
-template <int KIND, bool SEG, int WMODE, int MAXD, bool LIMIT = false, int IO = kIoAos>
+// THREADS: 512 (4096-tuple tiles, two CTAs per SM) everywhere except the 1024-digit pass 1 of the pipelined exchange, which
+// runs 1024 threads on 8192-tuple tiles (one CTA per SM): at 4 tuples per digit and tile the runs are 64 bytes and every
+// fourth tuple costs a global reservation; the larger tile doubles the runs and halves the reservations.
+template <int KIND, bool SEG, int WMODE, int MAXD, bool LIMIT = false, int IO = kIoAos, int THREADS = kPartThreads>
 #if RHJ_SCATTER_MAXNREG
 // 56 registers (0-48 bytes of spills) instead of the 62-64 two 512-thread CTAs per SM would allow: leaves room in the
 // register file for a CTA of the multi-GPU copy kernel next to two scatter CTAs (rhj_pipe_kernels.cuh)
 __global__ void __maxnreg__(RHJ_SCATTER_MAXNREG) k_scatter(PartArgs a) {
 #else
-__global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(PartArgs a) {
+__global__ void __launch_bounds__(THREADS, THREADS == kPartThreads ? RHJ_PART_MINBLOCKS : 1) k_scatter(PartArgs a) {
 #endif
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     Tup *s_tup = reinterpret_cast<Tup *>(dyn_smem);
@@ -298,12 +301,19 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
     const PartRel &r = a.rel[ri];
     u32 seg;
     u64 beg, end;
-    if (!tile_range<SEG>(r, blockIdx.x - (ri ? a.rel[0].ntiles : 0), seg, beg, end)) return;
+    if (SEG || THREADS == kPartThreads) {
+        if (!tile_range<SEG>(r, blockIdx.x - (ri ? a.rel[0].ntiles : 0), seg, beg, end)) return;
+    } else {  // unsegmented pass on THREADS * kPartItems-tuple tiles (PartRel::ntiles counts those)
+        seg = 0;
+        beg = (u64) (blockIdx.x - (ri ? a.rel[0].ntiles : 0)) * (THREADS * kPartItems);
+        end = min(beg + (u64) (THREADS * kPartItems), r.n);
+        if (beg >= r.n) return;
+    }
     const u32 ntile = (u32) (end - beg);
 
-    for (u32 d = tid; d < a.ndig; d += kPartThreads) s_cnt[d] = 0;
+    for (u32 d = tid; d < a.ndig; d += THREADS) s_cnt[d] = 0;
     Tup v[kPartItems];
-    u32 dr[kPartItems];  // digit << 16 | rank   (digit < 1024, rank < 4096)
+    u32 dr[kPartItems];  // digit << 16 | rank   (digit < 1024, rank < 8192)
     if (IO == kIoPacked12In) {
         // one TMA bulk copy brings the tile's 12-byte records into the staging area (which the sorted tile reuses later);
         // every thread then unpacks its 8 records with conflict-free 4-byte shared-memory loads (stride 3 words)
@@ -319,7 +329,7 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
         const u32 *w = reinterpret_cast<const u32 *>(dyn_smem);
 #pragma unroll
         for (int j = 0; j < kPartItems; ++j) {
-            u32 i = j * kPartThreads + tid;
+            u32 i = j * THREADS + tid;
             if (i < ntile) {
                 v[j].val = (u64) w[3 * i] | ((u64) w[3 * i + 1] << 32);
                 v[j].key = w[3 * i + 2];
@@ -328,14 +338,14 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
     } else {
 #pragma unroll
         for (int j = 0; j < kPartItems; ++j) {
-            u32 i = j * kPartThreads + tid;
+            u32 i = j * THREADS + tid;
             if (i < ntile) v[j] = ld_tuple<IO>(r, beg + i);
         }
     }
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < kPartItems; ++j) {
-        u32 i = j * kPartThreads + tid;
+        u32 i = j * THREADS + tid;
         if (i < ntile) {
             u32 d = digit<KIND>(v[j].val, a);
             u32 rk = atomicAdd(&s_cnt[d], 1u);
@@ -345,7 +355,7 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
     __syncthreads();
     // reserve the runs (global atomics issued first so their latency overlaps the block scan);
     // thread t owns the kDigitsPerThread consecutive digits starting at t * kDigitsPerThread
-    constexpr int kDigitsPerThread = (MAXD + kPartThreads - 1) / kPartThreads;
+    constexpr int kDigitsPerThread = (MAXD + THREADS - 1) / THREADS;
     u32 c[kDigitsPerThread];
     u64 g[kDigitsPerThread];
     u32 csum = 0;
@@ -361,7 +371,7 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
     if (lane == 31) s_w[warp] = inc;
     __syncthreads();
     if (warp == 0) {
-        u32 w = lane < (kPartThreads / 32) ? s_w[lane] : 0;
+        u32 w = lane < (THREADS / 32) ? s_w[lane] : 0;
         u32 wi = warp_incl_scan(w);
         s_w[lane] = wi - w;
     }
@@ -393,13 +403,13 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
     {
 #pragma unroll
     for (int j = 0; j < kPartItems; ++j) {
-        u32 i = j * kPartThreads + tid;
+        u32 i = j * THREADS + tid;
         if (i < ntile) s_tup[s_off[dr[j] >> 16] + (dr[j] & 0xffffu)] = v[j];
     }
     if (WMODE == kWriteBulk) {
         fence_async_smem();
         __syncthreads();
-        for (u32 d = tid; d < a.ndig; d += kPartThreads) {
+        for (u32 d = tid; d < a.ndig; d += THREADS) {
             u32 cd = s_cnt[d];
             Tup *ob = (KIND == kDigitShard && !a.shard_local) ? a.peer_out[ri][0] : r.out;
             if (cd) bulk_s2g(ob + s_delta[d] + s_off[d], s_tup + s_off[d], cd * (u32) sizeof(Tup));
@@ -410,7 +420,7 @@ __global__ void __launch_bounds__(kPartThreads, RHJ_PART_MINBLOCKS) k_scatter(Pa
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < kPartItems; ++j) {
-            u32 i = j * kPartThreads + tid;
+            u32 i = j * THREADS + tid;
             if (i < ntile) {
                 Tup t = s_tup[i];
                 u32 d = digit<KIND>(t.val, a);
