@@ -168,6 +168,46 @@ int rhj_intermediate_filter_host(rhj_ctx *ctx, const uint64_t *col1, const uint6
                                  const rhj_pair *pairs, uint64_t n_pairs, const uint64_t *const *cols, uint32_t n_cols,
                                  uint64_t **out_cols, uint64_t *out_rows);
 
+/* ---- the query path around the join, device resident ------------------------------ */
+
+/* relList columns (structs.cpp:18-60: read-only host arrays for the life of the process) are uploaded ONCE: the first
+ * call with a host column copies it to the device, every later call -- from any context of the process -- returns the
+ * same device copy.  *uploaded_bytes (optional) = bytes this call moved over PCIe (0 on a hit). */
+int rhj_column_device(rhj_ctx *ctx, const uint64_t *host_col, uint64_t n, const uint64_t **d_col, uint64_t *uploaded_bytes);
+int rhj_column_cache_clear(void);
+
+/* create_relation's row-id de-duplication (structs.cpp:238-241): d_out[0..*count) = the distinct values of d_rowids[n],
+ * ascending (the reference's unordered_set order is unspecified).  Row ids must be < n_rows, the relation's row count;
+ * d_out needs room for min(n, n_rows) values. */
+int rhj_unique_rowids_device(rhj_ctx *ctx, const uint64_t *d_rowids, uint64_t n, uint64_t n_rows, uint64_t *d_out,
+                             uint64_t *count, void *stream);
+
+/* Query::execute (Query.h:50, Query.cpp:204-211: run_filters -> run_joins -> column_proj) with row-id lists, relations,
+ * join results and the intermediate resident in HBM from the first filter to the last checksum.  A binding refers to a
+ * relList (its columns are HOST pointers, uploaded once through rhj_column_device); filters / joins / projections are
+ * the reference's filter_info / join_info / proj_info (Query.h:8-33) with `table` = binding index.
+ * sums[n_projs] = the projection checksums (Query.cpp:66-74); *empty = 1 when a filter or join left no row (the reference
+ * prints NULL for every projection, Query.cpp:226-235).  Rows of the intermediate come out in a different order than the
+ * reference's; the multiset is the same and only sums observe it. */
+#define RHJ_MAX_BINDINGS 16
+typedef struct rhj_q_relation { const uint64_t *const *columns; uint64_t num_tuples, num_columns; } rhj_q_relation;
+typedef struct rhj_q_filter { uint32_t binding, column; int32_t op; uint32_t reserved0; uint64_t constant; } rhj_q_filter;
+typedef struct rhj_q_join { uint32_t binding1, column1, binding2, column2; } rhj_q_join;
+typedef struct rhj_q_proj { uint32_t binding, column; } rhj_q_proj;
+typedef struct rhj_query_desc {
+    uint32_t n_bindings, n_filters, n_joins, n_projs;
+    const rhj_q_relation *bindings;
+    const rhj_q_filter *filters;
+    const rhj_q_join *joins;
+    const rhj_q_proj *projs;
+} rhj_query_desc;
+typedef struct rhj_query_stats {
+    uint64_t h2d_bytes;           /* column uploads of this query (0 once the columns are resident)          */
+    uint64_t d2h_bytes;           /* counts + checksums read back                                           */
+    uint64_t kernel_launches, joins, join_input_tuples, join_output_pairs, result_rows;
+} rhj_query_stats;
+int rhj_query_execute(rhj_ctx *ctx, const rhj_query_desc *query, uint64_t *sums, int *empty, rhj_query_stats *stats);
+
 /* ---- multi-GPU (no reference equivalent) --------------------------------------- */
 
 /* Groups d_in[n] by destination rank = top log2(world) bits of the join hash (world a power of

@@ -36,6 +36,37 @@ class PipeCfg(ctypes.Structure):
                 ("sym", ctypes.c_void_p * 16)]
 
 
+class QRelation(ctypes.Structure):
+    _fields_ = [("columns", ctypes.POINTER(ctypes.c_void_p)), ("num_tuples", ctypes.c_uint64), ("num_columns", ctypes.c_uint64)]
+
+
+class QFilter(ctypes.Structure):
+    _fields_ = [("binding", ctypes.c_uint32), ("column", ctypes.c_uint32), ("op", ctypes.c_int32), ("reserved0", ctypes.c_uint32),
+                ("constant", ctypes.c_uint64)]
+
+
+class QJoin(ctypes.Structure):
+    _fields_ = [("binding1", ctypes.c_uint32), ("column1", ctypes.c_uint32), ("binding2", ctypes.c_uint32),
+                ("column2", ctypes.c_uint32)]
+
+
+class QProj(ctypes.Structure):
+    _fields_ = [("binding", ctypes.c_uint32), ("column", ctypes.c_uint32)]
+
+
+class QueryDesc(ctypes.Structure):
+    """struct rhj_query_desc (include/rhj.h)."""
+    _fields_ = [("n_bindings", ctypes.c_uint32), ("n_filters", ctypes.c_uint32), ("n_joins", ctypes.c_uint32),
+                ("n_projs", ctypes.c_uint32), ("bindings", ctypes.POINTER(QRelation)), ("filters", ctypes.POINTER(QFilter)),
+                ("joins", ctypes.POINTER(QJoin)), ("projs", ctypes.POINTER(QProj))]
+
+
+class QueryStats(ctypes.Structure):
+    """struct rhj_query_stats (include/rhj.h)."""
+    _fields_ = [(n, ctypes.c_uint64) for n in ("h2d_bytes", "d2h_bytes", "kernel_launches", "joins", "join_input_tuples",
+                                               "join_output_pairs", "result_rows")]
+
+
 # name -> (restype, argtypes): every symbol include/rhj.h declares
 SIGNATURES = {
     "rhj_version": (ctypes.c_char_p, []),
@@ -59,6 +90,11 @@ SIGNATURES = {
                                                     c_vp, c_u64p]),
     "rhj_intermediate_filter_host": (ctypes.c_int, [c_vp, c_vp, c_vp, c_u64, c_vp, c_u64, c_vp, ctypes.c_uint32, c_vp,
                                                     c_u64p]),
+    "rhj_column_device": (ctypes.c_int, [c_vp, c_vp, c_u64, ctypes.POINTER(c_vp), c_u64p]),
+    "rhj_column_cache_clear": (ctypes.c_int, []),
+    "rhj_unique_rowids_device": (ctypes.c_int, [c_vp, c_vp, c_u64, c_u64, c_vp, c_u64p, c_vp]),
+    "rhj_query_execute": (ctypes.c_int, [c_vp, ctypes.POINTER(QueryDesc), c_u64p, ctypes.POINTER(ctypes.c_int),
+                                          ctypes.POINTER(QueryStats)]),
     "rhj_shuffle_partition_device": (ctypes.c_int, [c_vp, c_vp, c_u64, ctypes.c_int, c_vp, c_u64p, c_vp]),
     "rhj_shard_plan_make": (ctypes.c_int, [c_u64, c_u64, ctypes.c_int, ctypes.POINTER(ShardPlan)]),
     "rhj_shard_histogram_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), c_vp, c_u64, c_vp, c_u64, c_vp, c_vp]),

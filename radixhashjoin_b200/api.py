@@ -382,6 +382,50 @@ class RadixHashJoin:
                                                      ctypes.byref(s), self._stream(stream)))
         return int(s.value)
 
+    def unique_rowids(self, rowids, n_rows, stream=None):
+        """create_relation's de-duplication (structs.cpp:238-241): the distinct row ids of a device column, ascending."""
+        torch = _torch()
+        n = rowids.numel()
+        out = torch.empty(max(min(n, n_rows), 1), dtype=torch.int64, device=rowids.device)
+        cnt = ctypes.c_uint64()
+        self._ck(self._lib.rhj_unique_rowids_device(self._ctx, _ptr(rowids), n, n_rows, _ptr(out), ctypes.byref(cnt),
+                                                    self._stream(stream)))
+        return out[:cnt.value]
+
+    def query_execute(self, tables, filters, joins, projs, relations):
+        """Query::execute (Query.cpp:204-211) on the device.  `relations` = list of relLists (each a list of contiguous
+        numpy u64 host columns, which must stay alive: they are uploaded once and cached by address); `tables` = the
+        relList index of every binding; filters (binding, column, op, constant), joins (b1, c1, b2, c2), projs (binding,
+        column) as in Query.h:8-33.  Returns (sums or None when the result is empty, stats dict)."""
+        keep = []
+        binds = (_lib.QRelation * len(tables))()
+        for i, t in enumerate(tables):
+            cols = relations[t]
+            arr = (ctypes.c_void_p * len(cols))(*[c.ctypes.data for c in cols])
+            keep.append(arr)
+            binds[i].columns = ctypes.cast(arr, ctypes.POINTER(ctypes.c_void_p))
+            binds[i].num_tuples = len(cols[0])
+            binds[i].num_columns = len(cols)
+        fl = (_lib.QFilter * max(len(filters), 1))()
+        for i, (b, c, op, k) in enumerate(filters):
+            fl[i].binding, fl[i].column, fl[i].op, fl[i].constant = b, c, ord(op) if isinstance(op, str) else op, int(k)
+        jn = (_lib.QJoin * max(len(joins), 1))()
+        for i, (b1, c1, b2, c2) in enumerate(joins):
+            jn[i].binding1, jn[i].column1, jn[i].binding2, jn[i].column2 = b1, c1, b2, c2
+        pj = (_lib.QProj * max(len(projs), 1))()
+        for i, (b, c) in enumerate(projs):
+            pj[i].binding, pj[i].column = b, c
+        d = _lib.QueryDesc(len(tables), len(filters), len(joins), len(projs), binds, fl, jn, pj)
+        sums = (ctypes.c_uint64 * max(len(projs), 1))()
+        empty = ctypes.c_int()
+        st = _lib.QueryStats()
+        self._ck(self._lib.rhj_query_execute(self._ctx, ctypes.byref(d), sums, ctypes.byref(empty), ctypes.byref(st)))
+        stats = {f: int(getattr(st, f)) for f, _ in _lib.QueryStats._fields_}
+        return (None if empty.value else [int(sums[i]) for i in range(len(projs))]), stats
+
+    def column_cache_clear(self):
+        self._lib.rhj_column_cache_clear()
+
     def intermediate_expand_host(self, match_col, pairs, match_on_S, cols):
         """update_intermediate case 2 (intermediate.cpp:108-125,162-170) as join + gather on the GPU.
         match_col / cols: numpy u64 host columns of the old intermediate; pairs: PAIR_DTYPE join result.

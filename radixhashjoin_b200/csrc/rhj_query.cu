@@ -266,3 +266,5 @@ int rhj_intermediate_filter_host(rhj_ctx *ctx, const uint64_t *col1, const uint6
 }
 
 }  // extern "C"
+
+#include "rhj_exec.cuh"

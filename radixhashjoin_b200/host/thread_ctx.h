@@ -21,7 +21,7 @@ namespace rhj_host {
 struct Timing {
     std::atomic<long long> ns[4];
     std::atomic<long long> calls[4];
-    const char *names[4] = {"multiRadixHashJoin", "update_intermediate/unzip", "update_intermediate/expand",
+    const char *names[4] = {"multiRadixHashJoin | Query::execute", "update_intermediate/unzip", "update_intermediate/expand",
                             "update_intermediate/filter"};
     std::chrono::steady_clock::time_point start = std::chrono::steady_clock::now();
     std::atomic<long long> first_ns, last_ns, ctx_ns;
@@ -59,6 +59,29 @@ struct Scope {
         timing().calls[slot]++;
     }
 };
+
+// PCIe accounting of the device-resident query path (Query_execute.cpp): RHJ_HOST_TIMING=1 prints the totals at exit.
+struct Pcie {
+    std::atomic<unsigned long long> h2d, d2h, queries, launches, joins;
+    Pcie() : h2d(0), d2h(0), queries(0), launches(0), joins(0) {}
+    void add(const rhj_query_stats &s) {
+        h2d += s.h2d_bytes;
+        d2h += s.d2h_bytes;
+        queries++;
+        launches += s.kernel_launches;
+        joins += s.joins;
+    }
+    ~Pcie() {
+        if (!getenv("RHJ_HOST_TIMING") || !queries.load()) return;
+        fprintf(stderr, "[rhj host timing] %llu queries on the device: %llu joins, %llu kernel launches, H2D %llu bytes (columns, once), "
+                        "D2H %llu bytes (%.0f per query)\n", queries.load(), joins.load(), launches.load(), h2d.load(), d2h.load(),
+                (double) d2h.load() / (double) queries.load());
+    }
+};
+inline Pcie &pcie() {
+    static Pcie p;
+    return p;
+}
 
 struct ThreadCtx {
     rhj_ctx *ctx = nullptr;

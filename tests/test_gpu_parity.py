@@ -826,3 +826,95 @@ def test_pipe_shard_join_12_byte_wire_reports_wide_row_ids():
 
     for expect, res in _pipe_emulated_steps(world, n_local, 2, make, steps=1, wire_bytes=12):
         assert all(st & 8 for _, st in res), [st for _, st in res]
+
+
+# ---- the device-resident query path (rhj_query_execute) -------------------------------
+@pytest.mark.parametrize("n,n_rows", [(0, 10), (1, 1), (5000, 64), (100000, 100000), (300000, 70001), (10, 1 << 22)])
+def test_unique_rowids_equals_numpy_unique(engine, n, n_rows):
+    """create_relation's de-duplication (structs.cpp:238-241) as a bitmap kernel: == np.unique (ascending)."""
+    rng = np.random.default_rng(n + n_rows)
+    ids = rng.integers(0, n_rows, n, dtype=np.uint64)
+    got = engine.unique_rowids(torch.from_numpy(ids.view(np.int64)).to(DEV), n_rows).cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, np.unique(ids))
+
+
+def test_unique_rowids_rejects_out_of_range_ids(engine):
+    ids = torch.tensor([1, 2, 99], dtype=torch.int64, device=DEV)
+    with pytest.raises(RhjError):
+        engine.unique_rowids(ids, 50)
+
+
+def _device_query_lines(engine, queries, rels):
+    lines, stats = [], []
+    for q in queries:
+        filters = [(b, c, op, k) for (b, c, op, k) in q.filter]
+        sums, st = engine.query_execute(q.table, filters, q.join, q.proj, rels)
+        lines.append(" ".join("NULL" for _ in q.proj) if sums is None else " ".join(str(s) for s in sums))
+        stats.append(st)
+    return lines, stats
+
+
+def test_small_workload_through_device_query_path(engine, small_dir):
+    """small.work through rhj_query_execute -- filters, create_relation, 94 joins, update_intermediate and the checksums
+    all on the device: the 50 lines of small/small.result; the second pass moves no column over PCIe any more."""
+    rels = Q.load_workload(small_dir)
+    rels = [[np.ascontiguousarray(c) for c in r] for r in rels]
+    queries = Q.parse_work(os.path.join(small_dir, "small.work"))
+    expected = open(os.path.join(small_dir, "small.result")).read().split("\n")
+    engine.column_cache_clear()
+    lines, stats = _device_query_lines(engine, queries, rels)
+    assert lines == expected[:50]
+    assert sum(s["joins"] for s in stats) > 0 and sum(s["h2d_bytes"] for s in stats) > 0
+    lines, stats = _device_query_lines(engine, queries, rels)
+    assert lines == expected[:50]
+    assert sum(s["h2d_bytes"] for s in stats) == 0          # columns are resident
+    assert max(s["d2h_bytes"] for s in stats) < 4096        # counts + checksums only
+    engine.column_cache_clear()
+
+
+def test_edge_workload_through_device_query_path(engine, edge_dir):
+    """edge.work (same binding twice, a same-binding predicate, empty joins, out-of-range filter, values >= 2^32, a query
+    without joins, a third join over a 288000-row intermediate) through rhj_query_execute: the 13 lines the unmodified
+    reference printed."""
+    rels = Q.load_workload(edge_dir, "edge.init")
+    rels = [[np.ascontiguousarray(c) for c in r] for r in rels]
+    queries = Q.parse_work(os.path.join(edge_dir, "edge.work"))
+    expected = open(os.path.join(edge_dir, "edge.result")).read().split("\n")
+    engine.column_cache_clear()
+    lines, _ = _device_query_lines(engine, queries, rels)
+    assert lines == expected[:13]
+    engine.column_cache_clear()
+
+
+def test_device_query_path_random_queries_equal_query_oracle(engine):
+    """random relations and random 1-3 join queries (chains, stars, a join between two already joined bindings, duplicate
+    heavy columns): rhj_query_execute == the numpy query oracle line by line."""
+    rng = np.random.default_rng(77)
+    rels = []
+    for n, cols, dom in [(3000, 3, 50), (5000, 4, 400), (800, 2, 30), (12000, 3, 2000)]:
+        rels.append([np.ascontiguousarray(rng.integers(0, dom, n, dtype=np.uint64)) for _ in range(cols)])
+    work = ["0 1|0.0=1.1&0.1>10|0.2 1.0", "0 1 2|0.0=1.0&1.1=2.0&0.1<40|0.0 1.2 2.1", "1 3|0.2=1.1&1.0>5|0.0 1.2",
+            "0 1 2|0.0=1.0&1.1=2.0&0.1=2.1|0.2 2.0", "0 2 1 3|0.0=1.0&1.1=2.0&1.2=3.0&3.1<1000|3.2 0.1",
+            "2 2|0.0=1.1&0.1>3|0.0 1.0", "0 1|0.0=1.0&1.1=0.1&0.2>25|1.3 0.0", "3|0.0>100|0.1", "0 1|0.0=1.3&0.0>48&1.3<1|0.1"]
+    engine.column_cache_clear()
+    for line in work:
+        q = Q.Query(line)
+        want = Q.execute(q, rels, lambda R, S: O.oracle_join(R, S))
+        got, _ = _device_query_lines(engine, [q], rels)
+        assert got[0] == want, line
+    engine.column_cache_clear()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(HOST_BIN, "join_b200_query")),
+                    reason="drop-in binaries are built in the dev container (need the reference sources)")
+@pytest.mark.parametrize("which", ["small", "edge"])
+def test_reference_program_with_device_query_path(which, small_dir, edge_dir):
+    """The reference PROGRAM (join.cpp, parser, schedulers, printing unmodified) with Query::execute replaced by
+    host/Query_execute.cpp -> rhj_query_execute: output identical to the unmodified reference's."""
+    import subprocess
+    d = small_dir if which == "small" else edge_dir
+    data = open(os.path.join(d, which + ".init"), "rb").read() + open(os.path.join(d, which + ".work"), "rb").read()
+    out = subprocess.run([os.path.join(HOST_BIN, "join_b200_query")], input=data, cwd=os.path.dirname(d), capture_output=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stderr.decode()[-2000:]
+    assert out.stdout.decode() == open(os.path.join(d, which + ".result")).read()
