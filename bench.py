@@ -149,44 +149,72 @@ def cpu_reference_run(log2n, steps, warmup, budget_s=None):
 
 
 def small_work_wall(with_reference=False):
-    """BASELINE.json config 1 / metric part 2: wall time of `cat small.init small.work | ./join` for the
-    reference PROGRAM linked with our drop-in Result.cpp + intermediate.cpp + librhj.so
-    (radixhashjoin_b200/host/_build/join_b200_full, built in the dev container), output diffed
-    against small.result.  With --small-work-ref the unmodified reference program (oracle/_ref/join_ref)
-    is timed the same way (takes minutes)."""
+    """BASELINE.json config 1 / metric part 2: wall time of `cat small.init small.work | ./join` for the reference PROGRAM
+    with the CUDA path dropped in (binaries built in the dev container by radixhashjoin_b200/host/Makefile), output
+    diffed against small.result:
+      join_b200_query  Query::execute -> rhj_query_execute: the whole query path device resident (the product);
+      join_b200_full   Result.cpp + intermediate.cpp replaced, filters / relations / intermediates on the host (round 1).
+    A process pays ~1.5-2.5 s of CUDA context creation before its first query; the steady-state figure is the extra wall
+    time of running the workload three times instead of once inside ONE process, halved.  With --small-work-ref the
+    unmodified reference program (oracle/_ref/join_ref) is timed the same way (takes minutes)."""
+    import re
     import subprocess
     import tarfile
     import tempfile
-    host_bin = os.path.join(ROOT, "radixhashjoin_b200", "host", "_build", "join_b200_full")
-    if not os.path.exists(host_bin):
-        return {"unavailable": "radixhashjoin_b200/host/_build/join_b200_full not built (needs the reference sources)"}
+    host = os.path.join(ROOT, "radixhashjoin_b200", "host", "_build")
+    if not os.path.exists(os.path.join(host, "join_b200_query")):
+        return {"unavailable": "radixhashjoin_b200/host/_build/join_b200_query not built (needs the reference sources)"}
     golden = os.path.join(ROOT, "tests", "golden")
     with tempfile.TemporaryDirectory() as d:
         os.mkdir(os.path.join(d, "small"))
         with tarfile.open(os.path.join(golden, "small_relations.tar.xz")) as tf:
             tf.extractall(os.path.join(d, "small"))
-        data = open(os.path.join(golden, "small.init"), "rb").read() + open(os.path.join(golden, "small.work"), "rb").read()
+        init = open(os.path.join(golden, "small.init"), "rb").read()
+        work = open(os.path.join(golden, "small.work"), "rb").read()
         expect = open(os.path.join(golden, "small.result"), "rb").read()
 
-        def run(binary, reps):
-            walls, same = [], True
+        def run(binary, reps, times=1):
+            walls, same, err = [], True, b""
             for _ in range(reps):
                 t0 = time.perf_counter()
-                out = subprocess.run([binary], input=data, cwd=d, capture_output=True, timeout=1800)
+                out = subprocess.run([binary], input=init + work * times, cwd=d, capture_output=True, timeout=1800,
+                                     env=dict(os.environ, RHJ_HOST_TIMING="1"))
                 walls.append(time.perf_counter() - t0)
-                same = same and out.returncode == 0 and out.stdout == expect
-            return walls, same
+                same = same and out.returncode == 0 and out.stdout == expect * times
+                err = out.stderr
+            return walls, same, err.decode(errors="replace")
 
-        walls, same = run(host_bin, 3)
-        res = {"program": "reference join.cpp/Query.cpp/... + host/Result.cpp + host/intermediate.cpp + librhj.so",
-               "wall_s": min(walls), "wall_s_all": [round(w, 3) for w in walls], "output_identical_to_small_result": same,
-               "query_threads": 8}
+        res = {"query_threads": 8}
+        for name, what in (("join_b200_query", "reference join.cpp / parser / schedulers / printing + host/Query_execute.cpp -> "
+                                               "rhj_query_execute (device-resident query path) + librhj.so"),
+                           ("join_b200_full", "reference program + host/Result.cpp + host/intermediate.cpp + librhj.so")):
+            b = os.path.join(host, name)
+            if not os.path.exists(b):
+                continue
+            w1, s1, err = run(b, 3)
+            w3, s3, _ = run(b, 2, times=3)
+            r = {"program": what, "wall_s": min(w1), "wall_s_all": [round(w, 3) for w in w1], "output_identical_to_small_result": s1 and s3,
+                 "wall_s_three_passes": min(w3), "steady_state_s_per_pass": max(0.0, (min(w3) - min(w1)) / 2)}
+            m = re.search(r"(\d+) queries on the device: (\d+) joins, (\d+) kernel launches, H2D (\d+) bytes .* D2H (\d+) bytes", err)
+            if m:
+                r["pcie"] = {"queries": int(m.group(1)), "joins": int(m.group(2)), "kernel_launches": int(m.group(3)),
+                             "h2d_bytes_total_columns_once": int(m.group(4)), "d2h_bytes_total": int(m.group(5)),
+                             "d2h_bytes_per_query": round(int(m.group(5)) / max(int(m.group(1)), 1), 1)}
+            m = re.search(r"context creation thread-time ([0-9.]+) ms", err)
+            if m:
+                r["cuda_context_creation_thread_ms"] = float(m.group(1))
+            res[name] = r
+        res["wall_s"] = res["join_b200_query"]["wall_s"]
+        res["output_identical_to_small_result"] = all(v["output_identical_to_small_result"] for v in res.values() if isinstance(v, dict))
         ref_bin = os.path.join(ROOT, "oracle", "_ref", "join_ref")
         if with_reference and os.path.exists(ref_bin):
-            rw, rsame = run(ref_bin, 1)
+            rw, rsame, _ = run(ref_bin, 1)
             res["reference_wall_s"] = rw[0]
             res["reference_output_identical"] = rsame
             res["reference_build"] = "unmodified reference, g++ -Ofast -march=x86-64-v3 -funroll-loops -pthread"
+        else:
+            res["reference_wall_s_builder_measured"] = {"value": 94.0, "source": "profiles/r01_call9_small_work_wall.txt (same build, "
+                                                        "8 threads, GPU box host); re-time with --small-work-ref"}
         return res
 
 

@@ -196,6 +196,9 @@ typedef struct rhj_q_join { uint32_t binding1, column1, binding2, column2; } rhj
 typedef struct rhj_q_proj { uint32_t binding, column; } rhj_q_proj;
 typedef struct rhj_query_desc {
     uint32_t n_bindings, n_filters, n_joins, n_projs;
+    uint32_t reorder_joins;       /* 0: run the joins as written, like the reference (README.md:63-64); 1: cheapest-first over
+                                     the join graph using the filtered row counts (same result rows, same checksums) */
+    uint32_t reserved0;
     const rhj_q_relation *bindings;
     const rhj_q_filter *filters;
     const rhj_q_join *joins;
@@ -205,6 +208,7 @@ typedef struct rhj_query_stats {
     uint64_t h2d_bytes;           /* column uploads of this query (0 once the columns are resident)          */
     uint64_t d2h_bytes;           /* counts + checksums read back                                           */
     uint64_t kernel_launches, joins, join_input_tuples, join_output_pairs, result_rows;
+    uint64_t joins_reordered;     /* 1 when reorder_joins changed the order                                  */
 } rhj_query_stats;
 int rhj_query_execute(rhj_ctx *ctx, const rhj_query_desc *query, uint64_t *sums, int *empty, rhj_query_stats *stats);
 

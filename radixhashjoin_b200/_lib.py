@@ -57,14 +57,15 @@ class QProj(ctypes.Structure):
 class QueryDesc(ctypes.Structure):
     """struct rhj_query_desc (include/rhj.h)."""
     _fields_ = [("n_bindings", ctypes.c_uint32), ("n_filters", ctypes.c_uint32), ("n_joins", ctypes.c_uint32),
-                ("n_projs", ctypes.c_uint32), ("bindings", ctypes.POINTER(QRelation)), ("filters", ctypes.POINTER(QFilter)),
+                ("n_projs", ctypes.c_uint32), ("reorder_joins", ctypes.c_uint32), ("reserved0", ctypes.c_uint32),
+                ("bindings", ctypes.POINTER(QRelation)), ("filters", ctypes.POINTER(QFilter)),
                 ("joins", ctypes.POINTER(QJoin)), ("projs", ctypes.POINTER(QProj))]
 
 
 class QueryStats(ctypes.Structure):
     """struct rhj_query_stats (include/rhj.h)."""
     _fields_ = [(n, ctypes.c_uint64) for n in ("h2d_bytes", "d2h_bytes", "kernel_launches", "joins", "join_input_tuples",
-                                               "join_output_pairs", "result_rows")]
+                                               "join_output_pairs", "result_rows", "joins_reordered")]
 
 
 # name -> (restype, argtypes): every symbol include/rhj.h declares

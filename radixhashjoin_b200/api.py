@@ -392,7 +392,7 @@ class RadixHashJoin:
                                                     self._stream(stream)))
         return out[:cnt.value]
 
-    def query_execute(self, tables, filters, joins, projs, relations):
+    def query_execute(self, tables, filters, joins, projs, relations, reorder_joins=False):
         """Query::execute (Query.cpp:204-211) on the device.  `relations` = list of relLists (each a list of contiguous
         numpy u64 host columns, which must stay alive: they are uploaded once and cached by address); `tables` = the
         relList index of every binding; filters (binding, column, op, constant), joins (b1, c1, b2, c2), projs (binding,
@@ -415,7 +415,7 @@ class RadixHashJoin:
         pj = (_lib.QProj * max(len(projs), 1))()
         for i, (b, c) in enumerate(projs):
             pj[i].binding, pj[i].column = b, c
-        d = _lib.QueryDesc(len(tables), len(filters), len(joins), len(projs), binds, fl, jn, pj)
+        d = _lib.QueryDesc(len(tables), len(filters), len(joins), len(projs), 1 if reorder_joins else 0, 0, binds, fl, jn, pj)
         sums = (ctypes.c_uint64 * max(len(projs), 1))()
         empty = ctypes.c_int()
         st = _lib.QueryStats()

@@ -274,8 +274,59 @@ int rhj_query_execute(rhj_ctx *ctx, const rhj_query_desc *q, uint64_t *sums, int
         return RHJ_OK;
     };
 
-    for (u32 j = 0; j < q->n_joins && !*empty; ++j) {
-        const rhj_q_join &jn = q->joins[j];
+    // ---- join order.  The reference runs the joins as written (README.md:63-64 lists reordering as
+    // future work, the statistics of structs.cpp:40-60 / Query.cpp:88-154 are collected and never used).  With
+    // query->reorder_joins the executor goes cheapest-first over the join GRAPH: start with the join whose two filtered
+    // inputs are smallest, then always take a join that touches the bindings joined so far -- one that closes a cycle
+    // first (it is a row filter), else the one that brings in the smallest new binding.  Any order of a connected join
+    // graph yields the same multiset of result rows, so the checksums are unchanged; queries with a same-binding
+    // predicate or a disconnected graph keep the written order.
+    u32 order[64];
+    const u32 nj = q->n_joins;
+    if (nj > 64) return fail(ctx, RHJ_ERR_ARG, "more than 64 joins");
+    for (u32 j = 0; j < nj; ++j) order[j] = j;
+    if (q->reorder_joins && nj > 1) {
+        bool plain = true;
+        for (u32 j = 0; j < nj; ++j) {
+            const rhj_q_join &x = q->joins[j];
+            if (x.binding1 >= nb || x.binding2 >= nb) return fail(ctx, RHJ_ERR_ARG, "join binding out of range");
+            if (x.binding1 == x.binding2) plain = false;
+        }
+        if (plain) {
+            bool used[64] = {}, joined[RHJ_MAX_BINDINGS] = {};
+            u32 planned[64], np = 0;
+            for (; np < nj; ++np) {
+                u32 best = nj;
+                u64 best_cost = ~0ull;
+                for (u32 j = 0; j < nj; ++j) {
+                    if (used[j]) continue;
+                    const rhj_q_join &x = q->joins[j];
+                    const bool in1 = joined[x.binding1], in2 = joined[x.binding2];
+                    u64 cost;
+                    if (np == 0) cost = filtered[x.binding1].n + filtered[x.binding2].n;
+                    else if (in1 && in2) cost = 0;
+                    else if (in1 || in2) cost = 1 + filtered[in1 ? x.binding2 : x.binding1].n;
+                    else continue;  // not connected to what has been joined so far
+                    if (cost < best_cost) {
+                        best_cost = cost;
+                        best = j;
+                    }
+                }
+                if (best == nj) break;  // disconnected graph: keep the written order
+                used[best] = true;
+                planned[np] = best;
+                joined[q->joins[best].binding1] = joined[q->joins[best].binding2] = true;
+            }
+            if (np == nj) {
+                for (u32 j = 0; j < nj; ++j) order[j] = planned[j];
+                for (u32 j = 0; j < nj; ++j)
+                    if (order[j] != j) qs->joins_reordered = 1;
+            }
+        }
+    }
+
+    for (u32 jo = 0; jo < q->n_joins && !*empty; ++jo) {
+        const rhj_q_join &jn = q->joins[order[jo]];
         if (jn.binding1 >= nb || jn.binding2 >= nb) return fail(ctx, RHJ_ERR_ARG, "join binding out of range");
         const u64 *c1, *c2;
         if ((rc = column(jn.binding1, jn.column1, &c1))) return rc;

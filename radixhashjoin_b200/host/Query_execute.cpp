@@ -52,6 +52,9 @@ void Query::execute(JobScheduler &, std::vector<relList> &relations) {
     d.n_filters = (uint32_t) fl.size();
     d.n_joins = (uint32_t) jn.size();
     d.n_projs = (uint32_t) pj.size();
+    static const bool keep_order = getenv("RHJ_KEEP_JOIN_ORDER") != nullptr;   // default: cheapest-first (same checksums)
+    d.reorder_joins = keep_order ? 0 : 1;
+    d.reserved0 = 0;
     d.bindings = binds.data();
     d.filters = fl.data();
     d.joins = jn.data();

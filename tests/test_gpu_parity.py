@@ -844,11 +844,11 @@ def test_unique_rowids_rejects_out_of_range_ids(engine):
         engine.unique_rowids(ids, 50)
 
 
-def _device_query_lines(engine, queries, rels):
+def _device_query_lines(engine, queries, rels, reorder=False):
     lines, stats = [], []
     for q in queries:
         filters = [(b, c, op, k) for (b, c, op, k) in q.filter]
-        sums, st = engine.query_execute(q.table, filters, q.join, q.proj, rels)
+        sums, st = engine.query_execute(q.table, filters, q.join, q.proj, rels, reorder_joins=reorder)
         lines.append(" ".join("NULL" for _ in q.proj) if sums is None else " ".join(str(s) for s in sums))
         stats.append(st)
     return lines, stats
@@ -869,6 +869,10 @@ def test_small_workload_through_device_query_path(engine, small_dir):
     assert lines == expected[:50]
     assert sum(s["h2d_bytes"] for s in stats) == 0          # columns are resident
     assert max(s["d2h_bytes"] for s in stats) < 4096        # counts + checksums only
+    # cheapest-first join order: same checksums, and some query really is reordered
+    lines, stats = _device_query_lines(engine, queries, rels, reorder=True)
+    assert lines == expected[:50]
+    assert sum(s["joins_reordered"] for s in stats) > 0
     engine.column_cache_clear()
 
 
@@ -882,6 +886,8 @@ def test_edge_workload_through_device_query_path(engine, edge_dir):
     expected = open(os.path.join(edge_dir, "edge.result")).read().split("\n")
     engine.column_cache_clear()
     lines, _ = _device_query_lines(engine, queries, rels)
+    assert lines == expected[:13]
+    lines, _ = _device_query_lines(engine, queries, rels, reorder=True)
     assert lines == expected[:13]
     engine.column_cache_clear()
 
@@ -902,6 +908,8 @@ def test_device_query_path_random_queries_equal_query_oracle(engine):
         want = Q.execute(q, rels, lambda R, S: O.oracle_join(R, S))
         got, _ = _device_query_lines(engine, [q], rels)
         assert got[0] == want, line
+        got, _ = _device_query_lines(engine, [q], rels, reorder=True)
+        assert got[0] == want, line
     engine.column_cache_clear()
 
 
@@ -918,3 +926,36 @@ def test_reference_program_with_device_query_path(which, small_dir, edge_dir):
                          timeout=600)
     assert out.returncode == 0, out.stderr.decode()[-2000:]
     assert out.stdout.decode() == open(os.path.join(d, which + ".result")).read()
+
+
+# ---- the north-star kernel variants that are not the default: warp-aggregated histogram counters, TMA bulk-store scatter ----
+@pytest.mark.parametrize("env", [{"RHJ_HIST_AGG": "1"}, {"RHJ_SCATTER_MODE": "1"}, {"RHJ_HIST_AGG": "1", "RHJ_SCATTER_MODE": "1"}])
+def test_histogram_aggregation_and_bulk_store_scatter_variants(env, monkeypatch):
+    """RHJ_HIST_AGG=1 (k_hist<AGG>: match.any-combined shared-memory counters) and RHJ_SCATTER_MODE=1 (k_scatter<kWriteBulk>:
+    one TMA bulk store per run) are read at rhj_create: histogram, partition and the exact-path join with them == oracle,
+    on uniform and on one-hot-digit inputs."""
+    from radixhashjoin_b200 import RadixHashJoin
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    monkeypatch.setenv("RHJ_NO_OPT", "1")      # the exact path runs the histograms
+    e = RadixHashJoin(0)
+    try:
+        rng = np.random.default_rng(11)
+        n = 300000
+        for vals in (rng.integers(0, 1 << 40, n, dtype=np.uint64), np.full(n, 0x1234, dtype=np.uint64)):
+            T = O.as_tuples(np.arange(n, dtype=np.uint64), vals)
+            hist = e.histogram(to_dev(T), 8, 0, DIGIT_RAW).cpu().numpy().astype(np.uint64)
+            assert np.array_equal(hist, np.bincount((vals & np.uint64(0xFF)).astype(np.int64), minlength=256).astype(np.uint64))
+            out, off = e.partition(to_dev(T), 8, 0, DIGIT_RAW)
+            got, off = tuples_np(out), off.cpu().numpy()
+            assert np.array_equal(off[1:] - off[:-1], hist.astype(np.int64))
+            for d in np.flatnonzero(hist)[:8]:
+                seg = got[off[d]:off[d + 1]]
+                assert ((seg["payload"] & np.uint64(0xFF)) == d).all()
+                assert np.array_equal(np.sort(seg["key"]), np.sort(T["key"][(vals & np.uint64(0xFF)) == d]))
+        R, S = rand_rel(rng, 1 << 19, 1 << 18), rand_rel(rng, 1 << 19, 1 << 18, 1 << 33)
+        for emit in (EMIT_FUSED, EMIT_COUNT_THEN_WRITE):
+            plan = check_join(e, R, S, emit)
+            assert plan["bits_pass2"] > 0 and plan["optimistic_pass1"] == 0
+    finally:
+        e.close()
