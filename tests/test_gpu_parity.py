@@ -900,7 +900,7 @@ def test_device_query_path_random_queries_equal_query_oracle(engine):
     for n, cols, dom in [(3000, 3, 50), (5000, 4, 400), (800, 2, 30), (12000, 3, 2000)]:
         rels.append([np.ascontiguousarray(rng.integers(0, dom, n, dtype=np.uint64)) for _ in range(cols)])
     work = ["0 1|0.0=1.1&0.1>10|0.2 1.0", "0 1 2|0.0=1.0&1.1=2.0&0.1<40|0.0 1.2 2.1", "1 3|0.2=1.1&1.0>5|0.0 1.2",
-            "0 1 2|0.0=1.0&1.1=2.0&0.1=2.1|0.2 2.0", "0 2 1 3|0.0=1.0&1.1=2.0&1.2=3.0&3.1<1000|3.2 0.1",
+            "0 1 2|0.0=1.0&1.1=2.0&0.1=2.1|0.2 2.0", "0 2 1 3|0.0=1.0&1.1=2.0&2.2=3.0&3.1<1000|3.2 0.1",
             "2 2|0.0=1.1&0.1>3|0.0 1.0", "0 1|0.0=1.0&1.1=0.1&0.2>25|1.3 0.0", "3|0.0>100|0.1", "0 1|0.0=1.3&0.0>48&1.3<1|0.1"]
     engine.column_cache_clear()
     for line in work:
