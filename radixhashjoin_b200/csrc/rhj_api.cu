@@ -6,6 +6,10 @@
 // launches on one CUDA stream.  No host synchronisation happens between the launches of one
 // join; sizes that depend on the data (partition sizes, work items, match counts) stay on the
 // device.  There is no CPU fallback anywhere in this file.
+#include <future>
+#include <thread>
+#include <vector>
+
 #include "rhj_ctx.cuh"
 #include "rhj_kernels.cuh"
 
@@ -781,6 +785,58 @@ int partition_relation(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Meta
     return RHJ_OK;
 }
 
+// Host -> device copy of a caller's relation on stream `st`.  Pinned (or registered) sources go straight to the copy
+// engine.  PAGEABLE sources -- what the reference's Query::run_joins passes: relation::tuples is `new tuple[]`,
+// structs.cpp:217-243 -- would make cudaMemcpyAsync stage them through the driver's single-threaded bounce buffer at
+// ~13 GB/s and block the calling thread; here the host fills a pinned ring (4 x 32 MiB) with up to four memcpy threads
+// while the copy engine drains the slot before (measured on the 2^27 x 2^27 end-to-end join: 416 -> see DESIGN.md).
+// Returns when the last slice has been ENQUEUED; the copies complete in stream order.
+int upload_host(rhj_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, cudaStream_t st) {
+    if (!bytes) return RHJ_OK;
+    cudaPointerAttributes at{};
+    const bool pageable = cudaPointerGetAttributes(&at, h_src) != cudaSuccess || at.type == cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    if (!pageable || bytes < ((size_t) 8 << 20)) {
+        CK(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+        return RHJ_OK;
+    }
+    if (!ctx->stage_pin) {
+        cudaError_t e = cudaHostAlloc(&ctx->stage_pin, rhj_ctx::kStageSlot * rhj_ctx::kStageSlots, cudaHostAllocDefault);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            ctx->stage_pin = nullptr;
+            CK(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));  // no pinned memory left: the driver's path
+            return RHJ_OK;
+        }
+        for (auto &ev : ctx->stage_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const int nthr = (int) std::min<unsigned>(4, std::max(1u, hw / 4));
+    for (size_t off = 0; off < bytes; off += rhj_ctx::kStageSlot) {
+        const size_t len = std::min(rhj_ctx::kStageSlot, bytes - off);
+        const int slot = ctx->stage_next;
+        ctx->stage_next = (slot + 1) % rhj_ctx::kStageSlots;
+        char *pin = (char *) ctx->stage_pin + (size_t) slot * rhj_ctx::kStageSlot;
+        CK(cudaEventSynchronize(ctx->stage_ev[slot]));  // the copy engine is done with this slot (a fresh event is complete)
+        const char *src = (const char *) h_src + off;
+        if (nthr > 1 && len >= ((size_t) 4 << 20)) {
+            const size_t per = ((len / nthr) + 4095) & ~(size_t) 4095;
+            std::vector<std::thread> helpers;
+            for (int t = 1; t < nthr; ++t) {
+                const size_t b = std::min(len, (size_t) t * per), e2 = std::min(len, (size_t) (t + 1) * per);
+                if (e2 > b) helpers.emplace_back([=] { memcpy(pin + b, src + b, e2 - b); });
+            }
+            memcpy(pin, src, std::min(len, per));
+            for (auto &h : helpers) h.join();
+        } else {
+            memcpy(pin, src, len);
+        }
+        CK(cudaMemcpyAsync((char *) d_dst + off, pin, len, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(ctx->stage_ev[slot], st));
+    }
+    return RHJ_OK;
+}
+
 // Pipelined host join for large inputs: the build side is uploaded and partitioned once; the probe
 // side streams through in chunks -- H2D of chunk c+1, partition + count + write of chunk c and D2H
 // of chunk c-1's pairs run concurrently (three streams, double-buffered chunk and result buffers),
@@ -828,10 +884,23 @@ int join_host_pipelined(rhj_ctx *ctx, const Tup *hR, u64 nR, const Tup *hS, u64 
     if ((rc = ensure(ctx, ctx->item_cnt, (size_t) item_cap * 8))) return rc;
     if ((rc = ensure(ctx, ctx->item_off, (size_t) item_cap * 8))) return rc;
 
-    CK(cudaMemcpyAsync(ctx->inR.p, hB, pl.nB * sizeof(Tup), cudaMemcpyHostToDevice, st));
-    // the first probe chunk goes up while the build side is partitioned
-    CK(cudaMemcpyAsync(ctx->pin[0].p, hP, std::min(chunk, pl.nP) * sizeof(Tup), cudaMemcpyHostToDevice, ctx->s_in));
-    CK(cudaEventRecord(ctx->ev_in[0], ctx->s_in));
+    if ((rc = upload_host(ctx, ctx->inR.p, hB, pl.nB * sizeof(Tup), st))) return rc;
+    // Probe chunk c goes up on s_in from a helper thread (pageable sources are staged through the pinned ring there), so
+    // that the staging of chunk c + 1 overlaps the kernels AND the host-side count read-back of chunk c.
+    std::future<int> up;
+    auto start_upload = [&](u64 c) {
+        const int nb = (int) (c & 1);
+        const u64 n_up = std::min(chunk, pl.nP - c * chunk);
+        up = std::async(std::launch::async, [=]() -> int {
+            CK(cudaSetDevice(ctx->device));
+            if (c >= 2) CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_cmp[nb], 0));  // the buffer was last read by chunk c - 2's kernels
+            int rc2 = upload_host(ctx, ctx->pin[nb].p, hP + c * chunk, n_up * sizeof(Tup), ctx->s_in);
+            if (rc2) return rc2;
+            CK(cudaEventRecord(ctx->ev_in[nb], ctx->s_in));
+            return RHJ_OK;
+        });
+    };
+    start_upload(0);  // the first probe chunk goes up while the build side is partitioned
     CK(cudaMemsetAsync(ctx->zero.p, 0, m.zero_bytes, st));
     const Tup *finB;
     const u64 *offB;
@@ -844,13 +913,8 @@ int join_host_pipelined(rhj_ctx *ctx, const Tup *hR, u64 nR, const Tup *hS, u64 
     for (u64 c = 0; c < nchunks; ++c) {
         const int b = (int) (c & 1);
         const u64 n_c = std::min(chunk, pl.nP - c * chunk);
-        if (c + 1 < nchunks) {  // next chunk's upload: its buffer was last read by chunk c-1's kernels
-            const int nb = b ^ 1;
-            const u64 n_next = std::min(chunk, pl.nP - (c + 1) * chunk);
-            if (c >= 1) CK(cudaStreamWaitEvent(ctx->s_in, ctx->ev_cmp[nb], 0));
-            CK(cudaMemcpyAsync(ctx->pin[nb].p, hP + (c + 1) * chunk, n_next * sizeof(Tup), cudaMemcpyHostToDevice, ctx->s_in));
-            CK(cudaEventRecord(ctx->ev_in[nb], ctx->s_in));
-        }
+        if ((rc = up.get())) return rc;             // chunk c is on its way (ev_in[b] recorded)
+        if (c + 1 < nchunks) start_upload(c + 1);   // staged while this chunk is computed
         CK(cudaStreamWaitEvent(st, ctx->ev_in[b], 0));
         // counters of the probe side and the per-join scalars start from zero for every chunk
         CK(cudaMemsetAsync(m.hist1[1], 0, (size_t) kMaxDigits * 8, st));
@@ -970,6 +1034,9 @@ int rhj_destroy(rhj_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for_each_buf(ctx, [](DevBuf &b) { if (b.p) cudaFree(b.p); });
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->stage_pin) cudaFreeHost(ctx->stage_pin);
+    for (cudaEvent_t e : ctx->stage_ev)
+        if (e) cudaEventDestroy(e);
     if (ctx->h_iu) cudaFreeHost(ctx->h_iu);
     if (ctx->h_scalars) cudaFreeHost(ctx->h_scalars);
     for (cudaEvent_t e : ctx->ev)
@@ -1138,8 +1205,8 @@ int rhj_join_host(rhj_ctx *ctx, const rhj_tuple *R, uint64_t nR, const rhj_tuple
         return join_host_pipelined(ctx, (const Tup *) R, nR, (const Tup *) S, nS, out, count);
     if ((rc = ensure(ctx, ctx->inR, nR * sizeof(Tup)))) return rc;
     if ((rc = ensure(ctx, ctx->inS, nS * sizeof(Tup)))) return rc;
-    CK(cudaMemcpyAsync(ctx->inR.p, R, nR * sizeof(Tup), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(ctx->inS.p, S, nS * sizeof(Tup), cudaMemcpyHostToDevice, st));
+    if ((rc = upload_host(ctx, ctx->inR.p, R, nR * sizeof(Tup), st))) return rc;
+    if ((rc = upload_host(ctx, ctx->inS.p, S, nS * sizeof(Tup), st))) return rc;
     uint64_t n = 0;
     if ((rc = rhj_join_count_device(ctx, (const rhj_tuple *) ctx->inR.p, nR, (const rhj_tuple *) ctx->inS.p, nS, &n, st)))
         return rc;

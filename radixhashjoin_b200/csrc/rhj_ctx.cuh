@@ -70,6 +70,13 @@ struct rhj_ctx {
     DevBuf iu_col, iu_pairs, iu_A, iu_B, iu_ep, iu_out;  // update_intermediate staging (rhj_query.cu)
     void *h_iu = nullptr;     // pinned host result columns of the intermediate update
     size_t h_iu_cap = 0;
+    // staged upload of PAGEABLE host inputs (the reference's relation::tuples are `new tuple[]`): a pinned ring the host
+    // fills with a few memcpy threads while the copy engine drains it (rhj_api.cu: upload_host)
+    void *stage_pin = nullptr;
+    static constexpr size_t kStageSlot = (size_t) 32 << 20;
+    static constexpr int kStageSlots = 4;
+    cudaEvent_t stage_ev[kStageSlots] = {};
+    int stage_next = 0;
     void *h_out = nullptr;    // pinned host result of rhj_join_host
     size_t h_out_cap = 0;
     u64 *h_scalars = nullptr; // pinned, kScCount u64

@@ -953,7 +953,7 @@ def test_histogram_aggregation_and_bulk_store_scatter_variants(env, monkeypatch)
                 seg = got[off[d]:off[d + 1]]
                 assert ((seg["payload"] & np.uint64(0xFF)) == d).all()
                 assert np.array_equal(np.sort(seg["key"]), np.sort(T["key"][(vals & np.uint64(0xFF)) == d]))
-        R, S = rand_rel(rng, 1 << 19, 1 << 18), rand_rel(rng, 1 << 19, 1 << 18, 1 << 33)
+        R, S = rand_rel(rng, 1 << 21, 1 << 20), rand_rel(rng, 1 << 21, 1 << 20, 1 << 33)
         for emit in (EMIT_FUSED, EMIT_COUNT_THEN_WRITE):
             plan = check_join(e, R, S, emit)
             assert plan["bits_pass2"] > 0 and plan["optimistic_pass1"] == 0
