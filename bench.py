@@ -358,8 +358,8 @@ def run_b200(args, rank, world, local_rank):
         def step():
             return eng.join_device(R, S, out=out, emit=emit)
     else:
-        from radixhashjoin_b200.distributed import (BroadcastShardedJoin, DmaShardedJoin, FusedShardedJoin, PipeShardedJoin,
-                                                    ShardedJoin, broadcast_is_cheaper)
+        from radixhashjoin_b200.distributed import (BroadcastShardedJoin, DmaShardedJoin, PipeShardedJoin, ShardedJoin,
+                                                    broadcast_is_cheaper)
         n_max = max(nR, nS)
         # what a rank receives / emits: ~ its share for hashed distinct keys; the rank that owns the hot Zipf keys gets more
         slack = int(n_max * (2.0 if args.workload == "zipf" else 1.05)) + 4096
@@ -401,14 +401,9 @@ def run_b200(args, rank, world, local_rank):
                 torch.cuda.synchronize()
                 return pj.timeline(marks)
         elif strategy == "dma":
-            # pass 1 partitions on (rank | sub-digit) into staging; the copy engines ship one chunk per peer
-            # while the SMs partition the other relation; pass 2 runs on the received (source, partition) pieces
-            # 12-byte shipping when every row id fits 32 bits (checked here once, and by the kernels every step)
-            mx = torch.stack([R[:, 0].max(), S[:, 0].max()]).max()
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-            compact = args.ship_bytes == 12 and int(mx.item()) < (1 << 32)
-            dj = DmaShardedJoin(eng, world, rank, nR * world, nS * world, n_max, slack,
-                                split_probe=args.split_probe, compact_rowids=compact)
+            # the exact exchange (what the pipelined one falls back to): pass 1 with histograms into staging, the copy engines
+            # ship one chunk per peer while the SMs partition the other relation, pass 2 on the received pieces
+            dj = DmaShardedJoin(eng, world, rank, nR * world, nS * world, n_max, slack)
             del recvR, recvS
 
             def step():
@@ -420,14 +415,6 @@ def run_b200(args, rank, world, local_rank):
                 dj.step(R, S, out, marks)
                 torch.cuda.synchronize()
                 return dj.timeline(marks)
-        elif strategy == "stores":
-            # pass 1 of the join IS the shuffle: runs are stored straight into the peers' receive buffers
-            fj = FusedShardedJoin(eng, world, rank, nR * world, nS * world, slack)
-            del recvR, recvS
-
-            def step():
-                pairs, count, _ = fj.step(R, S, out)
-                return pairs, count
         else:
             sj = ShardedJoin(world, rank, lambda T: eng.shuffle_partition(T, world),
                              lambda a, b: eng.join_device(a, b, out=out, emit=emit))
@@ -619,11 +606,9 @@ def run_b200(args, rank, world, local_rank):
                                "the next chunk is partitioned, "
                                "pass 2 appends each arrived chunk to fixed-capacity final partitions, one join; no collective in the "
                                f"step (exact-path steps among the timed ones: {pj.exact_steps})" if strategy == "pipe" else
-                               f"{world} ranks: pass 1 partitions on (rank | sub-digit), copy engines ship one chunk per peer "
-                               f"({12 if compact else 16} B per tuple) over "
-                               "NVLink overlapped with the other relation's passes, then local pass 2 + join" if strategy == "dma" else
-                               f"{world} ranks: pass-1 scatter stores into peer receive buffers over NVLink (fused partition+shuffle), "
-                               "then local pass 2 + join" if strategy == "stores" else
+                               f"{world} ranks: exact exchange -- pass 1 with histograms on (rank | sub-digit), copy engines ship one chunk per "
+                               "peer over NVLink overlapped with the other relation's passes, then local pass 2 + join"
+                               if strategy == "dma" else
                                f"{world} ranks: rank-radix partition + NCCL all-to-all + local join")},
                 "verified": verified, "clocks": clocks, "gpu_launches": launches_per_step * args.steps,
                 "phase_ms": {k: round(v, 4) for k, v in acc.items() if v > 0},
@@ -663,16 +648,12 @@ def main():
     ap.add_argument("--cpu-log2n", type=int, default=26, help="cpu_baseline sample size (2^k x 2^k)")
     ap.add_argument("--ref-log2n", type=int, default=0, help="--impl reference: 2^k x 2^k per step (default: --log2n, the stated config)")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: stop timing after this many seconds of joins")
-    ap.add_argument("--shuffle", default="pipe", choices=["pipe", "dma", "stores", "nccl"],
-                    help="multi-GPU exchange: pipelined histogram-free chunks shipped by our copy kernel (default), pass-1 chunks "
-                         "shipped by the copy engines after exact histograms, pass-1 scatter storing straight into peer memory, "
-                         "or rank partition + NCCL all-to-all")
+    ap.add_argument("--shuffle", default="pipe", choices=["pipe", "dma", "nccl"],
+                    help="multi-GPU exchange: pipelined histogram-free chunks shipped by our copy kernel (default), the exact exchange "
+                         "(pass-1 chunks shipped by the copy engines after histograms), or rank partition + NCCL all-to-all")
     ap.add_argument("--chunks", type=int, default=4, help="pipe shuffle: row chunks per relation")
     ap.add_argument("--wire-bytes", type=int, default=0, choices=[0, 12, 16],
                     help="pipe shuffle: bytes per tuple on the wire (0 = 12 when row ids fit 32 bits and N >= 4, else 16)")
-    ap.add_argument("--ship-bytes", type=int, default=16, choices=[12, 16],
-                    help="dma shuffle: bytes per tuple on the wire; 12 = {u64 value, u32 row id}, used when row ids fit 32 bits")
-    ap.add_argument("--split-probe", action="store_true", help="dma shuffle: ship the probe relation in two halves (measured slower)")
     ap.add_argument("--no-small-work", action="store_true")
     ap.add_argument("--small-work-ref", action="store_true", help="also time the unmodified reference program (minutes)")
     ap.add_argument("--no-e2e", action="store_true")

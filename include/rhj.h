@@ -221,37 +221,20 @@ int rhj_query_execute(rhj_ctx *ctx, const rhj_query_desc *query, uint64_t *sums,
 int rhj_shuffle_partition_device(rhj_ctx *ctx, const rhj_tuple *d_in, uint64_t n, int world,
                                  rhj_tuple *d_out, uint64_t *h_counts, void *stream);
 
-/* Fused partition + shuffle: pass 1 of the join partitions on (destination rank | sub-digit) and
- * its scatter stores every run directly into the destination rank's receive buffer through peer
- * memory (NVLink / NVSwitch), so the exchange costs no extra pass over HBM and overlaps the
- * scatter tile by tile.  Call sequence per join, on every rank, with the same plan:
- *   rhj_shard_plan_make -> rhj_shard_histogram_device -> [all-gather the histograms] ->
- *   rhj_shard_offsets_device -> [barrier: receive buffers free] -> rhj_shard_scatter_device ->
- *   [barrier: all stores landed] -> rhj_shard_join_device.
- * The two small collectives and the barriers are the caller's (torch.distributed / symmetric
- * memory in radixhashjoin_b200/distributed.py). */
+/* Radix plan shared by the sharded joins: destination rank = top rank_bits of the HIGH hash word, local partition = top
+ * bits_total bits of the low word, bits_pass1 of them taken in the pass that also separates the destinations. */
 typedef struct rhj_shard_plan {
     uint32_t world, rank_bits;                       /* ranks (power of two <= 16), log2(world)        */
     uint32_t bits_total, bits_pass1, bits_pass2;     /* local radix bits: total, fused pass, second pass */
     uint32_t build_is_S;
 } rhj_shard_plan;
 int rhj_shard_plan_make(uint64_t nR_global, uint64_t nS_global, int world, rhj_shard_plan *plan);
-int rhj_shard_histogram_device(rhj_ctx *ctx, const rhj_shard_plan *plan, const rhj_tuple *dR, uint64_t nR,
-                               const rhj_tuple *dS, uint64_t nS, uint64_t *d_hist, void *stream);
-int rhj_shard_offsets_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int rank, const uint64_t *d_all_hist,
-                             uint64_t *recv_counts, void *stream);
-int rhj_shard_scatter_device(rhj_ctx *ctx, const rhj_shard_plan *plan, const rhj_tuple *dR, uint64_t nR,
-                             const rhj_tuple *dS, uint64_t nS, void *const *peer_R, void *const *peer_S, void *stream);
-int rhj_shard_join_device(rhj_ctx *ctx, const rhj_shard_plan *plan, const rhj_tuple *d_recvR, uint64_t nR_recv,
-                          const rhj_tuple *d_recvS, uint64_t nS_recv, rhj_pair *d_out, uint64_t capacity,
-                          uint64_t *count, void *stream);
 
-/* DMA-shipped variant of the sharded join (the default of bench.py at N > 1).  Pass 1 partitions each
- * local shard on (destination rank | sub-digit) into a LOCAL staging buffer, so the data for one
- * destination is one contiguous chunk that is already pass-1 partitioned; the caller ships the chunks
- * with the copy engines (peer cudaMemcpyAsync over NVLink at full packet efficiency, no SM time) while
- * the SMs partition the other relation; pass 2 consumes the received chunks as (source, partition)
- * pieces.  Per relation (rel 0 = R, 1 = S), on every rank, same plan:
+/* Exact (histogram) exchange: the fallback of the pipelined exchange below for skewed / duplicate-heavy inputs.  Pass 1
+ * partitions each local shard on (destination rank | sub-digit) into a LOCAL staging buffer, so the data for one
+ * destination is one contiguous chunk that is already pass-1 partitioned; the caller all-gathers the histograms, ships the
+ * chunks with the copy engines (peer cudaMemcpyAsync over NVLink, no SM time) while the SMs partition the other relation;
+ * pass 2 consumes the received chunks as (source, partition) pieces.  Per relation (rel 0 = R, 1 = S), on every rank:
  *   rhj_shardx_begin -> rhj_shardx_pass1_device(rel) -> [all-gather d_hist] -> rhj_shardx_layout_device(rel)
  *   -> [barrier; peer copies of send_cnt[d] tuples from stage+send_off[d] to dest d's buffer+dst_off[d];
  *      barrier] -> rhj_shardx_pass2_device(rel) ... -> rhj_shardx_join_device. */
@@ -265,20 +248,6 @@ int rhj_shardx_pass2_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int rel, c
                             void *stream);
 int rhj_shardx_join_device(rhj_ctx *ctx, const rhj_shard_plan *plan, rhj_pair *d_out, uint64_t capacity, uint64_t *count,
                            void *stream);
-/* 12-byte shipping: pass 1 stages {u64 value, u32 row id} in two arrays and pass 2 reads what arrived in that
- * form (the final partitions are 16-byte tuples again), so 25 % fewer bytes cross NVLink.  The caller promises
- * that every row id fits 32 bits (relation cardinality < 2^32); a wider one makes the join call fail with
- * RHJ_ERR_ARG.  The chunk arithmetic of rhj_shardx_layout_device is the same: offsets and counts are in tuples. */
-int rhj_shardx_pass1_soa_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int rel, const rhj_tuple *d_in, uint64_t n,
-                                uint64_t *d_stage_val, uint32_t *d_stage_rid, uint64_t *d_hist, void *stream);
-int rhj_shardx_pass2_soa_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int rel, const uint64_t *d_recv_val,
-                                const uint32_t *d_recv_rid, uint64_t n_recv, void *stream);
-/* Slots: `rel` above is 0 = R, 1 = S, or 2 = the second half of the PROBE relation (the larger one) when the
- * caller ships it in two halves.  rhj_shardx_join_slots_device joins one (build slot, probe slot) pair; with
- * first = 0 it appends to the previous call's result, so the join of the first half overlaps the transfer of
- * the second.  *count = pairs emitted so far. */
-int rhj_shardx_join_slots_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int build_slot, int probe_slot, int first,
-                                 rhj_pair *d_out, uint64_t capacity, uint64_t *count, void *stream);
 
 /* Pipelined exchange (the default of bench.py at N > 1): histogram-free, chunked, no host synchronisation and
  * no collective call inside a step.  Every rank cuts each local relation into `chunks` row chunks; pass 1 of a

@@ -98,21 +98,11 @@ SIGNATURES = {
                                           ctypes.POINTER(QueryStats)]),
     "rhj_shuffle_partition_device": (ctypes.c_int, [c_vp, c_vp, c_u64, ctypes.c_int, c_vp, c_u64p, c_vp]),
     "rhj_shard_plan_make": (ctypes.c_int, [c_u64, c_u64, ctypes.c_int, ctypes.POINTER(ShardPlan)]),
-    "rhj_shard_histogram_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), c_vp, c_u64, c_vp, c_u64, c_vp, c_vp]),
-    "rhj_shard_offsets_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, c_vp, c_u64p, c_vp]),
-    "rhj_shard_scatter_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), c_vp, c_u64, c_vp, c_u64, c_vp, c_vp, c_vp]),
-    "rhj_shard_join_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), c_vp, c_u64, c_vp, c_u64, c_vp, c_u64,
-                                             c_u64p, c_vp]),
     "rhj_shardx_begin": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), c_vp]),
     "rhj_shardx_pass1_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, c_vp, c_u64, c_vp, c_vp, c_vp]),
     "rhj_shardx_layout_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, ctypes.c_int, c_vp, c_u64p,
                                                 c_u64p, c_u64p, c_u64p, c_vp]),
     "rhj_shardx_pass2_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, c_vp, c_u64, c_vp]),
-    "rhj_shardx_pass1_soa_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, c_vp, c_u64, c_vp, c_vp, c_vp,
-                                                   c_vp]),
-    "rhj_shardx_pass2_soa_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, c_vp, c_vp, c_u64, c_vp]),
-    "rhj_shardx_join_slots_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                                    c_vp, c_u64, c_u64p, c_vp]),
     "rhj_shardx_join_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), c_vp, c_u64, c_u64p, c_vp]),
     "rhj_pipe_sym_bytes": (c_u64, [ctypes.POINTER(ShardPlan), ctypes.POINTER(PipeCfg)]),
     "rhj_pipe_open": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.POINTER(PipeCfg)]),

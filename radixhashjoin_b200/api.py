@@ -202,51 +202,12 @@ class RadixHashJoin:
                                                         self._stream(stream)))
         return out, [int(c) for c in counts]
 
-    # ---- multi-GPU: fused partition + shuffle (include/rhj.h, rhj_shard_*) ----------------------
+    # ---- multi-GPU: radix plan + the exact (histogram) exchange (include/rhj.h, rhj_shard_plan_make, rhj_shardx_*) ----
     def shard_plan(self, nR_global, nS_global, world):
         plan = _lib.ShardPlan()
         self._ck(self._lib.rhj_shard_plan_make(nR_global, nS_global, world, ctypes.byref(plan)))
         return plan
 
-    def shard_histogram(self, plan, R, S, hist=None, stream=None):
-        """pass-1 histogram on (destination rank | sub-digit): int64 tensor [2, world << bits_pass1]"""
-        torch = _torch()
-        nR, nS = _check_rel(R), _check_rel(S)
-        if hist is None:
-            hist = torch.empty((2, plan.world << plan.bits_pass1), dtype=torch.int64, device=R.device)
-        self._ck(self._lib.rhj_shard_histogram_device(self._ctx, ctypes.byref(plan), _ptr(R), nR, _ptr(S), nS, _ptr(hist),
-                                                      self._stream(stream)))
-        return hist
-
-    def shard_offsets(self, plan, rank, all_hist, stream=None):
-        """write cursors + receive layout from the all-gathered histograms; returns (nR_recv, nS_recv)"""
-        recv = (ctypes.c_uint64 * 2)()
-        self._ck(self._lib.rhj_shard_offsets_device(self._ctx, ctypes.byref(plan), rank, _ptr(all_hist), recv,
-                                                    self._stream(stream)))
-        return int(recv[0]), int(recv[1])
-
-    def shard_scatter(self, plan, R, S, peer_ptrs_R, peer_ptrs_S, stream=None):
-        """the fused pass: scatter both shards straight into the destination ranks' receive buffers"""
-        nR, nS = _check_rel(R), _check_rel(S)
-        pr = (ctypes.c_void_p * plan.world)(*peer_ptrs_R)
-        ps = (ctypes.c_void_p * plan.world)(*peer_ptrs_S)
-        self._ck(self._lib.rhj_shard_scatter_device(self._ctx, ctypes.byref(plan), _ptr(R), nR, _ptr(S), nS, pr, ps,
-                                                    self._stream(stream)))
-
-    def shard_join(self, plan, recvR, recvS, out, stream=None):
-        """second radix pass + build/probe + fused emit on what this rank received"""
-        nR, nS = _check_rel(recvR), _check_rel(recvS)
-        cnt = ctypes.c_uint64()
-        rc = self._lib.rhj_shard_join_device(self._ctx, ctypes.byref(plan), _ptr(recvR), nR, _ptr(recvS), nS, _ptr(out),
-                                             out.shape[0], ctypes.byref(cnt), self._stream(stream))
-        if rc == 4:
-            e = RhjError(rc, self._lib.rhj_last_error(self._ctx).decode())
-            e.needed = int(cnt.value)
-            raise e
-        self._ck(rc)
-        return out[:cnt.value], int(cnt.value)
-
-    # ---- multi-GPU: DMA-shipped sharded join (include/rhj.h, rhj_shardx_*) ------------------------
     def shardx_begin(self, plan, stream=None):
         self._ck(self._lib.rhj_shardx_begin(self._ctx, ctypes.byref(plan), self._stream(stream)))
 
@@ -255,20 +216,6 @@ class RadixHashJoin:
         n = _check_rel(T)
         self._ck(self._lib.rhj_shardx_pass1_device(self._ctx, ctypes.byref(plan), rel, _ptr(T), n, _ptr(stage), _ptr(hist),
                                                    self._stream(stream)))
-
-    def shardx_pass1_soa(self, plan, rel, T, stage_val, stage_rid, hist, stream=None):
-        """pass 1 staging 12-byte tuples: stage_val int64[n] + stage_rid int32[n] (row ids must fit 32 bits)"""
-        n = _check_rel(T)
-        if stage_val.numel() < n or stage_rid.numel() < n:
-            raise ValueError("staging arrays too small")
-        self._ck(self._lib.rhj_shardx_pass1_soa_device(self._ctx, ctypes.byref(plan), rel, _ptr(T), n, _ptr(stage_val),
-                                                       _ptr(stage_rid), _ptr(hist), self._stream(stream)))
-
-    def shardx_pass2_soa(self, plan, rel, recv_val, recv_rid, n, stream=None):
-        if recv_val.numel() < n or recv_rid.numel() < n:
-            raise ValueError("receive arrays too small")
-        self._ck(self._lib.rhj_shardx_pass2_soa_device(self._ctx, ctypes.byref(plan), rel, _ptr(recv_val), _ptr(recv_rid), n,
-                                                       self._stream(stream)))
 
     def shardx_layout(self, plan, rank, rel, all_hist, stream=None):
         """(send_off[d], send_cnt[d], dst_off[d], recv_total) from the all-gathered histograms"""
@@ -287,18 +234,6 @@ class RadixHashJoin:
         cnt = ctypes.c_uint64()
         rc = self._lib.rhj_shardx_join_device(self._ctx, ctypes.byref(plan), _ptr(out), out.shape[0], ctypes.byref(cnt),
                                               self._stream(stream))
-        if rc == 4:
-            e = RhjError(rc, self._lib.rhj_last_error(self._ctx).decode())
-            e.needed = int(cnt.value)
-            raise e
-        self._ck(rc)
-        return out[:cnt.value], int(cnt.value)
-
-    def shardx_join_slots(self, plan, build_slot, probe_slot, first, out, stream=None):
-        """join one (build slot, probe slot) pair; first=False appends to the previous call's result"""
-        cnt = ctypes.c_uint64()
-        rc = self._lib.rhj_shardx_join_slots_device(self._ctx, ctypes.byref(plan), build_slot, probe_slot, 1 if first else 0,
-                                                    _ptr(out), out.shape[0], ctypes.byref(cnt), self._stream(stream))
         if rc == 4:
             e = RhjError(rc, self._lib.rhj_last_error(self._ctx).decode())
             e.needed = int(cnt.value)

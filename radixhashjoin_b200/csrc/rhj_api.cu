@@ -54,14 +54,6 @@ int launch_hist(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, bool
     if (!total) return RHJ_OK;
     u32 grid = std::min<u32>(total, (u32) ctx->num_sms * 4);
     bool agg = ctx->hist_agg;
-    if (!a.rel[0].in && a.rel[0].in_val) {  // 12-byte input (received shards): pass 2 of the DMA-shipped sharded join
-        if (kind != kDigitHash || !seg) return fail(ctx, RHJ_ERR_STATE, "12-byte input is only wired for the segmented hash pass");
-        if (agg) k_hist<kDigitHash, true, true, kIoSoaIn><<<grid, kPartThreads, 0, st>>>(a);
-        else k_hist<kDigitHash, true, false, kIoSoaIn><<<grid, kPartThreads, 0, st>>>(a);
-        CK(cudaGetLastError());
-        ctx->info.kernel_launches++;
-        return RHJ_OK;
-    }
 #define HIST(K, S)                                                            \
     do {                                                                      \
         if (agg) k_hist<K, S, true><<<grid, kPartThreads, 0, st>>>(a);        \
@@ -146,21 +138,6 @@ int launch_scatter(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, b
     }
     const int w = kind == kDigitShard ? ctx->shard_scatter_mode : ctx->scatter_mode;
     cudaError_t e;
-    if (!a.rel[0].in && a.rel[0].in_val) {  // 12-byte input -> 16-byte partitions (pass 2 of the DMA-shipped sharded join)
-        if (kind != kDigitHash || !seg) return fail(ctx, RHJ_ERR_STATE, "12-byte input is only wired for the segmented hash pass");
-        if (w == 1) e = launch_scatter_t<kDigitHash, true, kWriteBulk, kIoSoaIn>(st, a, grid);
-        else e = launch_scatter_t<kDigitHash, true, kWriteStaged, kIoSoaIn>(st, a, grid);
-        CK(e);
-        ctx->info.kernel_launches++;
-        return RHJ_OK;
-    }
-    if (!a.rel[0].out && a.rel[0].out_val) {  // 16-byte input -> 12-byte staging (pass 1 of the same); per-thread stores
-        if (kind != kDigitShard || !a.shard_local) return fail(ctx, RHJ_ERR_STATE, "12-byte output is only wired for local staging");
-        e = launch_scatter_t<kDigitShard, false, kWriteStaged, kIoSoaOut>(st, a, grid);
-        CK(e);
-        ctx->info.kernel_launches++;
-        return RHJ_OK;
-    }
 #define SC(K, S) (w == 1 ? launch_scatter_t<K, S, kWriteBulk>(st, a, grid) : launch_scatter_t<K, S, kWriteStaged>(st, a, grid))
     if (kind == kDigitRaw) e = seg ? SC(kDigitRaw, true) : SC(kDigitRaw, false);
     else if (kind == kDigitHash) e = seg ? SC(kDigitHash, true) : SC(kDigitHash, false);
@@ -667,8 +644,6 @@ int read_scalars(rhj_ctx *ctx, cudaStream_t st) {
     u64 *sc = scalars_of(ctx, ctx->cur.nparts);
     CK(cudaMemcpyAsync(ctx->h_scalars, sc, kScCount * sizeof(u64), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    if (ctx->h_scalars[kScWideKey])
-        return fail(ctx, RHJ_ERR_ARG, "a row id does not fit 32 bits: 12-byte shipping (rhj_shardx_*_soa_device) cannot be used");
     if (ctx->h_scalars[kScOverflow]) return kRetryExact;  // the optimistic pass-1 layout was too small
     if (ctx->h_scalars[kScErr]) return fail(ctx, RHJ_ERR_STATE, "device-side planning error (work-item table overflow)");
     ctx->info.n_items = (u32) ctx->h_scalars[kScNItems];
@@ -1337,7 +1312,7 @@ int rhj_shuffle_partition_device(rhj_ctx *ctx, const rhj_tuple *d_in, uint64_t n
     return RHJ_OK;
 }
 
-// ---- multi-GPU: fused partition + shuffle over peer memory ---------------------------
+// ---- multi-GPU -------------------------------------------------------------------------
 
 int rhj_shard_plan_make(uint64_t nR_global, uint64_t nS_global, int world, rhj_shard_plan *plan) {
     if (!plan || world < 1 || world > kMaxPeers || (world & (world - 1))) return RHJ_ERR_ARG;
@@ -1369,132 +1344,6 @@ static PartArgs shard_args(const rhj_shard_plan *sp) {
     return a;
 }
 
-// Step 1: pass-1 histogram on the digit (destination rank | sub-digit) of both local shards.
-// d_hist[2][world << bits_pass1] (u64; [0] = R, [1] = S).  Enqueues only.
-int rhj_shard_histogram_device(rhj_ctx *ctx, const rhj_shard_plan *sp, const rhj_tuple *dR, uint64_t nR,
-                               const rhj_tuple *dS, uint64_t nS, uint64_t *d_hist, void *stream) {
-    if (!ctx || !sp || !d_hist) return RHJ_ERR_ARG;
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = pick(ctx, stream);
-    ctx->cur.valid = false;
-    ctx->nmarks = 0;
-    ctx->info = rhj_plan_info{};
-    Meta m;
-    int rc;
-    if ((rc = layout_meta(ctx, 1u << sp->bits_total, m))) return rc;
-    PartArgs a = shard_args(sp);
-    CK(cudaMemsetAsync(d_hist, 0, 2 * (size_t) a.ndig * sizeof(u64), st));
-    a.rel[0] = PartRel{(const Tup *) dR, nullptr, nR, (u64 *) d_hist, nullptr, nullptr, nullptr, 1, tiles_of(nR)};
-    a.rel[1] = PartRel{(const Tup *) dS, nullptr, nS, (u64 *) d_hist + a.ndig, nullptr, nullptr, nullptr, 1, tiles_of(nS)};
-    mark(ctx, st, RHJ_PHASE_HIST1);
-    if ((rc = launch_hist(ctx, st, a, kDigitShard, false))) return rc;
-    mark(ctx, st, RHJ_PHASE_SCAN1);
-    return RHJ_OK;
-}
-
-// Step 2: from the all-gathered histograms d_all_hist[world][2][world << bits_pass1], this rank's
-// write cursors inside every destination buffer and the layout of what it will receive.
-// recv_counts[2] (host; [0] = R, [1] = S) = tuples this rank receives.  Synchronises the stream.
-int rhj_shard_offsets_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rank, const uint64_t *d_all_hist,
-                             uint64_t *recv_counts, void *stream) {
-    if (!ctx || !sp || !d_all_hist || !recv_counts || rank < 0 || rank >= (int) sp->world) return RHJ_ERR_ARG;
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = pick(ctx, stream);
-    Meta m;
-    int rc;
-    if ((rc = layout_meta(ctx, 1u << sp->bits_total, m))) return rc;
-    if ((rc = ensure(ctx, ctx->filt_off, 16))) return rc;
-    ShardOffsetsArgs a{};
-    a.all_hist = (const u64 *) d_all_hist;
-    for (int i = 0; i < 2; ++i) {
-        a.cursor[i] = m.cur1[i];
-        a.off1[i] = m.off1[i];
-        a.tile0[i] = m.tile0[i];
-    }
-    a.recv_total = (u64 *) ctx->filt_off.p;
-    a.world = sp->world;
-    a.rank = (u32) rank;
-    a.sub_bits = sp->bits_pass1;
-    k_shard_offsets<<<2, kMaxDigits, 0, st>>>(a);
-    CK(cudaGetLastError());
-    ctx->info.kernel_launches++;
-    CK(cudaMemcpyAsync(ctx->h_scalars, a.recv_total, 16, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    recv_counts[0] = ctx->h_scalars[0];
-    recv_counts[1] = ctx->h_scalars[1];
-    return RHJ_OK;
-}
-
-// Step 3: the scatter of pass 1 IS the shuffle: every tile is staged in shared memory sorted by
-// (destination rank, sub-digit) and each run is stored straight into the destination rank's
-// receive buffer (peer memory over NVLink, or local HBM for the rank itself).
-// peer_R[world] / peer_S[world] are device pointers to the ranks' receive buffers, valid in this
-// process (CUDA IPC / symmetric memory).  Enqueues only; the caller fences across ranks.
-int rhj_shard_scatter_device(rhj_ctx *ctx, const rhj_shard_plan *sp, const rhj_tuple *dR, uint64_t nR,
-                             const rhj_tuple *dS, uint64_t nS, void *const *peer_R, void *const *peer_S, void *stream) {
-    if (!ctx || !sp || !peer_R || !peer_S) return RHJ_ERR_ARG;
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = pick(ctx, stream);
-    Meta m;
-    int rc;
-    if ((rc = layout_meta(ctx, 1u << sp->bits_total, m))) return rc;
-    PartArgs a = shard_args(sp);
-    a.rel[0] = PartRel{(const Tup *) dR, nullptr, nR, nullptr, m.cur1[0], nullptr, nullptr, 1, tiles_of(nR)};
-    a.rel[1] = PartRel{(const Tup *) dS, nullptr, nS, nullptr, m.cur1[1], nullptr, nullptr, 1, tiles_of(nS)};
-    for (u32 r = 0; r < sp->world; ++r) {
-        a.peer_out[0][r] = (Tup *) peer_R[r];
-        a.peer_out[1][r] = (Tup *) peer_S[r];
-    }
-    mark(ctx, st, RHJ_PHASE_SCATTER1);
-    if ((rc = launch_scatter(ctx, st, a, kDigitShard, false))) return rc;
-    mark(ctx, st, RHJ_PHASE_HIST2);
-    return RHJ_OK;
-}
-
-// Step 4: local continuation on what this rank received (pass-1 partitioned by step 3): second
-// radix pass, build/probe, emit.  d_recvR[nR_recv] / d_recvS[nS_recv] are this rank's receive buffers.
-int rhj_shard_join_device(rhj_ctx *ctx, const rhj_shard_plan *sp, const rhj_tuple *d_recvR, uint64_t nR_recv,
-                          const rhj_tuple *d_recvS, uint64_t nS_recv, rhj_pair *d_out, uint64_t capacity,
-                          uint64_t *count, void *stream) {
-    if (!ctx || !sp || !count) return RHJ_ERR_ARG;
-    *count = 0;
-    CK(cudaSetDevice(ctx->device));
-    cudaStream_t st = pick(ctx, stream);
-    if (nR_recv == 0 || nS_recv == 0) return RHJ_OK;
-    Plan pl{};
-    pl.build_is_S = sp->build_is_S;
-    pl.nB = pl.build_is_S ? nS_recv : nR_recv;
-    pl.nP = pl.build_is_S ? nR_recv : nS_recv;
-    pl.bits = sp->bits_total;
-    pl.b1 = sp->bits_pass1;
-    pl.b2 = sp->bits_pass2;
-    pl.nparts = 1u << pl.bits;
-    ctx->info.bits_total = pl.bits;
-    ctx->info.bits_pass1 = pl.b1;
-    ctx->info.bits_pass2 = pl.b2;
-    ctx->info.build_is_S = pl.build_is_S;
-    ctx->info.n_partitions = pl.nparts;
-    Meta m;
-    int rc;
-    if ((rc = layout_meta(ctx, pl.nparts, m))) return rc;
-    CK(cudaMemsetAsync(ctx->zero.p, 0, m.zero_bytes, st));
-    const int bi = pl.build_is_S ? 1 : 0;
-    const Tup *inX[2] = {(const Tup *) (bi ? d_recvS : d_recvR), (const Tup *) (bi ? d_recvR : d_recvS)};
-    const u64 *off1X[2] = {m.off1[bi], m.off1[bi ^ 1]};
-    const u32 *tile0X[2] = {m.tile0[bi], m.tile0[bi ^ 1]};
-    if ((rc = second_pass_and_plan(ctx, st, pl, m, inX, off1X, tile0X))) return rc;
-    JoinArgs j = join_args(ctx, kScWork0);
-    j.out = (Pair *) d_out;
-    j.capacity = capacity;
-    mark(ctx, st, RHJ_PHASE_JOIN);
-    if ((rc = launch_join<kJoinFused>(ctx, st, j, ctx->cur.item_cap))) return rc;
-    mark(ctx, st, -1);
-    if ((rc = read_scalars(ctx, st))) return rc;
-    *count = ctx->h_scalars[kScCursor];
-    if (*count > capacity) return fail(ctx, RHJ_ERR_CAPACITY, "output buffer too small for the fused emitter");
-    return RHJ_OK;
-}
-
 // ---- multi-GPU, DMA-shipped variant: pass 1 partitions locally on (destination rank | sub-digit) into
 // a staging buffer, the copy engines ship one contiguous chunk per destination over NVLink while the
 // SMs work on the other relation, and pass 2 consumes the received chunks as (source, partition) pieces.
@@ -1518,9 +1367,7 @@ int layout_shard_meta(rhj_ctx *ctx, ShardMeta &sm) {
     return RHJ_OK;
 }
 
-// Per-slot view of the sharded join's metadata.  Slots 0 / 1 are relations R / S (the arrays of
-// Meta / ShardMeta); slot 2 is the second half of the PROBE relation when it is shipped in two halves
-// so that the join of the first half overlaps the transfer of the second.
+// Per-slot view of the sharded join's metadata: slots 0 / 1 are relations R / S (the arrays of Meta / ShardMeta).
 struct SlotArrays {
     u64 *cur1, *loc_off, *seg_off, *off1, *hist2, *cur2, *off2;
     u32 *tile0;
@@ -1532,23 +1379,9 @@ int slot_arrays(rhj_ctx *ctx, u32 nparts, int slot, SlotArrays &a) {
     int rc;
     if ((rc = layout_meta(ctx, nparts, m))) return rc;
     if ((rc = layout_shard_meta(ctx, sm))) return rc;
-    if (slot < 2) {
-        a = SlotArrays{m.cur1[slot], sm.loc_off[slot], sm.seg_off[slot], m.off1[slot], m.hist2[slot], m.cur2[slot], m.off2[slot],
-                       m.tile0[slot], slot ? &ctx->bufB2 : &ctx->bufB};
-        return RHJ_OK;
-    }
-    size_t n = 3 * (size_t) nparts + 1 + 5 * (size_t) (kMaxDigits + 2);
-    if ((rc = ensure(ctx, ctx->shard_meta2, n * 8))) return rc;
-    u64 *q = (u64 *) ctx->shard_meta2.p;
-    a.hist2 = q; q += nparts;          // first: begin() zeroes exactly this part
-    a.off2 = q; q += nparts + 1;
-    a.cur2 = q; q += nparts;
-    a.cur1 = q; q += kMaxDigits + 2;
-    a.loc_off = q; q += kMaxDigits + 2;
-    a.seg_off = q; q += kMaxDigits + 2;
-    a.off1 = q; q += kMaxDigits + 2;
-    a.tile0 = (u32 *) q;               // (kMaxDigits + 2) u32 fit the remaining kMaxDigits + 2 u64... sized above with slack
-    a.out = &ctx->bufB3;
+    if (slot < 0 || slot > 1) return RHJ_ERR_ARG;
+    a = SlotArrays{m.cur1[slot], sm.loc_off[slot], sm.seg_off[slot], m.off1[slot], m.hist2[slot], m.cur2[slot], m.off2[slot],
+                   m.tile0[slot], slot ? &ctx->bufB2 : &ctx->bufB};
     return RHJ_OK;
 }
 
@@ -1584,9 +1417,6 @@ int rhj_shardx_begin(rhj_ctx *ctx, const rhj_shard_plan *sp, void *stream) {
     int rc;
     if ((rc = layout_meta(ctx, 1u << sp->bits_total, m))) return rc;
     CK(cudaMemsetAsync(ctx->zero.p, 0, m.zero_bytes, st));
-    SlotArrays s2;
-    if ((rc = slot_arrays(ctx, 1u << sp->bits_total, 2, s2))) return rc;
-    CK(cudaMemsetAsync(s2.hist2, 0, ((size_t) 1 << sp->bits_total) * 8, st));
     ctx->shard_n[0] = ctx->shard_n[1] = ctx->shard_n[2] = 0;
     ctx->shard_cap[0] = ctx->shard_cap[1] = ctx->shard_cap[2] = 0;
     ctx->shard_poisson[0] = ctx->shard_poisson[1] = ctx->shard_poisson[2] = false;
@@ -1594,31 +1424,22 @@ int rhj_shardx_begin(rhj_ctx *ctx, const rhj_shard_plan *sp, void *stream) {
     return RHJ_OK;
 }
 
-// Pass 1 of slot `rel` (0 = R, 1 = S, 2 = second half of the probe relation): histogram on
+// Pass 1 of relation `rel` (0 = R, 1 = S): histogram on
 // (destination rank | sub-digit) into d_hist[world << bits_pass1] (the caller all-gathers it), prefix
 // sum, scatter into the local staging buffer d_stage[n], which ends up ordered by destination rank,
 // then by pass-1 partition.  Enqueues only.
-static int shardx_pass1_impl(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_in, uint64_t n,
-                             rhj_tuple *d_stage, uint64_t *d_stage_val, uint32_t *d_stage_rid, uint64_t *d_hist,
-                             void *stream) {
-    if (!ctx || !sp || !d_hist || rel < 0 || rel > 2 || (n && (!d_in || (!d_stage && (!d_stage_val || !d_stage_rid)))))
-        return RHJ_ERR_ARG;
+int rhj_shardx_pass1_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_in, uint64_t n,
+                            rhj_tuple *d_stage, uint64_t *d_hist, void *stream) {
+    if (!ctx || !sp || !d_hist || rel < 0 || rel > 1 || (n && (!d_in || !d_stage))) return RHJ_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = pick(ctx, stream);
     SlotArrays sl;
-    Meta m;
     int rc;
     if ((rc = slot_arrays(ctx, 1u << sp->bits_total, rel, sl))) return rc;
-    if ((rc = layout_meta(ctx, 1u << sp->bits_total, m))) return rc;
     PartArgs a = shard_args(sp);
     a.shard_local = 1;
-    a.overflow = (u32 *) (m.scalars + kScWideKey);
     CK(cudaMemsetAsync(d_hist, 0, (size_t) a.ndig * sizeof(u64), st));
     a.rel[0] = PartRel{(const Tup *) d_in, (Tup *) d_stage, n, (u64 *) d_hist, sl.cur1, nullptr, nullptr, 1, tiles_of(n)};
-    if (!d_stage) {  // 12-byte staging: values and 32-bit row ids in two arrays
-        a.rel[0].out_val = (u64 *) d_stage_val;
-        a.rel[0].out_rid = d_stage_rid;
-    }
     if (rel == 0) mark(ctx, st, RHJ_PHASE_HIST1);
     if ((rc = launch_hist(ctx, st, a, kDigitShard, false))) return rc;
     ScanDigitsArgs sd{};
@@ -1630,23 +1451,7 @@ static int shardx_pass1_impl(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, co
     k_scan_digits<<<1, kMaxDigits, 0, st>>>(sd);
     CK(cudaGetLastError());
     ctx->info.kernel_launches++;
-    if ((rc = launch_scatter(ctx, st, a, kDigitShard, false))) return rc;
-    return RHJ_OK;
-}
-
-int rhj_shardx_pass1_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_in, uint64_t n,
-                            rhj_tuple *d_stage, uint64_t *d_hist, void *stream) {
-    if (n && !d_stage) return RHJ_ERR_ARG;
-    return shardx_pass1_impl(ctx, sp, rel, d_in, n, d_stage, nullptr, nullptr, d_hist, stream);
-}
-
-// Same, staging the tuples as 12 bytes: d_stage_val[n] (u64 values) + d_stage_rid[n] (u32 row ids).  The
-// caller promises that every row id fits 32 bits (relation cardinality < 2^32); a wider one is reported
-// by the join call as RHJ_ERR_ARG.  25 % fewer bytes cross NVLink.
-int rhj_shardx_pass1_soa_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_in, uint64_t n,
-                                uint64_t *d_stage_val, uint32_t *d_stage_rid, uint64_t *d_hist, void *stream) {
-    if (n && (!d_stage_val || !d_stage_rid)) return RHJ_ERR_ARG;
-    return shardx_pass1_impl(ctx, sp, rel, d_in, n, nullptr, d_stage_val, d_stage_rid, d_hist, stream);
+    return launch_scatter(ctx, st, a, kDigitShard, false);
 }
 
 // Layout of slot `rel` from the all-gathered histograms d_all_hist[world][world << bits_pass1]:
@@ -1658,7 +1463,7 @@ int rhj_shardx_pass1_soa_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel,
 int rhj_shardx_layout_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rank, int rel, const uint64_t *d_all_hist,
                              uint64_t *send_off, uint64_t *send_cnt, uint64_t *dst_off, uint64_t *recv_total,
                              void *stream) {
-    if (!ctx || !sp || !d_all_hist || !send_off || !send_cnt || !dst_off || !recv_total || rel < 0 || rel > 2 || rank < 0 ||
+    if (!ctx || !sp || !d_all_hist || !send_off || !send_cnt || !dst_off || !recv_total || rel < 0 || rel > 1 || rank < 0 ||
         rank >= (int) sp->world)
         return RHJ_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -1714,10 +1519,9 @@ int rhj_shardx_layout_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rank, i
 
 // Pass 2 of slot `rel` over what this rank received (d_recv[n_recv], world << bits_pass1 pieces):
 // histogram, per-partition offsets, scatter into the slot's final partition buffer.  Enqueues only.
-static int shardx_pass2_impl(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_recv,
-                             const uint64_t *d_recv_val, const uint32_t *d_recv_rid, uint64_t n_recv, void *stream,
+static int shardx_pass2_impl(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_recv, uint64_t n_recv, void *stream,
                              bool allow_fixed = true) {
-    if (!ctx || !sp || rel < 0 || rel > 2 || (n_recv && !d_recv && (!d_recv_val || !d_recv_rid))) return RHJ_ERR_ARG;
+    if (!ctx || !sp || rel < 0 || rel > 1 || (n_recv && !d_recv)) return RHJ_ERR_ARG;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = pick(ctx, stream);
     SlotArrays sl;
@@ -1725,8 +1529,6 @@ static int shardx_pass2_impl(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, co
     const u32 nparts = 1u << sp->bits_total;
     if ((rc = slot_arrays(ctx, nparts, rel, sl))) return rc;
     ctx->shard_recv[rel] = (const Tup *) d_recv;
-    ctx->shard_recv_val[rel] = (const u64 *) d_recv_val;
-    ctx->shard_recv_rid[rel] = d_recv_rid;
     // histogram-free second pass (fixed-capacity final partitions) when the received sizes look Poisson.  On by default
     // only where it was measured to help: 8.29 -> 7.49 ms per join on 2 GPUs; the one run on 8 GPUs that the round's GPU
     // budget allowed gave 12.2 instead of 10.3-10.6 ms, 4 GPUs are unmeasured (profiles/r01_multi_gpu_notes.md).
@@ -1750,10 +1552,6 @@ static int shardx_pass2_impl(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, co
     b.rel[0] = PartRel{(const Tup *) d_recv, (Tup *) sl.out->p, n_recv, sl.hist2, sl.cur2, sl.seg_off, sl.tile0,
                        npieces, tiles_of(n_recv) + npieces, nd1 - 1};
     if (nd1 == 1) b.rel[0].group_mask = 0x80000000u;  // every piece is partition 0: (seg & mask) == 0
-    if (!d_recv) {  // received as 12-byte SoA; the final partitions are 16-byte tuples again
-        b.rel[0].in_val = (const u64 *) d_recv_val;
-        b.rel[0].in_rid = d_recv_rid;
-    }
     if ((rc = build_tile_tables(ctx, st, b, 1, rel))) return rc;
     if (fixed) {
         Meta m;
@@ -1791,23 +1589,14 @@ static int shardx_pass2_impl(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, co
 
 int rhj_shardx_pass2_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const rhj_tuple *d_recv, uint64_t n_recv,
                             void *stream) {
-    if (n_recv && !d_recv) return RHJ_ERR_ARG;
-    return shardx_pass2_impl(ctx, sp, rel, d_recv, nullptr, nullptr, n_recv, stream);
+    return shardx_pass2_impl(ctx, sp, rel, d_recv, n_recv, stream);
 }
 
-int rhj_shardx_pass2_soa_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, const uint64_t *d_recv_val,
-                                const uint32_t *d_recv_rid, uint64_t n_recv, void *stream) {
-    if (n_recv && (!d_recv_val || !d_recv_rid)) return RHJ_ERR_ARG;
-    return shardx_pass2_impl(ctx, sp, rel, nullptr, d_recv_val, d_recv_rid, n_recv, stream);
-}
-
-// Work-item plan + build/probe + fused emit over the final partitions of a (build slot, probe slot)
-// pair.  `first` = 1 starts a new result (the output cursor is reset); 0 appends to it, which is how
-// the two halves of a probe relation are joined one after the other.  *count = pairs emitted so far.
-int rhj_shardx_join_slots_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int build_slot, int probe_slot, int first,
-                                 rhj_pair *d_out, uint64_t capacity, uint64_t *count, void *stream) {
-    if (!ctx || !sp || !count || build_slot < 0 || build_slot > 2 || probe_slot < 0 || probe_slot > 2 || build_slot == probe_slot)
-        return RHJ_ERR_ARG;
+// Work-item plan + build/probe + fused emit over the final partitions of both relations (slots 0 = R, 1 = S).
+int rhj_shardx_join_device(rhj_ctx *ctx, const rhj_shard_plan *sp, rhj_pair *d_out, uint64_t capacity, uint64_t *count,
+                           void *stream) {
+    if (!ctx || !sp || !count) return RHJ_ERR_ARG;
+    const int build_slot = sp->build_is_S ? 1 : 0, probe_slot = build_slot ^ 1;
     CK(cudaSetDevice(ctx->device));
     cudaStream_t st = pick(ctx, stream);
     const u64 nB = ctx->shard_n[build_slot], nP = ctx->shard_n[probe_slot];
@@ -1818,7 +1607,7 @@ int rhj_shardx_join_slots_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int bui
     if ((rc = layout_meta(ctx, nparts, m))) return rc;
     if ((rc = slot_arrays(ctx, nparts, build_slot, sb))) return rc;
     if ((rc = slot_arrays(ctx, nparts, probe_slot, spb))) return rc;
-    if (first) ctx->shard_count = 0;
+    ctx->shard_count = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {  // attempt 1 = after a fixed-capacity second pass overflowed
         // per-launch scalars start from zero; the output cursor restarts where the previous join of this step ended
         CK(cudaMemsetAsync(m.scalars + kScWork0, 0, 8, st));
@@ -1857,7 +1646,6 @@ int rhj_shardx_join_slots_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int bui
             ctx->cur.endP = capP ? spb.cur2 : spb.off2 + 1;
             ctx->cur.nparts = nparts;
             ctx->cur.item_cap = item_cap;
-            // slot 0 is R; slots 1 and 2 hold S tuples unless S is the (unsplit) build side
             ctx->cur.build_is_S = build_slot != 0;
             ctx->info.optimistic_pass1 = (capB ? 4u : 0u) | (capP ? 8u : 0u);
             JoinArgs j = join_args(ctx, kScWork0);
@@ -1873,11 +1661,9 @@ int rhj_shardx_join_slots_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int bui
         // the exact histogram path -- what they received is still in place -- and join again.
         CK(cudaMemsetAsync(m.scalars + kScOverflow, 0, 8, st));
         ctx->opt2_skip = 16;
-        for (int sl = 0; sl < 3; ++sl) {  // every slot partitioned so far: the flag does not say which one overflowed
+        for (int sl = 0; sl < 2; ++sl) {  // both relations: the flag does not say which one overflowed
             if (!ctx->shard_cap[sl]) continue;
-            if ((rc = shardx_pass2_impl(ctx, sp, sl, (const rhj_tuple *) ctx->shard_recv[sl], (const uint64_t *) ctx->shard_recv_val[sl],
-                                        ctx->shard_recv_rid[sl], ctx->shard_n[sl], stream, false)))
-                return rc;
+            if ((rc = shardx_pass2_impl(ctx, sp, sl, (const rhj_tuple *) ctx->shard_recv[sl], ctx->shard_n[sl], stream, false))) return rc;
         }
     }
     if (rc == kRetryExact) return fail(ctx, RHJ_ERR_STATE, "sharded join: overflow flag set on the exact path");
@@ -1886,14 +1672,6 @@ int rhj_shardx_join_slots_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int bui
     if (*count > capacity) return fail(ctx, RHJ_ERR_CAPACITY, "output buffer too small for the fused emitter");
     ctx->shard_count = *count;
     return RHJ_OK;
-}
-
-// Both relations whole: slots 0 (R) and 1 (S).
-int rhj_shardx_join_device(rhj_ctx *ctx, const rhj_shard_plan *sp, rhj_pair *d_out, uint64_t capacity, uint64_t *count,
-                           void *stream) {
-    if (!sp) return RHJ_ERR_ARG;
-    const int bi = sp->build_is_S ? 1 : 0;
-    return rhj_shardx_join_slots_device(ctx, sp, bi, bi ^ 1, 1, d_out, capacity, count, stream);
 }
 
 }  // extern "C"

@@ -33,7 +33,6 @@ enum Scalar {
     kScDigXor = 7,
     kScFilt = 8,
     kScOverflow = 9,  // optimistic pass 1: a partition outgrew its fixed-capacity region
-    kScWideKey = 10,  // 12-byte shipping: a row id did not fit 32 bits
     kScPipeStatus = 11,  // pipelined exchange: RHJ_PIPE_* bits of this step, own and received
     kScCount = 16
 };
@@ -50,13 +49,12 @@ struct rhj_ctx {
     int opt2_skip = 0;        // joins left to run without the pass-2 shortcut after it overflowed (duplicate-heavy data)
     DevBuf sample;            // sampled pass-1 histogram
     int scatter_mode = 0;     // 0 staged per-thread stores, 1 TMA bulk stores (RHJ_SCATTER_MODE)
-    int shard_scatter_mode = 1;  // same choice for the fused partition+shuffle pass: bulk stores make
-                                 // larger NVLink packets (measured 4.85 vs 5.17 ms at N=2) (RHJ_SHARD_SCATTER_MODE)
+    int shard_scatter_mode = 1;  // same choice for pass 1 of the exact sharded exchange (local staging): bulk stores were
+                                 // measured faster for its 1024-digit runs (RHJ_SHARD_SCATTER_MODE)
 
     DevBuf bufA, bufB;        // pass-1 / pass-2 partitioned tuples (build side first, then probe side)
     DevBuf tiles;             // TileDesc tables of the second pass (both relations)
-    DevBuf bufB2, bufB3;      // sharded join: pass-2 outputs of slots 1 and 2 (relations / probe halves arrive separately)
-    DevBuf shard_meta2;       // sharded join: metadata of slot 2 (second half of the probe relation)
+    DevBuf bufB2;             // sharded join: pass-2 output of relation S (the relations arrive separately)
     DevBuf shard_meta;        // sharded join: local offsets, piece tables, ship matrix
     DevBuf zero;              // hist1 | hist2 | scalars   (memset to 0 per call)
     DevBuf meta;              // offsets, cursors, tile tables
@@ -96,8 +94,6 @@ struct rhj_ctx {
     rhj_plan_info info{};
     u64 shard_n[3] = {0, 0, 0};            // sharded join: tuples received per slot
     const Tup *shard_recv[3] = {nullptr, nullptr, nullptr};
-    const u64 *shard_recv_val[3] = {nullptr, nullptr, nullptr};   // 12-byte form of the same
-    const u32 *shard_recv_rid[3] = {nullptr, nullptr, nullptr};
     bool shard_poisson[3] = {false, false, false};  // the received pass-1 partition sizes look like hashed distinct keys
     u64 shard_cap[3] = {0, 0, 0};                   // > 0: the slot's final partitions lie in fixed-capacity regions of this size
     u64 shard_count = 0;                            // pairs emitted by the joins of this sharded step so far
@@ -133,7 +129,7 @@ struct rhj_ctx {
 
 template <typename F>
 inline void for_each_buf(rhj_ctx *c, F f) {
-    DevBuf *bufs[] = {&c->bufA, &c->bufB, &c->tiles, &c->sample, &c->bufB2, &c->bufB3, &c->shard_meta2, &c->shard_meta, &c->zero, &c->meta, &c->items, &c->item_cnt, &c->item_off, &c->filt_cnt,
+    DevBuf *bufs[] = {&c->bufA, &c->bufB, &c->tiles, &c->sample, &c->bufB2, &c->shard_meta, &c->zero, &c->meta, &c->items, &c->item_cnt, &c->item_off, &c->filt_cnt,
                       &c->filt_off, &c->filt_tmp, &c->inR, &c->inS, &c->outP, &c->pin[0], &c->pin[1], &c->pout[0], &c->pout[1],
                       &c->pA, &c->pB, &c->iu_col, &c->iu_pairs, &c->iu_A,
                       &c->iu_B, &c->iu_ep, &c->iu_out, &c->pipe.stage[0], &c->pipe.stage[1], &c->pipe.cursors, &c->pipe.segs,

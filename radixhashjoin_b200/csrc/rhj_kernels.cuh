@@ -57,31 +57,16 @@ struct PartRel {
     const void *tiles;     // SEG: optional TileDesc[ntiles] built by k_tile_table (else binary search)
     const u64 *seg_end;    // SEG: optional [nseg] segment ends (null: seg_off[seg + 1]); fixed-capacity pass-1 layout
     u64 limit_cap;         // k_scatter<LIMIT>: digit d may only fill [d * limit_cap, (d + 1) * limit_cap) of `out`
-    // 12-byte SoA form of a relation {u64 value, u32 row id} (multi-GPU shipping: -25 % NVLink bytes):
-    const u64 *in_val;     // input when `in` is null
-    const u32 *in_rid;
-    u64 *out_val;          // output when `out` is null (non-peer scatter only)
-    u32 *out_rid;
     const unsigned char *in_packed;  // kIoPacked12In: record i at byte 12 * i
     // k_scatter<LIMIT>: a run that does not fit its partition's region is written to the kTile tuples at out[dump..]
     // instead (nothing out of bounds, no per-tuple check); the overflow flag makes the host discard the attempt.
     u64 dump;
     Tup *dump_ptr;         // same, as an absolute address, for scatters whose output base depends on the digit (peer_out)
 };
-// tuple idx of a relation in either form
-// How a partitioning kernel reads / writes tuples: 16-byte AoS both ways (everything single-GPU), or the
-// 12-byte form the DMA-shipped sharded join puts on the wire ({u64 value}[n] + {u32 row id}[n]) on one side.
+// How a partitioning kernel reads tuples: 16-byte AoS (everything single-GPU, pass 1 of the sharded joins), or
 // kIoPacked12In: packed 12-byte records {u64 value, u32 row id} -- the wire format of the pipelined exchange
 // (rhj_pipe_kernels.cuh); a tile is fetched with one TMA bulk copy and unpacked from shared memory.
-enum TupleIo { kIoAos = 0, kIoSoaIn = 1, kIoSoaOut = 2, kIoPacked12In = 3 };
-template <int IO>
-__device__ __forceinline__ Tup ld_tuple(const PartRel &r, u64 idx) {
-    if (IO != kIoSoaIn) return ld_stream(r.in + idx);
-    Tup t;
-    t.key = __ldg(r.in_rid + idx);
-    t.val = __ldg(r.in_val + idx);
-    return t;
-}
+enum TupleIo { kIoAos = 0, kIoPacked12In = 1 };
 // One 16-byte descriptor per pass-2 tile (k_tile_table): a CTA finds its tuple range with ONE load
 // instead of a 9-step binary search over seg_tile0 -- that dependent-load chain sat in front of
 // every tile's first tuple load.
@@ -165,7 +150,7 @@ __global__ void __launch_bounds__(256) k_tile_table(const u64 *seg_off, const u6
 // first by match.any so a skewed digit costs one atomic per warp instead of 32 serialised ones)
 // and flushes to the global u64 counters only when its (relation, segment) changes.
 // Algorithmic bytes: 16 per tuple read.
-template <int KIND, bool SEG, bool AGG, int IO = kIoAos>
+template <int KIND, bool SEG, bool AGG>
 __global__ void __launch_bounds__(kPartThreads) k_hist(PartArgs a) {
     __shared__ u32 s_h[kMaxDigits];
     const u32 tid = threadIdx.x;
@@ -199,10 +184,7 @@ __global__ void __launch_bounds__(kPartThreads) k_hist(PartArgs a) {
         for (int j = 0; j < kPartItems; ++j) {
             u64 idx = beg + (u64) j * kPartThreads + tid;
             ok[j] = idx < end;
-            if (ok[j]) {
-                if (IO != kIoSoaIn) v[j] = ld_stream(r.in + idx);
-                else v[j].val = __ldg(r.in_val + idx);  // the histogram only needs the value: 8 bytes per tuple
-            }
+            if (ok[j]) v[j] = ld_stream(r.in + idx);
         }
 #pragma unroll
         for (int j = 0; j < kPartItems; ++j) {
@@ -339,7 +321,7 @@ __global__ void __launch_bounds__(THREADS, THREADS == kPartThreads ? RHJ_PART_MI
 #pragma unroll
         for (int j = 0; j < kPartItems; ++j) {
             u32 i = j * THREADS + tid;
-            if (i < ntile) v[j] = ld_tuple<IO>(r, beg + i);
+            if (i < ntile) v[j] = ld_stream(r.in + beg + i);
         }
     }
     __syncthreads();
@@ -425,79 +407,10 @@ __global__ void __launch_bounds__(THREADS, THREADS == kPartThreads ? RHJ_PART_MI
                 Tup t = s_tup[i];
                 u32 d = digit<KIND>(t.val, a);
                 Tup *ob = (KIND == kDigitShard && !a.shard_local) ? a.peer_out[ri][0] : r.out;
-                if (IO != kIoSoaOut) {
-                    st_stream(ob + s_delta[d] + i, t);
-                } else {  // 12-byte SoA output; a row id that does not fit 32 bits is an error the host reports
-                    if (t.key >> 32) *a.overflow = 2;
-                    r.out_val[s_delta[d] + i] = t.val;
-                    r.out_rid[s_delta[d] + i] = (u32) t.key;
-                }
+                st_stream(ob + s_delta[d] + i, t);
             }
         }
     }
-    }
-}
-
-// Fused partition + shuffle bookkeeping.  all_hist[src][rel][dest << sub_bits | p1] are the pass-1
-// histograms of every rank (all-gathered).  For relation `rel` (one CTA each) this rank gets
-//   - as a DESTINATION: off1[p1] / tile table of what it will receive (pass-1 partition p1 holds
-//     the runs of all sources, source-major), and the received total;
-//   - as a SOURCE: its private write cursor inside every destination's partition p1
-//     (= that destination's off1[p1] + what lower-ranked sources put there), so the scatter needs
-//     no cross-GPU atomics.
-struct ShardOffsetsArgs {
-    const u64 *all_hist;   // [world][2][world << sub_bits]
-    u64 *cursor[2];        // [world << sub_bits] source-side cursors
-    u64 *off1[2];          // [(1 << sub_bits) + 1] destination-side pass-1 offsets
-    u32 *tile0[2];         // [(1 << sub_bits) + 1] first pass-2 tile of each pass-1 partition
-    u64 *recv_total;       // [2]
-    u32 world, rank;
-    int sub_bits;
-};
-__global__ void __launch_bounds__(kMaxDigits) k_shard_offsets(ShardOffsetsArgs a) {
-    __shared__ u64 s_w[32];
-    __shared__ u32 s_wt[32];
-    const int rel = blockIdx.x;
-    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const u32 nd1 = 1u << a.sub_bits, ndig = a.world << a.sub_bits;
-    for (u32 dest = 0; dest < a.world; ++dest) {
-        u64 tot = 0, before_me = 0;   // over sources, for (dest, p1 = tid)
-        if (tid < nd1) {
-            for (u32 src = 0; src < a.world; ++src) {
-                u64 c = a.all_hist[((u64) src * 2 + rel) * ndig + (dest << a.sub_bits) + tid];
-                if (src < a.rank) before_me += c;
-                tot += c;
-            }
-        }
-        u32 tl = (u32) ((tot + kTile - 1) / kTile);
-        u64 inc = warp_incl_scan64(tot);
-        u32 tinc = warp_incl_scan(tl);
-        if (lane == 31) { s_w[warp] = inc; s_wt[warp] = tinc; }
-        __syncthreads();
-        if (warp == 0) {
-            u64 w = s_w[lane];
-            u32 wt = s_wt[lane];
-            u64 wi = warp_incl_scan64(w);
-            u32 wti = warp_incl_scan(wt);
-            s_w[lane] = wi - w;
-            s_wt[lane] = wti - wt;
-        }
-        __syncthreads();
-        u64 ex = inc - tot + s_w[warp];
-        u32 tex = tinc - tl + s_wt[warp];
-        if (tid < nd1) {
-            a.cursor[rel][(dest << a.sub_bits) + tid] = ex + before_me;
-            if (dest == a.rank) {
-                a.off1[rel][tid] = ex;
-                a.tile0[rel][tid] = tex;
-                if (tid == nd1 - 1) {
-                    a.off1[rel][nd1] = ex + tot;
-                    a.tile0[rel][nd1] = tex + tl;
-                    a.recv_total[rel] = ex + tot;
-                }
-            }
-        }
-        __syncthreads();
     }
 }
 

@@ -102,52 +102,6 @@ def cpu_partition_by_rank(T, world):
     return torch.from_numpy(a[order].view(np.int64).copy()), counts
 
 
-class FusedShardedJoin:
-    """Multi-GPU join with the exchange FUSED into pass 1 (rhj_shard_* in include/rhj.h).
-
-    Every rank owns two receive buffers in symmetric (peer-mapped) memory.  Pass 1 of the join
-    partitions on (destination rank | sub-digit) and its scatter kernel stores each run directly
-    into the destination's receive buffer over NVLink / NVSwitch -- no separate shuffle pass, no
-    staging copy, and the transfer overlaps the scatter tile by tile.  torch.distributed supplies
-    the plumbing: one all-gather of the 2 x (world << bits) histograms, symmetric-memory rendezvous
-    for the peer pointers, and two device-side barriers per join.
-    """
-
-    def __init__(self, engine, world, rank, nR_global, nS_global, recv_capacity, group=None):
-        import torch
-        import torch.distributed as dist
-        import torch.distributed._symmetric_memory as symm_mem
-        self.torch, self.dist = torch, dist
-        self.engine, self.world, self.rank = engine, world, rank
-        self.group = group if group is not None else dist.group.WORLD
-        self.plan = engine.shard_plan(nR_global, nS_global, world)
-        dev = torch.device("cuda", engine.device)
-        self.recvR = symm_mem.empty((recv_capacity, 2), dtype=torch.int64, device=dev)
-        self.recvS = symm_mem.empty((recv_capacity, 2), dtype=torch.int64, device=dev)
-        self.hR = symm_mem.rendezvous(self.recvR, self.group)
-        self.hS = symm_mem.rendezvous(self.recvS, self.group)
-        self.peers_R = [int(p) for p in self.hR.buffer_ptrs]
-        self.peers_S = [int(p) for p in self.hS.buffer_ptrs]
-        ndig = world << self.plan.bits_pass1
-        self.hist = torch.empty((2, ndig), dtype=torch.int64, device=dev)
-        self.all_hist = torch.empty((world, 2, ndig), dtype=torch.int64, device=dev)
-        self.capacity = recv_capacity
-
-    def step(self, R_local, S_local, out):
-        """One sharded join; returns (pairs, count, (received nR, nS))."""
-        eng, plan = self.engine, self.plan
-        eng.shard_histogram(plan, R_local, S_local, self.hist)
-        self.dist.all_gather_into_tensor(self.all_hist, self.hist, group=self.group)
-        nR, nS = eng.shard_offsets(plan, self.rank, self.all_hist)
-        if max(nR, nS) > self.capacity:
-            raise RuntimeError(f"rank {self.rank}: receive buffer too small ({max(nR, nS)} > {self.capacity})")
-        self.hR.barrier(channel=0)       # every rank is done reading its receive buffers (previous join)
-        eng.shard_scatter(plan, R_local, S_local, self.peers_R, self.peers_S)
-        self.hR.barrier(channel=1)       # every rank's stores have landed
-        pairs, count = eng.shard_join(plan, self.recvR[:nR], self.recvS[:nS], out)
-        return pairs, count, (nR, nS)
-
-
 def broadcast_is_cheaper(nR_global, nS_global, world):
     """Exchange strategy of a sharded join (skew / small-build caveat): replicating the build side
     costs every rank nB * (world - 1) / world tuples in, shuffling both sides (nB + nP) * (world - 1) / world^2;
@@ -312,28 +266,18 @@ class PipeShardedJoin:
 
 
 class DmaShardedJoin:
-    """Multi-GPU join, DMA-shipped (rhj_shardx_* in include/rhj.h): the default at N > 1.
+    """Multi-GPU join over the EXACT exchange (rhj_shardx_* in include/rhj.h): what PipeShardedJoin falls back to when a
+    fixed-capacity region overflows (skewed or duplicate-heavy inputs), and the r01 default.
 
-    Pass 1 of the join partitions each local shard on (destination rank | sub-digit) into a local
-    staging buffer; the chunk for every destination is contiguous and already pass-1 partitioned, so
-    the copy engines ship it with ONE peer copy per destination over NVLink / NVSwitch (full-size
-    packets, no SM time) straight into the destination's symmetric receive buffer.  The pipeline per
-    join: the build relation is partitioned and shipped first; the probe relation is partitioned while
-    it is in flight and shipped next; pass 2 of a relation runs as soon as it has landed, i.e. while the
-    other one is still on the wire.  With split_probe=True the probe relation goes in two row halves
-    (slots) and the first half is joined while the second is in flight -- implemented and verified, but
-    measured slower on 2 and 8 B200s (the extra kernels slow the concurrent peer copies and every half
-    re-builds the tables), so it is off by default.  torch.distributed supplies the plumbing: one small
-    all-gather per slot (histograms), symmetric-memory rendezvous for the peer buffers, device-side barriers.
-
-    compact_rowids=True ships 12 bytes per tuple instead of 16 ({u64 value} and {u32 row id} arrays, two peer
-    copies per destination): the link is the bottleneck at N > 2, so 25 % fewer bytes is ~25 % less exchange
-    time.  The caller promises that row ids fit 32 bits (any relation under 2^32 rows); the kernels check and
-    the join call fails otherwise.
+    Pass 1 of the join partitions each local shard on (destination rank | sub-digit) into a local staging buffer after an
+    exact histogram; the chunk for every destination is contiguous and already pass-1 partitioned, so the copy engines
+    ship it with ONE peer copy per destination over NVLink / NVSwitch straight into the destination's symmetric receive
+    buffer.  The build relation is partitioned and shipped first; the probe relation is partitioned while it is in flight
+    and shipped next; pass 2 of a relation runs as soon as it has landed.  torch.distributed supplies the plumbing: one
+    small all-gather per relation (histograms), symmetric-memory rendezvous for the peer buffers, device-side barriers.
     """
 
-    def __init__(self, engine, world, rank, nR_global, nS_global, n_local_max, recv_capacity, group=None,
-                 split_probe=False, compact_rowids=False):
+    def __init__(self, engine, world, rank, nR_global, nS_global, n_local_max, recv_capacity, group=None):
         import os
         import torch
         import torch.distributed as dist
@@ -344,48 +288,24 @@ class DmaShardedJoin:
         self.plan = engine.shard_plan(nR_global, nS_global, world)
         self.build_rel = 1 if self.plan.build_is_S else 0
         self.probe_rel = 1 - self.build_rel
-        self.split = bool(split_probe)
-        # slots in shipping order: build relation, probe relation (first half), probe second half
-        self.slots = [self.build_rel, self.probe_rel] + ([2] if self.split else [])
+        self.slots = [self.build_rel, self.probe_rel]      # shipping order
         dev = torch.device("cuda", engine.device)
-        cap = {s: recv_capacity for s in self.slots}
-        stage_n = {s: n_local_max for s in self.slots}
-        if self.split:
-            for s in (self.probe_rel, 2):
-                cap[s] = recv_capacity // 2 + 4096
-                stage_n[s] = n_local_max // 2 + 1
-        self.capacity = cap
-        self.compact = bool(compact_rowids)
-        if self.compact:
-            # one symmetric allocation per slot: cap values (8 B) followed by cap row ids (4 B), as int32 words
-            for s in self.slots:
-                cap[s] = (cap[s] + 3) & ~3
-            self.recv = {s: symm_mem.empty((cap[s] * 3,), dtype=torch.int32, device=dev) for s in self.slots}
-            self.hdl = {s: symm_mem.rendezvous(self.recv[s], self.group) for s in self.slots}
-            self.recv_val = {s: self.recv[s][:cap[s] * 2].view(torch.int64) for s in self.slots}
-            self.recv_rid = {s: self.recv[s][cap[s] * 2:] for s in self.slots}
-            peer = {s: [self.hdl[s].get_buffer(p, (cap[s] * 3,), torch.int32) for p in range(world)] for s in self.slots}
-            self.peer_val = {s: [b[:cap[s] * 2].view(torch.int64) for b in peer[s]] for s in self.slots}
-            self.peer_rid = {s: [b[cap[s] * 2:] for b in peer[s]] for s in self.slots}
-            self.stage_val = {s: torch.empty(stage_n[s], dtype=torch.int64, device=dev) for s in self.slots}
-            self.stage_rid = {s: torch.empty(stage_n[s], dtype=torch.int32, device=dev) for s in self.slots}
-        else:
-            self.recv = {s: symm_mem.empty((cap[s], 2), dtype=torch.int64, device=dev) for s in self.slots}
-            self.hdl = {s: symm_mem.rendezvous(self.recv[s], self.group) for s in self.slots}
-            self.peer = {s: [self.hdl[s].get_buffer(p, (cap[s], 2), torch.int64) for p in range(world)] for s in self.slots}
-            self.stage = {s: torch.empty((stage_n[s], 2), dtype=torch.int64, device=dev) for s in self.slots}
+        self.capacity = {s: recv_capacity for s in self.slots}
+        self.recv = {s: symm_mem.empty((recv_capacity, 2), dtype=torch.int64, device=dev) for s in self.slots}
+        self.hdl = {s: symm_mem.rendezvous(self.recv[s], self.group) for s in self.slots}
+        self.peer = {s: [self.hdl[s].get_buffer(p, (recv_capacity, 2), torch.int64) for p in range(world)] for s in self.slots}
+        self.stage = {s: torch.empty((n_local_max, 2), dtype=torch.int64, device=dev) for s in self.slots}
         ndig = world << self.plan.bits_pass1
         self.hist = {s: torch.empty(ndig, dtype=torch.int64, device=dev) for s in self.slots}
         self.all_hist = {s: torch.empty((world, ndig), dtype=torch.int64, device=dev) for s in self.slots}
         self.copy_stream = torch.cuda.Stream(device=dev)
-        # a few copy lanes: the peer copies of a slot run on different copy engines (measured on
-        # 8 x B200: 1 lane 10.6 ms/join, 2 lanes 10.7, 4 lanes 13.9, 8 lanes 14.6 -- too many concurrent
-        # flows through the switch collapse)
+        # a few copy lanes: the peer copies of a relation run on different copy engines (measured on 8 x B200: 1 lane
+        # 10.6 ms/join, 2 lanes 10.7, 4 lanes 13.9, 8 lanes 14.6 -- too many concurrent flows through the switch collapse)
         lanes = int(os.environ.get("RHJ_COPY_LANES", "2"))
         self.peer_streams = [torch.cuda.Stream(device=dev) for _ in range(max(1, min(world, lanes)))]
 
     def _ship(self, slot, lay, marks=None):
-        """peer copies of one slot on the copy stream, fenced by device-side barriers"""
+        """peer copies of one relation on the copy stream, fenced by device-side barriers"""
         torch = self.torch
         send_off, send_cnt, dst_off, _ = lay
         cs = self.copy_stream
@@ -403,11 +323,7 @@ class DmaShardedJoin:
                     ps.wait_event(fork)
                     a, b, n = dst_off[d], send_off[d], send_cnt[d]
                     with torch.cuda.stream(ps):
-                        if self.compact:
-                            self.peer_val[slot][d][a:a + n].copy_(self.stage_val[slot][b:b + n], non_blocking=True)
-                            self.peer_rid[slot][d][a:a + n].copy_(self.stage_rid[slot][b:b + n], non_blocking=True)
-                        else:
-                            self.peer[slot][d][a:a + n].copy_(self.stage[slot][b:b + n], non_blocking=True)
+                        self.peer[slot][d][a:a + n].copy_(self.stage[slot][b:b + n], non_blocking=True)
                     cs.wait_stream(ps)
             if marks is not None:
                 marks.append((f"dma{slot}_sent", self._mark(cs)))
@@ -427,43 +343,29 @@ class DmaShardedJoin:
         """One sharded join; returns (pairs, count, (received build, received probe)).  `marks` (a list)
         collects (label, CUDA event) pairs for a timeline of the step."""
         torch, eng, plan = self.torch, self.engine, self.plan
-        rels = (R_local, S_local)
-        B, P = rels[self.build_rel], rels[self.probe_rel]
-        half = (P.shape[0] + 1) // 2 if self.split else P.shape[0]
-        src = {self.build_rel: B, self.probe_rel: P[:half]}
-        if self.split:
-            src[2] = P[half:]
+        src = {0: R_local, 1: S_local}
         if marks is not None:
             marks.append(("start", self._mark()))
         eng.shardx_begin(plan)
         lay, landed = {}, {}
         for s in self.slots:
-            if self.compact:
-                eng.shardx_pass1_soa(plan, s, src[s], self.stage_val[s], self.stage_rid[s], self.hist[s])
-            else:
-                eng.shardx_pass1(plan, s, src[s], self.stage[s], self.hist[s])
+            eng.shardx_pass1(plan, s, src[s], self.stage[s], self.hist[s])
             if marks is not None:
                 marks.append((f"pass1_{s}_done", self._mark()))
             self.dist.all_gather_into_tensor(self.all_hist[s], self.hist[s], group=self.group)
             lay[s] = eng.shardx_layout(plan, self.rank, s, self.all_hist[s])
             if lay[s][3] > self.capacity[s]:
-                raise RuntimeError(f"rank {self.rank}: receive buffer of slot {s} too small ({lay[s][3]} > {self.capacity[s]})")
-            landed[s] = self._ship(s, lay[s], marks)         # in flight while the next slot is partitioned
-        pairs, count = out[:0], 0
-        for i, s in enumerate(self.slots):
+                raise RuntimeError(f"rank {self.rank}: receive buffer of relation {s} too small ({lay[s][3]} > {self.capacity[s]})")
+            landed[s] = self._ship(s, lay[s], marks)         # in flight while the next relation is partitioned
+        for s in self.slots:
             torch.cuda.current_stream().wait_event(landed[s])
-            if self.compact:                                     # overlaps the transfer of the slots behind it
-                eng.shardx_pass2_soa(plan, s, self.recv_val[s], self.recv_rid[s], lay[s][3])
-            else:
-                eng.shardx_pass2(plan, s, self.recv[s][:lay[s][3]])
+            eng.shardx_pass2(plan, s, self.recv[s][:lay[s][3]])   # overlaps the transfer of the relation behind it
             if marks is not None:
                 marks.append((f"pass2_{s}_done", self._mark()))
-            if i >= 1:                                           # a probe slot: join it against the build slot
-                pairs, count = eng.shardx_join_slots(plan, self.build_rel, s, i == 1, out)
-                if marks is not None:
-                    marks.append((f"join_{s}_done", self._mark()))
-        nP = sum(lay[s][3] for s in self.slots[1:])
-        return pairs, count, (lay[self.build_rel][3], nP)
+        pairs, count = eng.shardx_join(plan, out)
+        if marks is not None:
+            marks.append(("join_done", self._mark()))
+        return pairs, count, (lay[self.build_rel][3], lay[self.probe_rel][3])
 
     @staticmethod
     def timeline(marks):

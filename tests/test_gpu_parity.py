@@ -377,44 +377,7 @@ def test_reference_program_with_dropin_translation_units_edge_workload(edge_dir)
         assert out.stdout.decode() == open(os.path.join(edge_dir, "edge.result")).read()
 
 
-# ---- multi-GPU fused partition + shuffle, emulated on one GPU ---------------------------------------------
-@pytest.mark.parametrize("world,n_local,dom", [(1, 50000, 20000), (2, 60000, 50000), (4, 40000, 1 << 40), (8, 300000, 1 << 20),
-                                               (8, 700, 300)])
-def test_fused_shard_join_emulated_ranks(world, n_local, dom):
-    """rhj_shard_*: every virtual rank (its own context and receive buffers, all on cuda:0) runs the
-    fused sequence; the union of the per-rank results must equal the oracle join of the global
-    relations, and every received tuple must belong to its rank."""
-    from radixhashjoin_b200 import RadixHashJoin
-    from radixhashjoin_b200.distributed import rank_of_values
-    rng = np.random.default_rng(world * 1000 + n_local)
-    Rg, Sg = rand_rel(rng, world * n_local, dom), rand_rel(rng, world * n_local, dom, 1 << 35)
-    expect = O.sort_pairs(O.oracle_join(Rg, Sg))
-    engines = [RadixHashJoin(0) for _ in range(world)]
-    shards = [(to_dev(Rg[r * n_local:(r + 1) * n_local]), to_dev(Sg[r * n_local:(r + 1) * n_local])) for r in range(world)]
-    plan = engines[0].shard_plan(len(Rg), len(Sg), world)
-    hists = torch.stack([engines[r].shard_histogram(plan, *shards[r]) for r in range(world)])   # the all-gather
-    recv = [engines[r].shard_offsets(plan, r, hists) for r in range(world)]
-    assert sum(n for n, _ in recv) == len(Rg) and sum(n for _, n in recv) == len(Sg)
-    bufR = [torch.empty((max(n, 1), 2), dtype=torch.int64, device=DEV) for n, _ in recv]
-    bufS = [torch.empty((max(n, 1), 2), dtype=torch.int64, device=DEV) for _, n in recv]
-    for r in range(world):                                                                         # barrier; scatter
-        engines[r].shard_scatter(plan, *shards[r], [b.data_ptr() for b in bufR], [b.data_ptr() for b in bufS])
-    torch.cuda.synchronize()                                                                       # barrier
-    got = []
-    for r in range(world):
-        nR, nS = recv[r]
-        myR, myS = tuples_np(bufR[r][:nR]), tuples_np(bufS[r][:nS])
-        assert (rank_of_values(myR["payload"], world) == r).all() and (rank_of_values(myS["payload"], world) == r).all()
-        out = torch.empty((max(len(expect), 1), 2), dtype=torch.int64, device=DEV)
-        pairs, n = engines[r].shard_join(plan, bufR[r][:nR], bufS[r][:nS], out)
-        got.append(pairs_np(pairs))
-    got = np.concatenate(got)
-    assert len(got) == len(expect)
-    assert np.array_equal(O.sort_pairs(got), expect)
-    for e in engines:
-        e.close()
-
-
+# ---- multi-GPU, exact exchange (rhj_shardx_*): emulated ranks on one GPU ------------------------------------
 @pytest.mark.parametrize("world,n_local,dom", [(1, 50000, 20000), (2, 60000, 50000), (4, 40000, 1 << 40), (8, 300000, 1 << 20),
                                                (4, 500, 200), (2, 3000, 1000)])
 def test_dma_shard_join_emulated_ranks(world, n_local, dom):
@@ -460,65 +423,6 @@ def test_dma_shard_join_emulated_ranks(world, n_local, dom):
     got = np.concatenate(got)
     assert len(got) == len(expect)
     assert np.array_equal(O.sort_pairs(got), expect)
-    for e in engines:
-        e.close()
-
-
-@pytest.mark.parametrize("world,n_local,dom,id_base", [(1, 50000, 20000, 0), (2, 60000, 50000, (1 << 32) - 120000),
-                                                       (4, 40000, 1 << 40, 1 << 31), (8, 300000, 1 << 20, 7), (4, 500, 200, 0),
-                                                       (2, 3000, 1000, 1 << 32)])
-def test_dma_shard_join_compact_rowids_emulated_ranks(world, n_local, dom, id_base):
-    """rhj_shardx_pass1_soa / pass2_soa: the staged and shipped form is {u64 value}[n] + {u32 row id}[n]
-    (12 bytes per tuple on the wire).  Union == oracle; a row id >= 2^32 makes the join call fail."""
-    from radixhashjoin_b200 import RadixHashJoin, RhjError
-    rng = np.random.default_rng(world * 91 + n_local)
-    Rg, Sg = rand_rel(rng, world * n_local, dom), rand_rel(rng, world * n_local, dom, id_base)
-    wide = int(Sg["key"].max()) >= (1 << 32)
-    expect = O.sort_pairs(O.oracle_join(Rg, Sg))
-    engines = [RadixHashJoin(0) for _ in range(world)]
-    shards = [(to_dev(Rg[r * n_local:(r + 1) * n_local]), to_dev(Sg[r * n_local:(r + 1) * n_local])) for r in range(world)]
-    plan = engines[0].shard_plan(len(Rg), len(Sg), world)
-    ndig = world << plan.bits_pass1
-    sval = [[torch.empty(n_local, dtype=torch.int64, device=DEV) for _ in range(2)] for _ in range(world)]
-    srid = [[torch.empty(n_local, dtype=torch.int32, device=DEV) for _ in range(2)] for _ in range(world)]
-    hist = [[torch.empty(ndig, dtype=torch.int64, device=DEV) for _ in range(2)] for _ in range(world)]
-    for r in range(world):
-        engines[r].shardx_begin(plan)
-        for rel in (0, 1):
-            engines[r].shardx_pass1_soa(plan, rel, shards[r][rel], sval[r][rel], srid[r][rel], hist[r][rel])
-    lay = [[None, None] for _ in range(world)]
-    for rel in (0, 1):
-        all_hist = torch.stack([hist[r][rel] for r in range(world)])
-        for r in range(world):
-            lay[r][rel] = engines[r].shardx_layout(plan, r, rel, all_hist)
-    rval = [[torch.empty(max(lay[r][rel][3], 1), dtype=torch.int64, device=DEV) for rel in (0, 1)] for r in range(world)]
-    rrid = [[torch.empty(max(lay[r][rel][3], 1), dtype=torch.int32, device=DEV) for rel in (0, 1)] for r in range(world)]
-    for rel in (0, 1):
-        assert sum(lay[r][rel][3] for r in range(world)) == world * n_local
-        for r in range(world):
-            so, sc, do, _ = lay[r][rel]
-            for d in range(world):
-                rval[d][rel][do[d]:do[d] + sc[d]].copy_(sval[r][rel][so[d]:so[d] + sc[d]])
-                rrid[d][rel][do[d]:do[d] + sc[d]].copy_(srid[r][rel][so[d]:so[d] + sc[d]])
-    torch.cuda.synchronize()
-    got, failed = [], 0
-    for r in range(world):
-        for rel in (0, 1):
-            engines[r].shardx_pass2_soa(plan, rel, rval[r][rel], rrid[r][rel], lay[r][rel][3])
-        out = torch.empty((max(len(expect), 1), 2), dtype=torch.int64, device=DEV)
-        if wide:
-            with pytest.raises(RhjError, match="32 bits"):
-                engines[r].shardx_join(plan, out)
-            failed += 1
-            continue
-        pairs, n = engines[r].shardx_join(plan, out)
-        got.append(pairs_np(pairs))
-    if wide:
-        assert failed == world
-    else:
-        got = np.concatenate(got)
-        assert len(got) == len(expect)
-        assert np.array_equal(O.sort_pairs(got), expect)
     for e in engines:
         e.close()
 
@@ -670,62 +574,6 @@ def test_optimistic_pass2_overflow_falls_back_to_exact_path(emit, monkeypatch):
     assert (cnt,) + eng.pairs_digest(out)[1:] == exp
     assert eng.last_plan()["optimistic_pass1"] == 0          # the plan that produced the result is the exact one
     eng.close()
-
-
-@pytest.mark.parametrize("world,nR,nS,dom", [(2, 60000, 90000, 50000), (4, 40000, 40000, 1 << 40), (8, 100000, 300000, 1 << 20),
-                                             (2, 90000, 30000, 20000)])
-def test_dma_shard_join_split_probe_emulated_ranks(world, nR, nS, dom):
-    """three slots: the build relation whole, the probe relation in two row halves, each half joined
-    against the build slot as soon as its own second pass is done (rhj_shardx_join_slots_device)."""
-    from radixhashjoin_b200 import RadixHashJoin
-    rng = np.random.default_rng(world * 13 + nR)
-    Rg, Sg = rand_rel(rng, world * nR, dom), rand_rel(rng, world * nS, dom, 1 << 35)
-    expect = O.sort_pairs(O.oracle_join(Rg, Sg))
-    engines = [RadixHashJoin(0) for _ in range(world)]
-    plan = engines[0].shard_plan(len(Rg), len(Sg), world)
-    build_rel = 1 if plan.build_is_S else 0
-    probe_rel = 1 - build_rel
-    assert build_rel == (1 if nS < nR else 0)
-    glob, nloc = (Rg, Sg), (nR, nS)
-    slots = [build_rel, probe_rel, 2]
-    src = []
-    for r in range(world):
-        loc = [to_dev(glob[k][r * nloc[k]:(r + 1) * nloc[k]]) for k in (0, 1)]
-        P = loc[probe_rel]
-        h = (P.shape[0] + 1) // 2
-        src.append({build_rel: loc[build_rel], probe_rel: P[:h], 2: P[h:]})
-    ndig = world << plan.bits_pass1
-    stage = [{s: torch.empty((max(src[r][s].shape[0], 1), 2), dtype=torch.int64, device=DEV) for s in slots} for r in range(world)]
-    hist = [{s: torch.empty(ndig, dtype=torch.int64, device=DEV) for s in slots} for r in range(world)]
-    for r in range(world):
-        engines[r].shardx_begin(plan)
-        for s in slots:
-            engines[r].shardx_pass1(plan, s, src[r][s], stage[r][s], hist[r][s])
-    lay = [{} for _ in range(world)]
-    recv = [{} for _ in range(world)]
-    for s in slots:
-        all_hist = torch.stack([hist[r][s] for r in range(world)])
-        for r in range(world):
-            lay[r][s] = engines[r].shardx_layout(plan, r, s, all_hist)
-            recv[r][s] = torch.empty((max(lay[r][s][3], 1), 2), dtype=torch.int64, device=DEV)
-        for r in range(world):
-            so, sc, do, _ = lay[r][s]
-            for d in range(world):
-                recv[d][s][do[d]:do[d] + sc[d]].copy_(stage[r][s][so[d]:so[d] + sc[d]])
-    torch.cuda.synchronize()
-    got = []
-    for r in range(world):
-        out = torch.empty((max(len(expect), 1), 2), dtype=torch.int64, device=DEV)
-        for i, s in enumerate(slots):
-            engines[r].shardx_pass2(plan, s, recv[r][s][:lay[r][s][3]])
-            if i >= 1:
-                pairs, n = engines[r].shardx_join_slots(plan, build_rel, s, i == 1, out)
-        got.append(pairs_np(pairs))
-    got = np.concatenate(got)
-    assert len(got) == len(expect)
-    assert np.array_equal(O.sort_pairs(got), expect)
-    for e in engines:
-        e.close()
 
 
 # ---- multi-GPU, pipelined exchange (rhj_pipe_*): emulated ranks on one GPU -------------------------------
