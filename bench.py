@@ -486,7 +486,7 @@ def run_b200(args, rank, world, local_rank):
             acc[k] = acc.get(k, 0.0) + v / reps
     eng.set_profiling(False)
     nvlink = None
-    if shard_timeline and strategy == "pipe" and any(k == "join_done" for k, _ in shard_timeline):
+    if shard_timeline and strategy == "pipe" and any(k.startswith("ship_") for k, _ in shard_timeline):
         # the pipelined exchange has no library phase marks: the join kernel is what runs between the last pass 2 and the
         # end of the step; the wire is busy from the first chunk's pass 1 to the last chunk's copy kernel
         tl = dict(shard_timeline)
