@@ -83,3 +83,41 @@ def test_rank_function_is_a_function_of_the_value():
         assert np.array_equal(r, rank_of_values(v.copy(), world))
         if world > 1:
             assert np.bincount(r, minlength=world).min() > 10000 / world * 0.8
+
+
+def test_broadcast_strategy_rule():
+    """the build side is replicated only when shuffling both sides would move more (SURVEY 8e small-build caveat)"""
+    from radixhashjoin_b200.distributed import broadcast_is_cheaper
+    assert broadcast_is_cheaper(1 << 24, 1 << 30, 8)          # BASELINE config 3
+    assert broadcast_is_cheaper(1 << 30, 1 << 24, 2)          # either side may be the small one
+    assert not broadcast_is_cheaper(1 << 27, 1 << 27, 8)      # config 5 shape: shuffle
+    assert not broadcast_is_cheaper(1 << 24, 1 << 30, 1)      # one rank: nothing to exchange
+    assert not broadcast_is_cheaper(1 << 28, 1 << 30, 8)      # build x world > probe
+
+
+def test_sharded_workload_generators_tile_the_global_relations():
+    """rank r of N generates exactly rows [r n/N, (r+1) n/N) of the global relation pair, and the per-rank closed-form
+    digests add up to the global one -- what bench.py's multi-GPU verification relies on."""
+    import torch
+    from radixhashjoin_b200 import workloads as W
+    M = (1 << 64) - 1
+    for make, glob in ((lambda r, n: W.foreign_key(9, 13, rank=r, world=n), W.foreign_key(9, 13)),
+                       (lambda r, n: W.zipf_probe(13, rank=r, world=n), W.zipf_probe(13))):
+        for world in (2, 4):
+            parts = [make(r, world) for r in range(world)]
+            assert torch.equal(torch.cat([p.R for p in parts]), glob.R)
+            assert torch.equal(torch.cat([p.S for p in parts]), glob.S)
+            cnt = sum(p.expected[0] for p in parts)
+            s = sum(p.expected[1] for p in parts) & M
+            x = 0
+            for p in parts:
+                x ^= p.expected[2]
+            assert (cnt, s, x) == tuple(glob.expected)
+    # uniform: rows by offset, digest by range
+    g = W.uniform_unique(12)
+    a = W.uniform_unique(11, row_offset=0, log2_global=12)
+    b = W.uniform_unique(11, row_offset=2048, log2_global=12)
+    assert torch.equal(torch.cat([a.S, b.S]), g.S) and torch.equal(torch.cat([a.R, b.R]), g.R)
+    d0 = W.uniform_unique_global_digest(12, lo=0, hi=2048)
+    d1 = W.uniform_unique_global_digest(12, lo=2048, hi=4096)
+    assert (d0[0] + d1[0], (d0[1] + d1[1]) & M, d0[2] ^ d1[2]) == tuple(g.expected)
