@@ -507,17 +507,23 @@ def run_b200(args, rank, world, local_rank):
     peak, peak_src = measured_hbm_peak()
     roofline = None
     traffic = None
-    try:  # dram bytes of the same kernel from the committed ncu --set full capture of this workload
-        with open(os.path.join(ROOT, "profiles", "r01_final_ncu_traffic.json")) as f:
-            tj = json.load(f)
-        if world == 1 and tj["workload"] == wname and tj["emitter"] == args.emit and dom in tj["phases"]:
-            traffic = tj["phases"][dom]["traffic_bytes"]
-    except Exception:
-        traffic = None
+    traffic_src = None
+    for cand in ("r02_final_ncu_traffic.json", "r01_final_ncu_traffic.json"):
+        # dram bytes of the same kernel from a committed `ncu --set full` capture of this workload: a SNAPSHOT of the build named
+        # in the file, not a measurement of the running one (ncu cannot run inside the timed bench)
+        try:
+            with open(os.path.join(ROOT, "profiles", cand)) as f:
+                tj = json.load(f)
+            if world == 1 and tj["workload"] == wname and tj["emitter"] == args.emit and dom in tj["phases"]:
+                traffic = tj["phases"][dom]["traffic_bytes"]
+                traffic_src = f"profiles/{cand} (ncu snapshot of build {tj.get('build', 'r01 final')})"
+                break
+        except Exception:
+            continue
     if dom:
         ach = alg_bytes[dom] / (acc[dom] * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": traffic, "traffic_source": "profiles/r01_final_ncu_traffic.json" if traffic else None,
+                    "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peak_src, "kernel_ms": acc[dom],
                     "algorithmic_bytes_per_launch": alg_bytes[dom]}
     b_alg_step = 96 * n_join + 16 * m_local     # canonical 2-pass plan

@@ -201,6 +201,33 @@ def test_baseline_config2_uniform_2p27(engine):
     assert plan["bits_total"] == 16
 
 
+def test_baseline_config3_foreign_key_full_size(engine):
+    """BASELINE.json configs[2] at its full single-GPU size: 2^24-tuple build x 2^30-tuple probe (16 GiB), every probe
+    tuple matches one build row -- count and digest in closed form (the oracle does not fit host RAM at this size)."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 100 * (1 << 30):
+        pytest.skip("needs ~90 GiB of free HBM")
+    w = W.foreign_key(24, 30, DEV)
+    out, n = engine.join_device(w.R, w.S, capacity=1 << 30, emit=EMIT_FUSED)
+    assert (n,) + engine.pairs_digest(out)[1:] == tuple(w.expected)
+    del out, w
+    torch.cuda.empty_cache()
+
+
+def test_baseline_config4_zipf_2p28(engine):
+    """BASELINE.json configs[3] at full size: Zipf(1.0) probe keys over 2^28 unique build keys; the hottest key draws 1/28
+    of the probe side, which forces the exact (histogram) path for the probe relation and probe-chunked work items."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 * (1 << 30):
+        pytest.skip("needs ~50 GiB of free HBM")
+    w = W.zipf_probe(28, DEV)
+    out, n = engine.join_device(w.R, w.S, capacity=1 << 28, emit=EMIT_FUSED)
+    assert (n,) + engine.pairs_digest(out)[1:] == tuple(w.expected)
+    assert engine.last_plan()["optimistic_pass1"] & 2 == 0      # the skewed probe side kept its histograms
+    del out, w
+    torch.cuda.empty_cache()
+
+
 # ---- neighbours: filters, gathers, checksum -----------------------------------------------------------
 def test_filter_gather_sum_equal_oracle(engine):
     rng = np.random.default_rng(11)
