@@ -763,7 +763,7 @@ int partition_relation(rhj_ctx *ctx, cudaStream_t st, const Plan &pl, const Meta
 // Host -> device copy of a caller's relation on stream `st`.  Pinned (or registered) sources go straight to the copy
 // engine.  PAGEABLE sources -- what the reference's Query::run_joins passes: relation::tuples is `new tuple[]`,
 // structs.cpp:217-243 -- would make cudaMemcpyAsync stage them through the driver's single-threaded bounce buffer at
-// ~13 GB/s and block the calling thread; here the host fills a pinned ring (4 x 32 MiB) with up to four memcpy threads
+// ~13 GB/s and block the calling thread; here the host fills a pinned ring (4 x 32 MiB) with a few memcpy threads (RHJ_STAGE_THREADS, default 8)
 // while the copy engine drains the slot before (measured on the 2^27 x 2^27 end-to-end join: 416 -> see DESIGN.md).
 // Returns when the last slice has been ENQUEUED; the copies complete in stream order.
 int upload_host(rhj_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, cudaStream_t st) {
@@ -786,7 +786,7 @@ int upload_host(rhj_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, cuda
         for (auto &ev : ctx->stage_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     }
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const int nthr = (int) std::min<unsigned>(4, std::max(1u, hw / 4));
+    const int nthr = (int) std::min<unsigned>(ctx->stage_threads, std::max(1u, hw / 2));
     for (size_t off = 0; off < bytes; off += rhj_ctx::kStageSlot) {
         const size_t len = std::min(rhj_ctx::kStageSlot, bytes - off);
         const int slot = ctx->stage_next;
@@ -992,6 +992,7 @@ int rhj_create(int device, rhj_ctx **out) {
     if ((e = getenv("RHJ_NO_SHARD_OPT2"))) ctx->shard_optimistic2 = atoi(e) == 0;
     if ((e = getenv("RHJ_SHARD_OPT2_WORLD"))) ctx->shard_opt2_world = (u32) std::max(0, atoi(e));
     if ((e = getenv("RHJ_HOST_CHUNK"))) ctx->host_chunk = std::max<long long>(1, atoll(e));
+    if ((e = getenv("RHJ_STAGE_THREADS"))) ctx->stage_threads = (unsigned) std::max(1, std::min(32, atoi(e)));
     if ((e = getenv("RHJ_SHARD_SCATTER_MODE"))) ctx->shard_scatter_mode = atoi(e);
     if (cudaSetDevice(device) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||

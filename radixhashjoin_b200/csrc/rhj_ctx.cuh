@@ -75,6 +75,7 @@ struct rhj_ctx {
     static constexpr int kStageSlots = 4;
     cudaEvent_t stage_ev[kStageSlots] = {};
     int stage_next = 0;
+    unsigned stage_threads = 8;   // memcpy threads per staged slice (RHJ_STAGE_THREADS), at most half the host's CPUs
     void *h_out = nullptr;    // pinned host result of rhj_join_host
     size_t h_out_cap = 0;
     u64 *h_scalars = nullptr; // pinned, kScCount u64

@@ -188,6 +188,7 @@ class PipeShardedJoin:
         self.copy_stream = torch.cuda.Stream(device=dev, priority=-1)   # the copy kernel's CTAs go first when an SM frees up
         self.epoch = 0
         self.exact_left = 0
+        self.backoff = 0
         self.exact_steps = 0
         self._exact = None
 
@@ -255,8 +256,12 @@ class PipeShardedJoin:
             raise RuntimeError(f"rank {self.rank}: pipelined exchange failed (status {status}: "
                                f"{'timeout ' if status & self.TIMEOUT else ''}{'bad region end' if status & self.BAD else ''})")
         if status & self.OVERFLOW:
-            self.exact_left = 16
+            # every rank saw the same status: all redo this step exactly, and stay exact for a while -- twice as long each time
+            # the pipelined attempt fails again (a skewed workload should not pay a wasted step every 17 joins)
+            self.backoff = min(1024, 2 * self.backoff) if self.backoff else 16
+            self.exact_left = self.backoff
             return self._exact_step(R_local, S_local, out, marks)
+        self.backoff = 0
         return pairs, count, None
 
     @staticmethod
