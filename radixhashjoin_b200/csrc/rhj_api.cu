@@ -475,6 +475,7 @@ int partition_and_plan(rhj_ctx *ctx, cudaStream_t st, const Tup *dR, u64 nR, con
     ctx->cur.valid = false;
     ctx->cur.counted = false;
     ctx->nmarks = 0;
+    ctx->pending.nB = 0;
 
     Meta m;
     int rc;
@@ -499,7 +500,22 @@ int partition_and_plan(rhj_ctx *ctx, cudaStream_t st, const Tup *dR, u64 nR, con
         bool poisson[2] = {false, false};
         if (!allow_optimistic) ctx->opt2_skip = 16;  // an optimistic layout just overflowed: stay exact in pass 2 for a while
         if (allow_optimistic && ctx->optimistic && pl.b2 > 0 && ntot >= ((u64) 1 << 22)) {
-            if ((rc = sample_says_balanced(ctx, st, pl, inB, inP, opt, poisson))) return rc;
+            auto &tr = ctx->trust;
+            if (ctx->trust_sample && !ctx->force_optimistic && tr.streak >= 2 && tr.age < 64 && tr.nB == pl.nB && tr.nP == pl.nP) {
+                for (int i = 0; i < 2; ++i) {  // same shape as the last sampled joins, which all fitted: reuse their verdict
+                    opt[i] = tr.opt[i];
+                    poisson[i] = tr.poisson[i];
+                }
+                tr.age++;
+            } else {
+                if ((rc = sample_says_balanced(ctx, st, pl, inB, inP, opt, poisson))) return rc;
+                ctx->pending.nB = pl.nB;
+                ctx->pending.nP = pl.nP;
+                for (int i = 0; i < 2; ++i) {
+                    ctx->pending.opt[i] = opt[i];
+                    ctx->pending.poisson[i] = poisson[i];
+                }
+            }
             if (ctx->force_optimistic) opt[0] = opt[1] = poisson[0] = poisson[1] = true;  // test hook: exercise the overflow -> exact retry
         }
         bool fixed2 = opt[0] && opt[1] && poisson[0] && poisson[1] && ctx->optimistic2 && pl.b2 <= 9;
@@ -639,6 +655,23 @@ JoinArgs join_args(rhj_ctx *ctx, int work_slot) {
 }
 
 constexpr int kRetryExact = 1000;  // internal: re-run the partition phase with the exact histogram path
+
+// Book-keeping of the sample-free shortcut (rhj_ctx::trust): called with the outcome of the FIRST attempt of a join.
+void settle_trust(rhj_ctx *ctx, bool overflowed) {
+    auto &tr = ctx->trust;
+    if (overflowed) {
+        tr.streak = 0;
+        return;
+    }
+    const auto &pe = ctx->pending;
+    if (!pe.nB) return;  // this join did not sample (reused a verdict, or is too small for the optimistic passes)
+    const bool same = tr.streak > 0 && tr.nB == pe.nB && tr.nP == pe.nP && tr.opt[0] == pe.opt[0] && tr.opt[1] == pe.opt[1] &&
+                      tr.poisson[0] == pe.poisson[0] && tr.poisson[1] == pe.poisson[1];
+    const int streak = same ? tr.streak + 1 : 1;
+    tr = pe;
+    tr.streak = streak;
+    tr.age = 0;
+}
 
 int read_scalars(rhj_ctx *ctx, cudaStream_t st) {
     u64 *sc = scalars_of(ctx, ctx->cur.nparts);
@@ -989,6 +1022,7 @@ int rhj_create(int device, rhj_ctx **out) {
     if ((e = getenv("RHJ_NO_OPT"))) ctx->optimistic = atoi(e) == 0;
     if ((e = getenv("RHJ_FORCE_OPT"))) ctx->force_optimistic = atoi(e) != 0;
     if ((e = getenv("RHJ_NO_OPT2"))) ctx->optimistic2 = atoi(e) == 0;
+    if ((e = getenv("RHJ_NO_TRUST"))) ctx->trust_sample = atoi(e) == 0;
     if ((e = getenv("RHJ_NO_SHARD_OPT2"))) ctx->shard_optimistic2 = atoi(e) == 0;
     if ((e = getenv("RHJ_SHARD_OPT2_WORLD"))) ctx->shard_opt2_world = (u32) std::max(0, atoi(e));
     if ((e = getenv("RHJ_HOST_CHUNK"))) ctx->host_chunk = std::max<long long>(1, atoll(e));
@@ -1110,6 +1144,7 @@ int rhj_join_count_device(rhj_ctx *ctx, const rhj_tuple *dR, uint64_t nR, const 
     for (int attempt = 0; attempt < 2; ++attempt) {  // attempt 1 = exact histogram path after an optimistic overflow
         if ((rc = partition_and_plan(ctx, st, (const Tup *) dR, nR, (const Tup *) dS, nS, attempt == 0))) return rc;
         rc = count_phase(ctx, st);
+        if (attempt == 0 && (rc == RHJ_OK || rc == kRetryExact)) settle_trust(ctx, rc == kRetryExact);
         if (rc != kRetryExact) break;
     }
     if (rc) return rc;
@@ -1158,6 +1193,7 @@ int rhj_join_device(rhj_ctx *ctx, const rhj_tuple *dR, uint64_t nR, const rhj_tu
         if ((rc = launch_join<kJoinFused>(ctx, st, j, ctx->cur.item_cap))) return rc;
         mark(ctx, st, -1);
         rc = read_scalars(ctx, st);
+        if (attempt == 0 && (rc == RHJ_OK || rc == kRetryExact)) settle_trust(ctx, rc == kRetryExact);
         if (rc != kRetryExact) break;
     }
     if (rc) return rc;

@@ -47,6 +47,16 @@ struct rhj_ctx {
     bool force_optimistic = false;  // RHJ_FORCE_OPT=1 (tests): take the optimistic path even when the sample says skewed
     bool optimistic2 = true;  // also skip the pass-2 histogram (fixed-capacity final partitions; RHJ_NO_OPT2=1 disables)
     int opt2_skip = 0;        // joins left to run without the pass-2 shortcut after it overflowed (duplicate-heavy data)
+    // The sample only PREDICTS whether the histogram-free layouts will fit; an overflow is detected and redone exactly
+    // either way.  After two sampled joins of the same shape agreed and succeeded, the next joins of that shape reuse the
+    // decision without sampling (one kernel, one D2H and one host synchronisation less per join); an overflow, another shape
+    // or 64 joins bring the sample back.
+    struct {
+        u64 nB = 0, nP = 0;
+        bool opt[2] = {false, false}, poisson[2] = {false, false};
+        int streak = 0, age = 0;
+    } trust, pending;
+    bool trust_sample = true;  // RHJ_NO_TRUST=1 samples every join
     DevBuf sample;            // sampled pass-1 histogram
     int scatter_mode = 0;     // 0 staged per-thread stores, 1 TMA bulk stores (RHJ_SCATTER_MODE)
     int shard_scatter_mode = 1;  // same choice for pass 1 of the exact sharded exchange (local staging): bulk stores were

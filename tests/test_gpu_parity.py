@@ -834,3 +834,44 @@ def test_histogram_aggregation_and_bulk_store_scatter_variants(env, monkeypatch)
             assert plan["bits_pass2"] > 0 and plan["optimistic_pass1"] == 0
     finally:
         e.close()
+
+
+def test_sample_free_shortcut_after_agreeing_joins_and_its_overflow(monkeypatch):
+    """After two sampled joins of one shape fitted their histogram-free layouts, the next joins of that shape skip the sample
+    (one kernel launch less); a skewed input of the SAME shape then overflows, is redone exactly and correctly, and brings the
+    sample back.  RHJ_NO_TRUST=1 samples every time."""
+    from radixhashjoin_b200 import RadixHashJoin
+    e = RadixHashJoin(0)
+    try:
+        w = W.uniform_unique(25, DEV)
+        out = torch.empty((1 << 25, 2), dtype=torch.int64, device=DEV)
+        launches = []
+        for _ in range(5):
+            pairs, n = e.join_device(w.R, w.S, out=out)
+            assert (n,) + e.pairs_digest(pairs)[1:] == tuple(w.expected)
+            launches.append(e.last_plan()["kernel_launches"])
+            assert e.last_plan()["optimistic_pass1"] & 3 == 3
+        assert launches[0] == launches[1] and launches[2] == launches[1] - 1 and launches[4] == launches[2]
+        # same shape, but every probe tuple carries one value: the trusted verdict is wrong, the scatter overflows
+        S_hot = w.S.clone()
+        S_hot[:, 1] = int(w.R[12345, 1])
+        pairs, n = e.join_device(w.R, S_hot, out=out)
+        assert n == 1 << 25
+        p = pairs_np(pairs)
+        assert (p["keyR"] == 12345).all() and np.array_equal(np.sort(p["keyS"]), np.arange(1 << 25, dtype=np.uint64))
+        assert e.last_plan()["optimistic_pass1"] & 2 == 0          # redone with the probe side on the exact path
+        pairs, n = e.join_device(w.R, w.S, out=out)                # ... and the next join samples again
+        assert (n,) + e.pairs_digest(pairs)[1:] == tuple(w.expected)
+        assert e.last_plan()["kernel_launches"] == launches[0]
+    finally:
+        e.close()
+    monkeypatch.setenv("RHJ_NO_TRUST", "1")
+    e = RadixHashJoin(0)
+    try:
+        ls = []
+        for _ in range(4):
+            e.join_device(w.R, w.S, out=out)
+            ls.append(e.last_plan()["kernel_launches"])
+        assert len(set(ls)) == 1
+    finally:
+        e.close()
