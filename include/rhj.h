@@ -172,7 +172,9 @@ int rhj_intermediate_filter_host(rhj_ctx *ctx, const uint64_t *col1, const uint6
 
 /* relList columns (structs.cpp:18-60: read-only host arrays for the life of the process) are uploaded ONCE: the first
  * call with a host column copies it to the device, every later call -- from any context of the process -- returns the
- * same device copy.  *uploaded_bytes (optional) = bytes this call moved over PCIe (0 on a hit). */
+ * same device copy.  *uploaded_bytes (optional) = bytes this call moved over PCIe (0 on a hit).  The cache is keyed by the
+ * host address (plus length and a first / middle / last fingerprint, so a recycled address with other contents is uploaded
+ * again); a column must not be modified or freed while a query that uses it is running. */
 int rhj_column_device(rhj_ctx *ctx, const uint64_t *host_col, uint64_t n, const uint64_t **d_col, uint64_t *uploaded_bytes);
 int rhj_column_cache_clear(void);
 
