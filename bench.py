@@ -154,8 +154,9 @@ def small_work_wall(with_reference=False):
     diffed against small.result:
       join_b200_query  Query::execute -> rhj_query_execute: the whole query path device resident (the product);
       join_b200_full   Result.cpp + intermediate.cpp replaced, filters / relations / intermediates on the host (round 1).
-    A process pays ~1.5-2.5 s of CUDA context creation before its first query; the steady-state figure is the extra wall
-    time of running the workload three times instead of once inside ONE process, halved.  With --small-work-ref the
+    A process pays ~1.5-2.5 s of CUDA context creation before its first query; the steady-state figures are the program's own
+    clock from the last context creation to the last call (`query_phase_*`, RHJ_HOST_TIMING) and the extra wall time per
+    additional pass when the workload runs three times inside ONE process (noisy: context creation varies by +-0.5 s).  With --small-work-ref the
     unmodified reference program (oracle/_ref/join_ref) is timed the same way (takes minutes)."""
     import re
     import subprocess
@@ -192,9 +193,9 @@ def small_work_wall(with_reference=False):
             if not os.path.exists(b):
                 continue
             w1, s1, err = run(b, 3)
-            w3, s3, _ = run(b, 2, times=3)
+            w3, s3, err3 = run(b, 2, times=3)
             r = {"program": what, "wall_s": min(w1), "wall_s_all": [round(w, 3) for w in w1], "output_identical_to_small_result": s1 and s3,
-                 "wall_s_three_passes": min(w3), "steady_state_s_per_pass": max(0.0, (min(w3) - min(w1)) / 2)}
+                 "wall_s_three_passes": min(w3), "extra_wall_s_per_additional_pass": (min(w3) - min(w1)) / 2}
             m = re.search(r"(\d+) queries on the device: (\d+) joins, (\d+) kernel launches, H2D (\d+) bytes .* D2H (\d+) bytes", err)
             if m:
                 r["pcie"] = {"queries": int(m.group(1)), "joins": int(m.group(2)), "kernel_launches": int(m.group(3)),
@@ -203,6 +204,12 @@ def small_work_wall(with_reference=False):
             m = re.search(r"context creation thread-time ([0-9.]+) ms", err)
             if m:
                 r["cuda_context_creation_thread_ms"] = float(m.group(1))
+            # the program's own clock: from the moment the last query thread had its CUDA context to the end of the last call
+            ph1 = re.search(r"query phase after the last context was created: ([0-9.]+) ms", err)
+            ph3 = re.search(r"query phase after the last context was created: ([0-9.]+) ms", err3)
+            if ph1 and ph3:
+                r["query_phase_s_one_pass"] = float(ph1.group(1)) / 1e3
+                r["query_phase_s_per_pass_of_three"] = float(ph3.group(1)) / 3e3
             res[name] = r
         res["wall_s"] = res["join_b200_query"]["wall_s"]
         res["output_identical_to_small_result"] = all(v["output_identical_to_small_result"] for v in res.values() if isinstance(v, dict))
