@@ -149,13 +149,51 @@ int launch_scatter(rhj_ctx *ctx, cudaStream_t st, const PartArgs &a, int kind, b
     return RHJ_OK;
 }
 
-template <int MODE>
+template <int MODE, bool POS = false>
 int launch_join(rhj_ctx *ctx, cudaStream_t st, const JoinArgs &a, u32 item_cap) {
     u32 grid = std::min<u32>(std::max<u32>(item_cap, 1), (u32) ctx->num_sms * RHJ_JOIN_MINBLOCKS);
-    CK(set_smem(k_join<MODE>, kJoinSmem));
-    k_join<MODE><<<grid, kJoinThreads, kJoinSmem, st>>>(a);
+    CK(set_smem(k_join<MODE, POS>, kJoinSmem));
+    k_join<MODE, POS><<<grid, kJoinThreads, kJoinSmem, st>>>(a);
     CK(cudaGetLastError());
     ctx->info.kernel_launches++;
+    return RHJ_OK;
+}
+
+// Closes the holes a positional emit left in d_out[0, cursor): the `holes` unmatched slots hold RHJ_HOLE pairs; the valid
+// pairs behind F = cursor - holes move into the holes before F.  *ok = false when the sentinel count does not add up (a
+// genuine pair equal to the sentinel): the caller then redoes the join with the ranked emitter.
+int close_holes(rhj_ctx *ctx, cudaStream_t st, Pair *d_out, u64 cursor, u64 holes, bool *ok) {
+    *ok = true;
+    const u64 F = cursor - holes;
+    const u64 ntile64 = (cursor + kHoleTile - 1) / kHoleTile;
+    if (ntile64 > 0x7fffffffull) return fail(ctx, RHJ_ERR_ARG, "result too large");
+    const u32 ntiles = (u32) ntile64;
+    int rc;
+    if ((rc = ensure(ctx, ctx->filt_cnt, (size_t) 2 * ntiles * 4))) return rc;
+    if ((rc = ensure(ctx, ctx->filt_off, (size_t) 2 * ntiles * 8 + 16))) return rc;
+    const u64 kmax = std::min(holes, F) + 1;   // a hole before F needs a valid pair behind it: at most min(holes, F) moves
+    if ((rc = ensure(ctx, ctx->filt_tmp, (size_t) 2 * kmax * 8))) return rc;
+    u32 *cnt = (u32 *) ctx->filt_cnt.p;
+    u64 *off = (u64 *) ctx->filt_off.p, *totals = off + 2 * (size_t) ntiles;
+    u64 *lh = (u64 *) ctx->filt_tmp.p, *lt = lh + kmax;
+    k_holes_count<<<ntiles, 256, 0, st>>>(d_out, cursor, F, ntiles, cnt);
+    k_holes_scan<<<2, 1024, 0, st>>>(cnt, ntiles, off, totals);
+    CK(cudaGetLastError());
+    ctx->info.kernel_launches += 2;
+    CK(cudaMemcpyAsync(ctx->h_scalars, totals, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    const u64 kh = ctx->h_scalars[0], kt = ctx->h_scalars[1];
+    if (kh != kt || kh >= kmax) {
+        *ok = false;
+        return RHJ_OK;
+    }
+    if (kh) {
+        k_holes_list<<<ntiles, 256, 0, st>>>(d_out, cursor, F, ntiles, off, lh, lt);
+        k_holes_fill<<<(u32) std::min<u64>((kh + 255) / 256, (u64) ctx->num_sms * 8), 256, 0, st>>>(d_out, lh, lt, kh);
+        CK(cudaGetLastError());
+        ctx->info.kernel_launches += 2;
+        CK(cudaStreamSynchronize(st));
+    }
     return RHJ_OK;
 }
 
@@ -1023,6 +1061,7 @@ int rhj_create(int device, rhj_ctx **out) {
     if ((e = getenv("RHJ_FORCE_OPT"))) ctx->force_optimistic = atoi(e) != 0;
     if ((e = getenv("RHJ_NO_OPT2"))) ctx->optimistic2 = atoi(e) == 0;
     if ((e = getenv("RHJ_NO_TRUST"))) ctx->trust_sample = atoi(e) == 0;
+    if ((e = getenv("RHJ_NO_POS"))) ctx->positional = atoi(e) == 0;
     if ((e = getenv("RHJ_NO_SHARD_OPT2"))) ctx->shard_optimistic2 = atoi(e) == 0;
     if ((e = getenv("RHJ_SHARD_OPT2_WORLD"))) ctx->shard_opt2_world = (u32) std::max(0, atoi(e));
     if ((e = getenv("RHJ_HOST_CHUNK"))) ctx->host_chunk = std::max<long long>(1, atoll(e));
@@ -1184,18 +1223,49 @@ int rhj_join_device(rhj_ctx *ctx, const rhj_tuple *dR, uint64_t nR, const rhj_tu
     }
     if (!dR || !dS || (!d_out && capacity)) return fail(ctx, RHJ_ERR_ARG, "null pointer");
     int rc;
-    for (int attempt = 0; attempt < 2; ++attempt) {  // attempt 1 = exact histogram path after an optimistic overflow
-        if ((rc = partition_and_plan(ctx, st, (const Tup *) dR, nR, (const Tup *) dS, nS, attempt == 0))) return rc;
+    // positional emit (one output slot per probe tuple, holes closed afterwards) needs room for a slot per probe tuple
+    bool pos = ctx->positional && capacity >= std::max(nR, nS);
+    if (pos && ctx->pos_skip > 0) {
+        ctx->pos_skip--;
+        pos = false;
+    }
+    bool allow_opt = true;
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        if ((rc = partition_and_plan(ctx, st, (const Tup *) dR, nR, (const Tup *) dS, nS, allow_opt))) return rc;
         JoinArgs j = join_args(ctx, kScWork0);
         j.out = (Pair *) d_out;
         j.capacity = capacity;
+        j.holes = scalars_of(ctx, ctx->cur.nparts) + kScHoles;
         mark(ctx, st, RHJ_PHASE_JOIN);
-        if ((rc = launch_join<kJoinFused>(ctx, st, j, ctx->cur.item_cap))) return rc;
+        if (pos) rc = launch_join<kJoinFused, true>(ctx, st, j, ctx->cur.item_cap);
+        else rc = launch_join<kJoinFused>(ctx, st, j, ctx->cur.item_cap);
+        if (rc) return rc;
         mark(ctx, st, -1);
         rc = read_scalars(ctx, st);
         if (attempt == 0 && (rc == RHJ_OK || rc == kRetryExact)) settle_trust(ctx, rc == kRetryExact);
-        if (rc != kRetryExact) break;
+        if (rc == kRetryExact && allow_opt) {  // an optimistic layout overflowed: exact histogram path
+            allow_opt = false;
+            continue;
+        }
+        if (rc || !pos) break;
+        const u64 cursor = ctx->h_scalars[kScCursor], holes = ctx->h_scalars[kScHoles];
+        if (cursor > capacity) {  // slots + ranked items did not fit: the ranked emitter alone tells the exact need
+            pos = false;
+            continue;
+        }
+        if (holes) {
+            bool ok = false;
+            if ((rc = close_holes(ctx, st, (Pair *) d_out, cursor, holes, &ok))) return rc;
+            if (!ok) {
+                pos = false;
+                continue;
+            }
+            ctx->h_scalars[kScCursor] = cursor - holes;
+            if (holes * 64 > cursor) ctx->pos_skip = 16;  // many probe tuples without a match: the ranked emitter is cheaper
+        }
+        break;
     }
+    if (rc == kRetryExact) return fail(ctx, RHJ_ERR_STATE, "overflow flag set on the exact path");
     if (rc) return rc;
     *count = ctx->h_scalars[kScCursor];
     if (*count > capacity) return fail(ctx, RHJ_ERR_CAPACITY, "output buffer too small for the fused emitter");

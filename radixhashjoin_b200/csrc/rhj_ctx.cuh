@@ -33,6 +33,7 @@ enum Scalar {
     kScDigXor = 7,
     kScFilt = 8,
     kScOverflow = 9,  // optimistic pass 1: a partition outgrew its fixed-capacity region
+    kScHoles = 10,       // positional emit: reserved output slots left without a match
     kScPipeStatus = 11,  // pipelined exchange: RHJ_PIPE_* bits of this step, own and received
     kScCount = 16
 };
@@ -57,6 +58,10 @@ struct rhj_ctx {
         int streak = 0, age = 0;
     } trust, pending;
     bool trust_sample = true;  // RHJ_NO_TRUST=1 samples every join
+    // positional emit (k_join<FUSED, POS>): one output slot per probe tuple, holes closed afterwards.  Wins when (almost) every
+    // probe tuple matches (foreign-key style joins); a join that left more than 1/64 holes switches it off for the next 16.
+    bool positional = true;    // RHJ_NO_POS=1 disables
+    int pos_skip = 0;
     DevBuf sample;            // sampled pass-1 histogram
     int scatter_mode = 0;     // 0 staged per-thread stores, 1 TMA bulk stores (RHJ_SCATTER_MODE)
     int shard_scatter_mode = 1;  // same choice for pass 1 of the exact sharded exchange (local staging): bulk stores were

@@ -49,6 +49,9 @@ constexpr int kJoinThreads = RHJ_JOIN_THREADS;
 #ifndef RHJ_JOIN_ITEMS
 #define RHJ_JOIN_ITEMS 4
 #endif
+#ifndef RHJ_JOIN_ITEMS_POS
+#define RHJ_JOIN_ITEMS_POS 4
+#endif
 constexpr int kJoinItems = RHJ_JOIN_ITEMS;           // probe tuples per thread per round
 constexpr int kRound = kJoinThreads * kJoinItems;    // probe tuples per round
 constexpr u32 kBuildCap = RHJ_JOIN_CAP;              // build tuples per shared-memory table
@@ -82,12 +85,25 @@ struct JoinArgs {
     Pair *out;
     u64 capacity;
     int build_is_S;      // output is always (rowidR, rowidS): Result.cpp:66-69
+    u64 *holes;          // POS: output slots reserved by position that stayed without a match (they hold kHolePair)
 };
+
+// POSITIONAL emit (FUSED mode, template flag POS).  When a partition's build side is one chunk of unique keys, a probe tuple
+// has at most one match, so the item reserves ONE output slot per probe tuple up front -- a single global atomic per item,
+// issued at item fetch and hidden behind the build -- and tuple i writes its pair to slot base + i: no ballots, no ranking,
+// no CTA barrier and no reservation latency inside the probe loop.  A tuple without a match leaves kHolePair in its slot and
+// is counted in *holes; the host closes the holes afterwards (k_holes_*), which costs nothing on foreign-key style joins
+// where every probe tuple matches.  Items with duplicate build keys or several build chunks take the ranked path.
+#define RHJ_HOLE 0xFFFFFFFFFFFFFFFFull
 
 __device__ __forceinline__ u32 slot_of(u64 v) { return hash32(v) & (kSlots - 1); }
 
-template <int MODE>
+template <int MODE, bool POS = false>
 __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join(JoinArgs a) {
+    // probe tuples per thread and round (more than four were measured slower in either emitter: 5 -> 1.90 ms, 6 -> 1.83 ms
+    // against 1.61 ms for the positional kernel; registers / spills)
+    constexpr int ITEMS = POS ? RHJ_JOIN_ITEMS_POS : kJoinItems;
+    constexpr int ROUND = kJoinThreads * ITEMS;
     extern __shared__ __align__(128) unsigned char dyn_smem[];
     Tup *s_tup = reinterpret_cast<Tup *>(dyn_smem);
     slot_t *s_slot = reinterpret_cast<slot_t *>(dyn_smem + (size_t) kBuildCap * sizeof(Tup));
@@ -96,6 +112,8 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join(JoinA
     __shared__ u32 s_cnt[2];
     __shared__ u64 s_base[2];
     __shared__ u64 s_red[32];
+    __shared__ u64 s_posbase;
+    u64 my_miss = 0;  // POS: reserved slots of this thread's probe tuples that found no match
 
     const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const u32 lt_mask = lanemask_lt();
@@ -119,6 +137,10 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join(JoinA
         const u64 p1 = min(a.endP[it.part], p0 + (u64) kProbeChunk);
         u64 my_count = 0;                                   // COUNT
         u64 run_base = (MODE == kJoinWrite && tid == 0) ? a.item_off[item] : 0;  // WRITE (thread 0 only)
+        // POS: one slot per probe tuple, reserved now; the value is first looked at behind the build
+        const bool single = POS && MODE == kJoinFused && b1 - b0 <= kBuildCap;
+        u64 posres = 0;
+        if (single && tid == 0) posres = atomicAdd(a.out_cursor, p1 - p0);
 
         for (u64 bb = b0; bb < b1; bb += kBuildCap) {
             const u32 nb = (u32) min((u64) kBuildCap, b1 - bb);
@@ -126,10 +148,10 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join(JoinA
                 mbar_expect_tx(&s_bar, nb * (u32) sizeof(Tup));
                 bulk_g2s(s_tup, a.build + bb, nb * (u32) sizeof(Tup), &s_bar);
             }
-            Tup t[kJoinItems];
+            Tup t[ITEMS];
             {
 #pragma unroll
-                for (int j = 0; j < kJoinItems; ++j) {
+                for (int j = 0; j < ITEMS; ++j) {
                     u64 idx = p0 + (u64) j * kJoinThreads + tid;
                     if (idx < p1) t[j] = ld_stream(a.probe + idx);
                 }
@@ -151,23 +173,68 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join(JoinA
                     h = (h + 1) & (kSlots - 1);
                 }
             }
+            if (single && tid == 0) s_posbase = posres;
             dup = __syncthreads_or(dup);
 
-            // probe
-            for (u64 q0 = p0; q0 < p1; q0 += kRound) {
-                bool ok[kJoinItems];
+            if (single && !dup) {
+                // positional probe + emit: slot = reserved base + position of the tuple in the item's probe range
+                const u64 base = s_posbase;
+                for (u64 q0 = p0; q0 < p1; q0 += ROUND) {
 #pragma unroll
-                for (int j = 0; j < kJoinItems; ++j) {
+                    for (int j = 0; j < ITEMS; ++j) {
+                        const u64 idx = q0 + (u64) j * kJoinThreads + tid;
+                        if (idx < p1 && q0 != p0) t[j] = ld_stream(a.probe + idx);
+                    }
+#pragma unroll
+                    for (int j = 0; j < ITEMS; ++j) {
+                        const u64 idx = q0 + (u64) j * kJoinThreads + tid;
+                        if (idx < p1) {
+                            u32 h = slot_of(t[j].val);
+                            u32 c, hit = kEmpty;
+                            while ((c = s_slot[h]) != kSlotEmpty) {
+                                if (s_tup[c].val == t[j].val) { hit = c; break; }
+                                h = (h + 1) & (kSlots - 1);
+                            }
+                            const u64 at = base + (idx - p0);
+                            if (at < a.capacity) {
+                                if (hit != kEmpty) {
+                                    const u64 bk = s_tup[hit].key;
+                                    if (a.build_is_S) st_stream(a.out + at, t[j].key, bk);
+                                    else st_stream(a.out + at, bk, t[j].key);
+                                } else {
+                                    st_stream(a.out + at, RHJ_HOLE, RHJ_HOLE);
+                                }
+                            }
+                            my_miss += hit == kEmpty;
+                        }
+                    }
+                }
+                __syncthreads();  // everyone is done with this table before it is overwritten
+                continue;
+            }
+            if (single) {
+                // duplicate build keys after all: the reserved slots stay holes, the ranked path below reserves its own
+                const u64 base = s_posbase;
+                for (u64 i = tid; i < p1 - p0; i += kJoinThreads)
+                    if (base + i < a.capacity) st_stream(a.out + base + i, RHJ_HOLE, RHJ_HOLE);
+                if (tid == 0) my_miss += p1 - p0;
+            }
+
+            // probe
+            for (u64 q0 = p0; q0 < p1; q0 += ROUND) {
+                bool ok[ITEMS];
+#pragma unroll
+                for (int j = 0; j < ITEMS; ++j) {
                     u64 idx = q0 + (u64) j * kJoinThreads + tid;
                     ok[j] = idx < p1;
                     if (ok[j] && q0 != p0) t[j] = ld_stream(a.probe + idx);
                 }
                 if (!dup) {
                     // unique build keys: at most one match per probe tuple
-                    u32 m[kJoinItems], ball[kJoinItems];
+                    u32 m[ITEMS], ball[ITEMS];
                     u32 wtotal = 0;
 #pragma unroll
-                    for (int j = 0; j < kJoinItems; ++j) {
+                    for (int j = 0; j < ITEMS; ++j) {
                         m[j] = kEmpty;
                         if (ok[j]) {
                             u32 h = slot_of(t[j].val);
@@ -199,7 +266,7 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join(JoinA
                     __syncthreads();
                     u64 pos = s_base[rr] + wbase;
 #pragma unroll
-                    for (int j = 0; j < kJoinItems; ++j) {
+                    for (int j = 0; j < ITEMS; ++j) {
                         if (m[j] != kEmpty) {
                             u64 at = pos + __popc(ball[j] & lt_mask);
                             u64 bk = s_tup[m[j]].key;
@@ -213,10 +280,10 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join(JoinA
                     rr ^= 1;
                 } else {
                     // duplicate build keys: count every match, reserve, then re-walk and write
-                    u32 cnt[kJoinItems];
+                    u32 cnt[ITEMS];
                     u32 mine = 0;
 #pragma unroll
-                    for (int j = 0; j < kJoinItems; ++j) {
+                    for (int j = 0; j < ITEMS; ++j) {
                         cnt[j] = 0;
                         if (ok[j]) {
                             u32 h = slot_of(t[j].val);
@@ -249,7 +316,7 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join(JoinA
                     __syncthreads();
                     u64 at = s_base[rr] + wbase + (incl - mine);
 #pragma unroll
-                    for (int j = 0; j < kJoinItems; ++j) {
+                    for (int j = 0; j < ITEMS; ++j) {
                         if (cnt[j]) {
                             u32 h = slot_of(t[j].val);
                             u32 idx;
@@ -281,6 +348,10 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join(JoinA
                 if (lane == 0) a.item_cnt[item] = x;
             }
         }
+    }
+    if (POS) {
+        const u64 w = warp_sum64(my_miss);
+        if (lane == 0 && w) atomicAdd(a.holes, w);
     }
 }
 

@@ -851,4 +851,68 @@ __global__ void __launch_bounds__(1024) k_scan_items(const u64 *cnt, const u32 *
     }
 }
 
+// ---- closing the holes of a positional emit (rhj_join.cuh, k_join<FUSED, POS>) ------------------------------------
+// Order of the result is free, so the final count is F = cursor - holes and the valid pairs behind F move into the holes
+// before F.  k_holes_count / k_holes_scan / k_holes_list build the two position lists (holes in [0, F), valid pairs in
+// [F, cursor)), k_holes_fill moves.  Only launched when a join left holes.
+constexpr u32 kHoleTile = 2048;
+__device__ __forceinline__ bool is_hole(const Pair &q) { return q.r == RHJ_HOLE && q.s == RHJ_HOLE; }
+// cnt[tile] = holes of the tile that lie before F; cnt[ntiles + tile] = valid pairs of the tile at or behind F
+__global__ void __launch_bounds__(256) k_holes_count(const Pair *out, u64 cursor, u64 F, u32 ntiles, u32 *cnt) {
+    __shared__ u32 s_c[2];
+    if (threadIdx.x < 2) s_c[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 base = (u64) blockIdx.x * kHoleTile;
+    u32 h = 0, v = 0;
+    for (u32 k = threadIdx.x; k < kHoleTile; k += 256) {
+        const u64 i = base + k;
+        if (i < cursor) {
+            const bool hole = is_hole(out[i]);
+            h += i < F && hole;
+            v += i >= F && !hole;
+        }
+    }
+    h = (u32) warp_sum64(h);
+    v = (u32) warp_sum64(v);
+    if (lane_id() == 0) {
+        if (h) atomicAdd(&s_c[0], h);
+        if (v) atomicAdd(&s_c[1], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < 2) cnt[threadIdx.x * ntiles + blockIdx.x] = s_c[threadIdx.x];
+}
+// exclusive scans of both count arrays (one CTA each): off[part * ntiles + tile], totals[part]
+__global__ void __launch_bounds__(1024) k_holes_scan(const u32 *cnt, u32 ntiles, u64 *off, u64 *totals) {
+    __shared__ u64 s_w[33];
+    const u32 part = blockIdx.x;
+    const u32 per = (ntiles + 1023) / 1024;
+    const u32 i0 = min(ntiles, threadIdx.x * per), i1 = min(ntiles, i0 + per);
+    u64 c = 0;
+    for (u32 i = i0; i < i1; ++i) c += cnt[part * ntiles + i];
+    u64 total;
+    u64 run = block_excl_scan64(c, s_w, &total);
+    for (u32 i = i0; i < i1; ++i) {
+        off[part * ntiles + i] = run;
+        run += cnt[part * ntiles + i];
+    }
+    if (threadIdx.x == 0) totals[part] = total;
+}
+__global__ void __launch_bounds__(256) k_holes_list(const Pair *out, u64 cursor, u64 F, u32 ntiles, const u64 *off, u64 *list_head,
+                                                    u64 *list_tail) {
+    __shared__ u32 s_at[2];
+    if (threadIdx.x < 2) s_at[threadIdx.x] = 0;
+    __syncthreads();
+    const u64 base = (u64) blockIdx.x * kHoleTile;
+    for (u32 k = threadIdx.x; k < kHoleTile; k += 256) {
+        const u64 i = base + k;
+        if (i >= cursor) continue;
+        const bool hole = is_hole(out[i]);
+        if (i < F && hole) list_head[off[blockIdx.x] + atomicAdd(&s_at[0], 1u)] = i;
+        if (i >= F && !hole) list_tail[off[ntiles + blockIdx.x] + atomicAdd(&s_at[1], 1u)] = i;
+    }
+}
+__global__ void __launch_bounds__(256) k_holes_fill(Pair *out, const u64 *list_head, const u64 *list_tail, u64 k) {
+    for (u64 i = (u64) blockIdx.x * blockDim.x + threadIdx.x; i < k; i += (u64) gridDim.x * blockDim.x) out[list_head[i]] = out[list_tail[i]];
+}
+
 }  // namespace rhj

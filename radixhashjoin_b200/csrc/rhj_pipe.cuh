@@ -396,7 +396,13 @@ int rhj_pipe_join_device(rhj_ctx *ctx, rhj_pair *d_out, uint64_t capacity, uint6
     JoinArgs j = join_args(ctx, kScWork0);
     j.out = (Pair *) d_out;
     j.capacity = capacity;
-    if ((rc = launch_join<kJoinFused>(ctx, st, j, item_cap))) return rc;
+    j.holes = m.scalars + kScHoles;
+    // positional emit (rhj_join.cuh): one slot per probe tuple, no ranking and no reservation latency in the probe loop
+    bool pos = ctx->positional && ctx->pos_skip == 0;
+    if (!pos && ctx->pos_skip > 0) ctx->pos_skip--;
+    if (pos) rc = launch_join<kJoinFused, true>(ctx, st, j, item_cap);
+    else rc = launch_join<kJoinFused>(ctx, st, j, item_cap);
+    if (rc) return rc;
     PipeCollectArgs ca{};
     ca.status_in = pipe_status(ctx, P.rank, q);
     ca.status = m.scalars + kScPipeStatus;
@@ -408,7 +414,6 @@ int rhj_pipe_join_device(rhj_ctx *ctx, rhj_pair *d_out, uint64_t capacity, uint6
     u64 *sc = scalars_of(ctx, nparts);
     CK(cudaMemcpyAsync(ctx->h_scalars, sc, kScCount * sizeof(u64), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    ctx->cur.valid = false;
     u64 bits = ctx->h_scalars[kScPipeStatus] & 0xff;
     if (ctx->h_scalars[kScOverflow] & 1) bits |= kPipeOvf;
     if (ctx->h_scalars[kScOverflow] & 2) bits |= kPipeWide;
@@ -416,7 +421,24 @@ int rhj_pipe_join_device(rhj_ctx *ctx, rhj_pair *d_out, uint64_t capacity, uint6
     if (bits) return RHJ_OK;  // the caller redoes the step (or reports the timeout)
     if (ctx->h_scalars[kScErr]) return fail(ctx, RHJ_ERR_STATE, "device-side planning error (work-item table overflow)");
     ctx->info.n_items = (u32) ctx->h_scalars[kScNItems];
+    if (pos) {
+        const u64 cursor = ctx->h_scalars[kScCursor], holes = ctx->h_scalars[kScHoles];
+        bool ok = cursor <= capacity;
+        if (ok && holes) {
+            if ((rc = close_holes(ctx, st, (Pair *) d_out, cursor, holes, &ok))) return rc;
+            if (ok) ctx->h_scalars[kScCursor] = cursor - holes;
+            if (holes * 64 > cursor) ctx->pos_skip = 16;
+        }
+        if (!ok) {  // the slots did not fit the buffer (or a genuine pair looks like a hole): the ranked emitter over the same items
+            CK(cudaMemsetAsync(sc + kScWork0, 0, 8, st));
+            CK(cudaMemsetAsync(sc + kScCursor, 0, 8, st));
+            if ((rc = launch_join<kJoinFused>(ctx, st, j, item_cap))) return rc;
+            CK(cudaMemcpyAsync(ctx->h_scalars, sc, kScCount * sizeof(u64), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+    }
     *count = ctx->h_scalars[kScCursor];
+    ctx->cur.valid = false;
     if (*count > capacity) return fail(ctx, RHJ_ERR_CAPACITY, "output buffer too small for the fused emitter");
     return RHJ_OK;
 }
