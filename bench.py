@@ -9,7 +9,9 @@ A "step" is one complete radix hash join (histogram -> prefix sum -> partition s
 build/probe -> emit) of the workload; inputs are resident in HBM before the timed region, the
 result stays in HBM.  N = 1 runs BASELINE.json configs[1] (2^27 x 2^27 unique uniform u64 keys).
 N > 1 is weak scaling: every rank owns 2^27 + 2^27 tuples of a global 2^(27+log2 N) pair of relations;
-a step = radix-partition both local shards by destination rank, NCCL all-to-all over NVLink, local join.
+a step = the pipelined exchange (histogram-free chunked pass 1 on (rank | sub-digit), our TMA copy kernel over NVLink,
+appended pass 2, one join; radixhashjoin_b200/distributed.py).  --shuffle dma|nccl select the exact exchange and the
+NCCL all-to-all baseline; --workload fk runs config 3 (broadcast build side, strong scaling).
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 """
@@ -460,10 +462,11 @@ def run_b200(args, rank, world, local_rank):
     value = n_in_local * world / (ms_step * 1e-3)
 
     # ---- verification of the timed configuration (outside the timed region) ----
-    dig = eng.pairs_digest(pairs)
-    if world == 1:
-        verified = tuple(dig) == tuple(expected)
-    else:
+    def verify(dig):
+        """count + multiset digest of this rank's pairs against the closed form (N > 1: reduced over the ranks)"""
+        if world == 1:
+            return tuple(dig) == tuple(expected)
+
         def _i64(v):
             return v - (1 << 64) if v >= (1 << 63) else v
         # every rank knows the closed-form digest of what ITS probe rows must produce; digests add up (count, sum) / xor
@@ -476,7 +479,9 @@ def run_b200(args, rank, world, local_rank):
             x ^= a
             e ^= b
         m64 = (1 << 64) - 1
-        verified = (int(tot[0].item()), int(tot[1].item()) & m64, x) == (int(tot[2].item()), int(tot[3].item()) & m64, e)
+        return (int(tot[0].item()), int(tot[1].item()) & m64, x) == (int(tot[2].item()), int(tot[3].item()) & m64, e)
+
+    verified = verify(eng.pairs_digest(pairs))
     m_local = count
 
     shard_timeline = None
@@ -580,9 +585,28 @@ def run_b200(args, rank, world, local_rank):
         del dres, pR, pS
         e2e["pageable"] = {"value": n_in_local / dtp, "unit": UNIT, "ms_per_step": dtp * 1e3, "steps": kp, "verified": ok_p,
                            "note": "inputs in pageable (malloc'd) host arrays, as host/Result.cpp passes them"}
+    elif world > 1 and args.no_e2e:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "--no-e2e"}
     elif world > 1:
-        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "note": "multi-GPU run keeps shards device-resident; e2e is reported at N=1"}
+        # the shards live in pinned HOST memory: every step copies this rank's R and S to the device, runs the sharded join
+        # and copies the pairs back (radixhashjoin_b200/distributed.py: HostResidentSteps); wall clock, max over ranks
+        from radixhashjoin_b200.distributed import HostResidentSteps
+        hs = HostResidentSteps(step, R, S, out, world, dist=dist, local_world=env_int("LOCAL_WORLD_SIZE", world))
+        if hs.ok:
+            k = max(1, min(args.steps, args.e2e_steps))
+            dt, cnt, d2h = hs.run(k, warmup=1)
+            out[:cnt].copy_(hs.hout[:cnt])   # the HOST copy of the last result is what gets checked
+            e2e_ok = verify(eng.pairs_digest(out[:cnt]))
+            by = torch.tensor([hs.h2d_bytes, d2h], dtype=torch.int64, device=dev)
+            dist.all_reduce(by, op=dist.ReduceOp.SUM)
+            e2e = {"value": n_in_local * world / dt, "unit": UNIT, "h2d_bytes_per_step": int(by[0].item()),
+                   "d2h_bytes_per_step": int(by[1].item()), "ms_per_step": dt * 1e3, "steps": k, "verified": e2e_ok,
+                   "api": f"{strategy} sharded join with host-resident shards: per step and rank H2D of both shards from pinned "
+                          "host memory -> exchange + join -> D2H of the pairs into pinned host memory, read by the host; "
+                          "bytes are summed over the ranks, the time is the slowest rank's wall clock"}
+        else:
+            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": hs.why}
+        del hs
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only, bounded sample) ----
     cpu = None

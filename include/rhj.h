@@ -245,6 +245,7 @@ int rhj_shardx_pass1_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int rel, c
                             rhj_tuple *d_stage, uint64_t *d_hist, void *stream);
 int rhj_shardx_layout_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int rank, int rel, const uint64_t *d_all_hist,
                              uint64_t *send_off, uint64_t *send_cnt, uint64_t *dst_off, uint64_t *recv_total,
+                             uint64_t *recv_max /* optional: largest recv_total of any rank, equal on all ranks */,
                              void *stream);
 int rhj_shardx_pass2_device(rhj_ctx *ctx, const rhj_shard_plan *plan, int rel, const rhj_tuple *d_recv, uint64_t n_recv,
                             void *stream);

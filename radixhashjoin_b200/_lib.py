@@ -101,7 +101,7 @@ SIGNATURES = {
     "rhj_shardx_begin": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), c_vp]),
     "rhj_shardx_pass1_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, c_vp, c_u64, c_vp, c_vp, c_vp]),
     "rhj_shardx_layout_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, ctypes.c_int, c_vp, c_u64p,
-                                                c_u64p, c_u64p, c_u64p, c_vp]),
+                                                c_u64p, c_u64p, c_u64p, c_u64p, c_vp]),
     "rhj_shardx_pass2_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), ctypes.c_int, c_vp, c_u64, c_vp]),
     "rhj_shardx_join_device": (ctypes.c_int, [c_vp, ctypes.POINTER(ShardPlan), c_vp, c_u64, c_u64p, c_vp]),
     "rhj_pipe_sym_bytes": (c_u64, [ctypes.POINTER(ShardPlan), ctypes.POINTER(PipeCfg)]),

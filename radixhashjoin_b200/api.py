@@ -218,13 +218,14 @@ class RadixHashJoin:
                                                    self._stream(stream)))
 
     def shardx_layout(self, plan, rank, rel, all_hist, stream=None):
-        """(send_off[d], send_cnt[d], dst_off[d], recv_total) from the all-gathered histograms"""
+        """(send_off[d], send_cnt[d], dst_off[d], recv_total, recv_max) from the all-gathered histograms; recv_max = the
+        largest recv_total of any rank (the same number on every rank)"""
         W = plan.world
         so, sc, do = (ctypes.c_uint64 * W)(), (ctypes.c_uint64 * W)(), (ctypes.c_uint64 * W)()
-        tot = ctypes.c_uint64()
+        tot, worst = ctypes.c_uint64(), ctypes.c_uint64()
         self._ck(self._lib.rhj_shardx_layout_device(self._ctx, ctypes.byref(plan), rank, rel, _ptr(all_hist), so, sc, do,
-                                                    ctypes.byref(tot), self._stream(stream)))
-        return [int(v) for v in so], [int(v) for v in sc], [int(v) for v in do], int(tot.value)
+                                                    ctypes.byref(tot), ctypes.byref(worst), self._stream(stream)))
+        return [int(v) for v in so], [int(v) for v in sc], [int(v) for v in do], int(tot.value), int(worst.value)
 
     def shardx_pass2(self, plan, rel, recv, stream=None):
         n = _check_rel(recv)

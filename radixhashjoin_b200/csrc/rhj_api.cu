@@ -1011,8 +1011,7 @@ int join_host_pipelined(rhj_ctx *ctx, const Tup *hR, u64 nR, const Tup *hS, u64 
                 ctx->h_out_cap = guess * sizeof(Pair);
             }
             if (c >= 2) CK(cudaStreamWaitEvent(st, ctx->ev_out[b], 0));  // result buffer b is free again
-            else if (n_out * sizeof(Pair) > ctx->pout[b].cap) CK(cudaStreamSynchronize(ctx->s_out));
-            if (n_out * sizeof(Pair) > ctx->pout[b].cap) CK(cudaStreamSynchronize(ctx->s_out));
+            if (n_out * sizeof(Pair) > ctx->pout[b].cap) CK(cudaStreamSynchronize(ctx->s_out));  // ... before it is regrown
             if ((rc = ensure(ctx, ctx->pout[b], n_out * sizeof(Pair)))) return rc;
             if ((rc = write_phase(ctx, st, (Pair *) ctx->pout[b].p, n_out))) return rc;
         }
@@ -1569,10 +1568,13 @@ int rhj_shardx_pass1_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rel, con
 //   send_off[d], send_cnt[d]  this rank's chunk for destination d inside its staging buffer (tuples)
 //   dst_off[d]                where that chunk starts inside destination d's receive buffer
 //   *recv_total               tuples this rank receives
+//   *recv_max                 (optional) the largest recv_total of any rank: the same number on every rank, so a receive
+//                             buffer that is too small SOMEWHERE is an error every rank can raise together (a rank that
+//                             stops alone leaves its peers waiting in the exchange)
 // Synchronises the stream.
 int rhj_shardx_layout_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rank, int rel, const uint64_t *d_all_hist,
                              uint64_t *send_off, uint64_t *send_cnt, uint64_t *dst_off, uint64_t *recv_total,
-                             void *stream) {
+                             uint64_t *recv_max, void *stream) {
     if (!ctx || !sp || !d_all_hist || !send_off || !send_cnt || !dst_off || !recv_total || rel < 0 || rel > 1 || rank < 0 ||
         rank >= (int) sp->world)
         return RHJ_ERR_ARG;
@@ -1623,6 +1625,15 @@ int rhj_shardx_layout_device(rhj_ctx *ctx, const rhj_shard_plan *sp, int rank, i
         total += h_tot[d * W + rank];
     }
     *recv_total = total;
+    if (recv_max) {
+        u64 worst = 0;
+        for (u32 d = 0; d < W; ++d) {
+            u64 in = 0;
+            for (u32 s2 = 0; s2 < W; ++s2) in += h_tot[s2 * W + d];
+            worst = std::max(worst, in);
+        }
+        *recv_max = worst;
+    }
     ctx->shard_n[rel] = total;
     return RHJ_OK;
 }

@@ -110,6 +110,113 @@ def broadcast_is_cheaper(nR_global, nS_global, world):
     return world > 1 and nB * world <= nP
 
 
+def host_memory_available():
+    """Bytes of host RAM this process group may still take: the smaller of the machine's available memory and what is
+    left under the cgroup limit (a container that is OOM-killed cannot report anything)."""
+    import psutil
+    avail = psutil.virtual_memory().available
+    try:
+        with open("/sys/fs/cgroup/memory.max") as f:
+            lim = f.read().strip()
+        if lim != "max":
+            with open("/sys/fs/cgroup/memory.current") as f:
+                avail = min(avail, int(lim) - int(f.read().strip()))
+    except (OSError, ValueError):
+        pass
+    return max(0, int(avail))
+
+
+class HostResidentSteps:
+    """End-to-end driver of a sharded join whose shards live in HOST memory (bench.py `e2e` at N > 1): every timed step
+    copies this rank's R and S shards from pinned host memory into the device tensors the join reads, runs one sharded
+    join (`step_fn`, any of the classes below) and copies the result pairs back into a pinned host buffer, which the host
+    then reads.  Nothing is overlapped across steps: a step is H2D -> exchange + join -> D2H.
+
+    Whether the pinned buffers could be allocated is AGREED between the ranks before the first step (one all-reduce), so
+    that a rank which is out of host memory makes every rank skip the measurement instead of leaving its peers waiting in
+    the exchange.  `alloc_host` / `sync` / `avail_fn` are injectable for the CPU (gloo) test of this logic."""
+
+    SAFETY = 1.5      # pinned bytes of all local ranks x this must fit the host's available memory
+
+    def __init__(self, step_fn, R, S, out, world, dist=None, group=None, alloc_host=None, sync=None, avail_fn=None,
+                 local_world=None):
+        import torch
+        self.torch = torch
+        self.step_fn, self.R, self.S, self.out = step_fn, R, S, out
+        self.world, self.dist, self.group = world, dist, group
+        self.sync = sync if sync is not None else (lambda: torch.cuda.synchronize(R.device))
+        alloc_host = alloc_host if alloc_host is not None else (lambda shape: torch.empty(shape, dtype=torch.int64, pin_memory=True))
+        avail_fn = avail_fn if avail_fn is not None else host_memory_available
+        self.h2d_bytes = 8 * (R.numel() + S.numel())
+        need = self.h2d_bytes + 8 * out.numel()
+        self.hR = self.hS = self.hout = None
+        self.why = None
+        # phase 1: every rank looks at the host's free memory BEFORE anyone allocates (the ranks of one box share it)
+        ok = self._all(need * (local_world or world) * self.SAFETY <= avail_fn())
+        if not ok:
+            self.why = "not enough host memory for pinned copies of every rank's shards and result"
+        else:
+            # phase 2: allocate, then agree again
+            try:
+                self.hR, self.hS, self.hout = alloc_host(tuple(R.shape)), alloc_host(tuple(S.shape)), alloc_host(tuple(out.shape))
+                self.hR.copy_(R)
+                self.hS.copy_(S)
+                self.sync()
+                mine = True
+            except (RuntimeError, MemoryError) as ex:
+                mine, self.why = False, f"pinned host allocation failed: {str(ex)[:120]}"
+            ok = self._all(mine)
+            if not ok and self.why is None:
+                self.why = "another rank could not allocate its pinned host buffers"
+        self.ok = ok
+        if not self.ok:
+            self.hR = self.hS = self.hout = None
+
+    def _all(self, flag):
+        if self.dist is None or self.world == 1:
+            return bool(flag)
+        t = self.torch.tensor([1 if flag else 0], dtype=self.torch.int64, device=self.R.device)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN, group=self.group)
+        return bool(int(t.item()))
+
+    def one(self):
+        """H2D of both shards -> one sharded join -> D2H of the pairs; returns (host pairs view, count)."""
+        self.R.copy_(self.hR, non_blocking=True)
+        self.S.copy_(self.hS, non_blocking=True)
+        pairs, count = self.step_fn()
+        if count:
+            self.hout[:count].copy_(pairs, non_blocking=True)
+        self.sync()
+        return self.hout[:count], count
+
+    def run(self, steps, warmup=1):
+        """(seconds per step = max over ranks, count of the last step, D2H bytes of the last step on this rank)"""
+        import time
+        assert self.ok, self.why
+        for _ in range(warmup):
+            self.one()
+        self._barrier()
+        t0 = time.perf_counter()
+        count = 0
+        first = 0
+        for _ in range(steps):
+            view, count = self.one()
+            first ^= int(view[0, 0]) if count else 0     # the host reads the result
+        dt = (time.perf_counter() - t0) / steps
+        self._barrier()
+        if self.dist is not None and self.world > 1:
+            t = self.torch.tensor([dt], dtype=self.torch.float64, device=self.R.device)
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX, group=self.group)
+            dt = float(t.item())
+        return dt, count, 16 * count
+
+    def _barrier(self):
+        self.sync()
+        if self.dist is not None and self.world > 1:
+            self.dist.barrier(group=self.group)
+        self.sync()
+
+
 class BroadcastShardedJoin:
     """Multi-GPU join for a small build side (foreign-key joins, BASELINE config 3): every rank gathers the
     whole build relation (one all-gather of nB tuples; the probe relation is never shuffled) and joins it with
@@ -312,7 +419,7 @@ class DmaShardedJoin:
     def _ship(self, slot, lay, marks=None):
         """peer copies of one relation on the copy stream, fenced by device-side barriers"""
         torch = self.torch
-        send_off, send_cnt, dst_off, _ = lay
+        send_off, send_cnt, dst_off = lay[:3]
         cs = self.copy_stream
         cs.wait_stream(torch.cuda.current_stream())        # the staging buffer is complete
         with torch.cuda.stream(cs):
@@ -359,8 +466,11 @@ class DmaShardedJoin:
                 marks.append((f"pass1_{s}_done", self._mark()))
             self.dist.all_gather_into_tensor(self.all_hist[s], self.hist[s], group=self.group)
             lay[s] = eng.shardx_layout(plan, self.rank, s, self.all_hist[s])
-            if lay[s][3] > self.capacity[s]:
-                raise RuntimeError(f"rank {self.rank}: receive buffer of relation {s} too small ({lay[s][3]} > {self.capacity[s]})")
+            if lay[s][4] > self.capacity[s]:
+                # lay[s][4] = the largest share any rank receives, the same number everywhere: all ranks raise together
+                # (a rank that stopped alone would leave its peers waiting in the device-side barriers of _ship)
+                raise RuntimeError(f"rank {self.rank}: receive buffers of relation {s} too small on some rank "
+                                   f"({lay[s][4]} > {self.capacity[s]} tuples; this rank receives {lay[s][3]})")
             landed[s] = self._ship(s, lay[s], marks)         # in flight while the next relation is partitioned
         for s in self.slots:
             torch.cuda.current_stream().wait_event(landed[s])

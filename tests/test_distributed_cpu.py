@@ -121,3 +121,96 @@ def test_sharded_workload_generators_tile_the_global_relations():
     d0 = W.uniform_unique_global_digest(12, lo=0, hi=2048)
     d1 = W.uniform_unique_global_digest(12, lo=2048, hi=4096)
     assert (d0[0] + d1[0], (d0[1] + d1[1]) & M, d0[2] ^ d1[2]) == tuple(g.expected)
+
+
+def _e2e_worker(rank, world, port, q):
+    """HostResidentSteps (bench.py's e2e at N > 1) over gloo: the host buffers are plain CPU tensors, the sharded join is the
+    numpy partitioner + oracle join of the test above."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from radixhashjoin_b200.distributed import HostResidentSteps
+    gbits = LOG2_LOCAL + (world.bit_length() - 1)
+    n_local = 1 << LOG2_LOCAL
+    w = W.uniform_unique(LOG2_LOCAL, "cpu", row_offset=rank * n_local, log2_global=gbits)
+    R, S = w.R.clone(), w.S.clone()
+    out = torch.zeros((2 * n_local, 2), dtype=torch.int64)
+
+    def join_fn(a, b):
+        p = O.oracle_join(W.to_numpy_tuples(a), W.to_numpy_tuples(b))
+        t = torch.from_numpy(p.view(np.uint64).reshape(-1, 2).view(np.int64).copy())
+        out[:len(p)] = t
+        return out[:len(p)], len(p)
+
+    sj = ShardedJoin(world, rank, lambda T: cpu_partition_by_rank(T, world), join_fn)
+
+    def step():
+        pairs, count, _ = sj.step(R, S)
+        return pairs, count
+
+    def alloc(shape):
+        return torch.empty(shape, dtype=torch.int64)
+
+    def alloc_fails_on_rank0(shape):
+        if rank == 0:
+            raise RuntimeError("CUDA error: out of memory (simulated)")
+        return alloc(shape)
+
+    res = {}
+    # (a) everything fits: host copies are made, the device tensors are refilled from them in every step
+    hs = HostResidentSteps(step, R, S, out, world, dist=dist, alloc_host=alloc, sync=lambda: None, avail_fn=lambda: 1 << 40)
+    assert hs.ok and hs.h2d_bytes == 16 * 2 * n_local
+    R.zero_()
+    S.zero_()            # the next step must bring the shards back from the host copies
+    dt, count, d2h = hs.run(2, warmup=1)
+    cnt, s, x = O.pairs_digest(hs.hout[:count].numpy().view(np.uint64).reshape(-1, 2).copy().view(O.PAIR).reshape(-1))
+    parts = [None] * world
+    dist.all_gather_object(parts, (cnt, s, x))
+    res["a"] = (dt > 0, d2h == 16 * count, parts, torch.equal(R, w.R) and torch.equal(S, w.S))
+    # (b) ONE rank sees too little host memory: every rank skips, with a reason, and nobody allocates
+    hs = HostResidentSteps(step, R, S, out, world, dist=dist, alloc_host=alloc, sync=lambda: None,
+                           avail_fn=(lambda: 0) if rank == 1 else (lambda: 1 << 40))
+    res["b"] = (hs.ok, hs.why, hs.hR is None)
+    # (c) ONE rank's allocation fails: every rank skips
+    hs = HostResidentSteps(step, R, S, out, world, dist=dist, alloc_host=alloc_fails_on_rank0, sync=lambda: None,
+                           avail_fn=lambda: 1 << 40)
+    res["c"] = (hs.ok, hs.why, hs.hR is None)
+    q.put((rank, res))
+    dist.destroy_process_group()
+
+
+def test_host_resident_steps_agree_across_ranks():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_e2e_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    gbits = LOG2_LOCAL + 1
+    exp = W.uniform_unique_global_digest(gbits)
+    for rank in range(world):
+        timed, d2h_ok, parts, refilled = res[rank]["a"]
+        assert timed and d2h_ok and refilled
+        assert sum(p[0] for p in parts) == exp[0]
+        assert sum(p[1] for p in parts) & ((1 << 64) - 1) == exp[1]
+        x = 0
+        for p in parts:
+            x ^= p[2]
+        assert x == exp[2]
+        for case in ("b", "c"):
+            ok, why, freed = res[rank][case]
+            assert ok is False and why and freed
+    assert "host memory" in res[1]["b"][1] and "host memory" in res[0]["b"][1]
+    assert "simulated" in res[0]["c"][1] and "another rank" in res[1]["c"][1]
+
+
+def test_host_memory_available_is_bounded_by_the_machine():
+    import psutil
+    from radixhashjoin_b200.distributed import host_memory_available
+    a = host_memory_available()
+    assert 0 < a <= psutil.virtual_memory().total

@@ -434,7 +434,8 @@ def test_dma_shard_join_emulated_ranks(world, n_local, dom):
     for rel in (0, 1):
         assert sum(lay[r][rel][3] for r in range(world)) == world * n_local
         for r in range(world):                                                           # the peer copies
-            so, sc, do, _ = lay[r][rel]
+            so, sc, do, _, worst = lay[r][rel]
+            assert worst == max(lay[q][rel][3] for q in range(world))   # every rank knows the largest share
             for d in range(world):
                 recv[d][rel][do[d]:do[d] + sc[d]].copy_(stage[r][rel][so[d]:so[d] + sc[d]])
     torch.cuda.synchronize()
@@ -487,7 +488,8 @@ def test_dma_shard_join_histogram_free_second_pass(hot, monkeypatch):
     recv = [[torch.empty((max(lay[r][rel][3], 1), 2), dtype=torch.int64, device=DEV) for rel in (0, 1)] for r in range(world)]
     for rel in (0, 1):
         for r in range(world):
-            so, sc, do, _ = lay[r][rel]
+            so, sc, do, _, worst = lay[r][rel]
+            assert worst == max(lay[q][rel][3] for q in range(world))   # every rank knows the largest share
             for d in range(world):
                 recv[d][rel][do[d]:do[d] + sc[d]].copy_(stage[r][rel][so[d]:so[d] + sc[d]])
     torch.cuda.synchronize()
