@@ -241,6 +241,34 @@ u64 *scalars_of(rhj_ctx *ctx, u32 nparts) {
     return (u64 *) ctx->zero.p + 2 * (size_t) kMaxDigits + 2 * (size_t) nparts;
 }
 
+// The positional emitter.  Default: k_join_pos (build partitions of one chunk with unique keys; instruction-level-parallel
+// loops) followed by k_join<FUSED> over the items it left (several build chunks, duplicate build keys -- usually none).
+// RHJ_JOIN_LEAN=0: the r02 kernel k_join<FUSED, POS>, which handles everything in one launch.
+int launch_join_positional(rhj_ctx *ctx, cudaStream_t st, const JoinArgs &a, u32 item_cap) {
+    if (!ctx->join_lean) return launch_join<kJoinFused, true>(ctx, st, a, item_cap);
+    int rc;
+    if ((rc = ensure(ctx, ctx->items_left, (size_t) std::max<u32>(item_cap, 1) * sizeof(Item)))) return rc;
+    u64 *sc = scalars_of(ctx, ctx->cur.nparts);
+    Item *left = (Item *) ctx->items_left.p;
+    u32 *nleft = (u32 *) (sc + kScLeft);
+    const u32 grid = std::min<u32>(std::max<u32>(item_cap, 1), (u32) ctx->num_sms * RHJ_JOIN_MINBLOCKS);
+    if (ctx->join_pos_items == 4) {   // four tuples per thread and round, no prefetch (the second tuple set would spill)
+        CK(set_smem(k_join_pos<4, false>, kJoinSmem));
+        k_join_pos<4, false><<<grid, kJoinThreads, kJoinSmem, st>>>(a, left, nleft);
+    } else {                          // three tuples per thread and round, the next round's in flight
+        CK(set_smem(k_join_pos<3, true>, kJoinSmem));
+        k_join_pos<3, true><<<grid, kJoinThreads, kJoinSmem, st>>>(a, left, nleft);
+    }
+    CK(cudaGetLastError());
+    ctx->info.kernel_launches++;
+    JoinArgs r = a;   // the ranked emitter over the leftover list, appending behind the same output cursor
+    r.items = (const Item *) ctx->items_left.p;
+    r.nitems = (const u32 *) (sc + kScLeft);
+    r.work_counter = (u32 *) (sc + kScWork1);
+    return launch_join<kJoinFused>(ctx, st, r, item_cap);
+}
+
+
 // Builds the per-tile descriptor tables of a segmented pass (one 16-byte entry per tile) and points
 // the relations at them.  `slot` 0/1 selects the half of ctx->tiles a lone relation uses.
 int build_tile_tables(rhj_ctx *ctx, cudaStream_t st, PartArgs &b, int nrel, int slot = 0) {
@@ -1061,6 +1089,8 @@ int rhj_create(int device, rhj_ctx **out) {
     if ((e = getenv("RHJ_NO_OPT2"))) ctx->optimistic2 = atoi(e) == 0;
     if ((e = getenv("RHJ_NO_TRUST"))) ctx->trust_sample = atoi(e) == 0;
     if ((e = getenv("RHJ_NO_POS"))) ctx->positional = atoi(e) == 0;
+    if ((e = getenv("RHJ_JOIN_LEAN"))) ctx->join_lean = atoi(e) != 0;
+    if ((e = getenv("RHJ_JOIN_POS_ITEMS"))) ctx->join_pos_items = atoi(e);
     if ((e = getenv("RHJ_NO_SHARD_OPT2"))) ctx->shard_optimistic2 = atoi(e) == 0;
     if ((e = getenv("RHJ_SHARD_OPT2_WORLD"))) ctx->shard_opt2_world = (u32) std::max(0, atoi(e));
     if ((e = getenv("RHJ_HOST_CHUNK"))) ctx->host_chunk = std::max<long long>(1, atoll(e));
@@ -1236,7 +1266,7 @@ int rhj_join_device(rhj_ctx *ctx, const rhj_tuple *dR, uint64_t nR, const rhj_tu
         j.capacity = capacity;
         j.holes = scalars_of(ctx, ctx->cur.nparts) + kScHoles;
         mark(ctx, st, RHJ_PHASE_JOIN);
-        if (pos) rc = launch_join<kJoinFused, true>(ctx, st, j, ctx->cur.item_cap);
+        if (pos) rc = launch_join_positional(ctx, st, j, ctx->cur.item_cap);
         else rc = launch_join<kJoinFused>(ctx, st, j, ctx->cur.item_cap);
         if (rc) return rc;
         mark(ctx, st, -1);

@@ -16,6 +16,7 @@ using namespace rhj;
 static_assert(sizeof(rhj_tuple) == sizeof(Tup), "tuple layout");
 static_assert(sizeof(rhj_pair) == sizeof(Pair), "pair layout");
 
+#define RHJ_JOIN_POS_ITEMS_DEFAULT 3
 struct DevBuf {
     void *p = nullptr;
     size_t cap = 0;
@@ -35,6 +36,7 @@ enum Scalar {
     kScOverflow = 9,  // optimistic pass 1: a partition outgrew its fixed-capacity region
     kScHoles = 10,       // positional emit: reserved output slots left without a match
     kScPipeStatus = 11,  // pipelined exchange: RHJ_PIPE_* bits of this step, own and received
+    kScLeft = 12,        // k_join_pos: items left to the ranked kernel
     kScCount = 16
 };
 
@@ -62,6 +64,8 @@ struct rhj_ctx {
     // probe tuple matches (foreign-key style joins); a join that left more than 1/64 holes switches it off for the next 16.
     bool positional = true;    // RHJ_NO_POS=1 disables
     int pos_skip = 0;
+    int join_pos_items = RHJ_JOIN_POS_ITEMS_DEFAULT;  // probe tuples per thread and round of k_join_pos: 3 (default) or 4 (RHJ_JOIN_POS_ITEMS)
+    bool join_lean = true;     // positional emitter = k_join_pos + leftover launch (RHJ_JOIN_LEAN=0: the r02 kernel k_join<FUSED, POS>)
     DevBuf sample;            // sampled pass-1 histogram
     int scatter_mode = 0;     // 0 staged per-thread stores, 1 TMA bulk stores (RHJ_SCATTER_MODE)
     int shard_scatter_mode = 1;  // same choice for pass 1 of the exact sharded exchange (local staging): bulk stores were
@@ -74,6 +78,7 @@ struct rhj_ctx {
     DevBuf zero;              // hist1 | hist2 | scalars   (memset to 0 per call)
     DevBuf meta;              // offsets, cursors, tile tables
     DevBuf items, item_cnt, item_off;
+    DevBuf items_left;        // work items k_join_pos hands to the ranked kernel
     DevBuf filt_cnt, filt_off, filt_tmp;
     DevBuf inR, inS, outP;    // device staging of the host entry point
     DevBuf pin[2], pout[2], pA, pB;      // pipelined host join: probe chunk in (x2), result out (x2), chunk partitions
@@ -145,7 +150,7 @@ struct rhj_ctx {
 
 template <typename F>
 inline void for_each_buf(rhj_ctx *c, F f) {
-    DevBuf *bufs[] = {&c->bufA, &c->bufB, &c->tiles, &c->sample, &c->bufB2, &c->shard_meta, &c->zero, &c->meta, &c->items, &c->item_cnt, &c->item_off, &c->filt_cnt,
+    DevBuf *bufs[] = {&c->bufA, &c->bufB, &c->tiles, &c->sample, &c->bufB2, &c->shard_meta, &c->zero, &c->meta, &c->items, &c->items_left, &c->item_cnt, &c->item_off, &c->filt_cnt,
                       &c->filt_off, &c->filt_tmp, &c->inR, &c->inS, &c->outP, &c->pin[0], &c->pin[1], &c->pout[0], &c->pout[1],
                       &c->pA, &c->pB, &c->iu_col, &c->iu_pairs, &c->iu_A,
                       &c->iu_B, &c->iu_ep, &c->iu_out, &c->pipe.stage[0], &c->pipe.stage[1], &c->pipe.cursors, &c->pipe.segs,

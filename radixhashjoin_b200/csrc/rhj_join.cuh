@@ -355,5 +355,223 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join(JoinA
     }
 }
 
+// ---- k_join_pos: the positional emitter as a kernel of its own ---------------------------------------------------------
+// k_join<FUSED, POS> above handles one tuple at a time: every build tuple pays the dependent chain value read -> hash ->
+// CAS, every probe tuple hash -> slot read -> value read -> key read, with nothing else of the same warp to issue meanwhile
+// (ncu of the r02 build: 17.7 cycles between two issues of a warp, 0.9 eligible warps per scheduler, issue slots 51 % busy),
+// and the kernel carries the state of the ranked and duplicate-key paths through its hot loops (56 registers, the hash is
+// re-derived and the shared-memory window base re-read, S2R SR_CgaCtaId, in front of every access).
+// This kernel takes ONLY the common case -- a build partition that fits one table and has no duplicate keys -- and hands
+// every other item to k_join<FUSED> through the list left[*nleft] (a second, usually empty launch).  That leaves registers for
+// instruction-level parallelism:
+//   * build and probe do each step for ITEMS (3) tuples of the thread back to back (hashes, slot reads / CAS, value
+//     reads, key reads: independent, so their latencies overlap); only a tuple whose first slot held another key walks on;
+//   * pk = slot index << 16 | build index found there (0xFFFF: none) carries both in one register, so the walk needs no
+//     second hash;
+//   * shared memory is addressed from one opaque base register (ld.shared / atom.shared by 32-bit address);
+//   * the probe tuples of round r + 1 are loaded while round r is probed (three tuples per thread and round: a 2048-tuple
+//     partition is two rounds at 89 % lane use instead of 1 1/3 rounds of four at 67 %);
+//   * offsets inside an item are 32-bit; the output capacity is checked once per item, the build side once per round.
+static_assert(kBuildCap < 0xFFFFu && kSlots <= 0x10000u, "k_join_pos packs (slot index, build index) into 16 + 16 bits");
+
+__device__ __forceinline__ u32 smem_base_opaque(const void *p) {
+    u32 a = smem_u32(p), b;
+    asm volatile("mov.u32 %0, %1;" : "=r"(b) : "r"(a));
+    return b;
+}
+// `volatile` + "memory": these stay behind the barrier / mbarrier wait they follow; independent ones still issue back to back
+__device__ __forceinline__ u32 lds32(u32 addr) {
+    u32 v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ u64 lds64(u32 addr) {
+    u64 v;
+    asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ u32 cas32_shared(u32 addr, u32 cmp, u32 val) {
+    u32 old;
+    asm volatile("atom.shared.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"(addr), "r"(cmp), "r"(val) : "memory");
+    return old;
+}
+
+// PF: prefetch the next round's probe tuples (a second tuple set: 4 registers per tuple); without it a round loads its own.
+template <int ITEMS, bool PF>
+__global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join_pos(JoinArgs a, Item *left, u32 *nleft) {
+    constexpr u32 T = kJoinThreads, ROUND = T * ITEMS;
+    extern __shared__ __align__(128) unsigned char dyn_smem[];   // [kBuildCap] staged build tuples | [kSlots] u32 slots
+    __shared__ __align__(8) u64 s_bar;
+    __shared__ u32 s_item;
+    __shared__ u64 s_posbase;
+
+    const u32 tid = threadIdx.x;
+    const u32 sb = smem_base_opaque(dyn_smem);                 // shared address of the staged tuples ...
+    const u32 sl = sb + kBuildCap * (u32) sizeof(Tup);         // ... and of the slot table
+    u32 miss = 0;      // reserved slots of this thread's probe tuples that found no match (far fewer than 2^32 per launch)
+    u64 miss_items = 0;  // thread 0: slots of whole items handed to the ranked kernel
+    if (tid == 0) mbar_init(&s_bar, 1);
+    __syncthreads();
+    const u32 nitems = *a.nitems;
+    u32 phase = 0;
+
+    while (true) {
+        if (tid == 0) s_item = atomicAdd(a.work_counter, 1u);
+        __syncthreads();
+        const u32 item = s_item;
+        if (item >= nitems) break;
+        const Item it = a.items[item];
+        const u64 b0 = a.offB[it.part], b1 = a.endB[it.part];
+        const u64 p0 = a.offP[it.part] + (u64) it.chunk * kProbeChunk;
+        const u64 p1 = min(a.endP[it.part], p0 + (u64) kProbeChunk);
+        if (b1 - b0 > kBuildCap) {   // several build chunks (duplicate-heavy keys no radix bit can split)
+            if (tid == 0) left[atomicAdd(nleft, 1u)] = it;
+            __syncthreads();         // nobody is still reading s_item when thread 0 overwrites it
+            continue;
+        }
+        const u32 nb = (u32) (b1 - b0), n = (u32) (p1 - p0);   // n <= kProbeChunk
+        u64 posres = 0;
+        if (tid == 0) {
+            // one output slot per probe tuple, reserved now; the value is first looked at behind the build
+            posres = atomicAdd(a.out_cursor, (u64) n);
+            mbar_expect_tx(&s_bar, nb * (u32) sizeof(Tup));
+            bulk_g2s(dyn_smem, a.build + b0, nb * (u32) sizeof(Tup), &s_bar);
+        }
+        const Tup *const inp = a.probe + p0;
+        Tup t[ITEMS];
+#pragma unroll
+        for (int j = 0; j < ITEMS; ++j) {
+            const u32 o = j * T + tid;
+            if (o < n) t[j] = ld_stream(inp + o);
+        }
+        {
+            uint4 *slots = reinterpret_cast<uint4 *>(dyn_smem + (size_t) kBuildCap * sizeof(Tup));
+            for (u32 i = tid; i < kSlots * sizeof(slot_t) / 16; i += T) slots[i] = make_uint4(kEmpty, kEmpty, kEmpty, kEmpty);
+        }
+        mbar_wait(&s_bar, phase);
+        phase ^= 1;
+        __syncthreads();
+
+        // ---- build: ITEMS claims in flight per thread; only the losers of the first CAS walk on ----
+        int dup = 0;
+        for (u32 i0 = tid; i0 < nb; i0 += ROUND) {
+            u64 v[ITEMS];
+            u32 pk[ITEMS];
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                const u32 i = i0 + k * T;
+                v[k] = i < nb ? lds64(sb + i * 16 + 8) : 0;
+            }
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) pk[k] = slot_of(v[k]) << 16;
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                const u32 i = i0 + k * T;
+                const u32 old = i < nb ? cas32_shared(sl + (pk[k] >> 14), kSlotEmpty, i) : kSlotEmpty;
+                pk[k] |= old & 0xFFFFu;
+            }
+#pragma unroll
+            for (int k = 0; k < ITEMS; ++k) {
+                u32 o = pk[k] & 0xFFFFu, hs = pk[k] >> 16;
+                while (o != 0xFFFFu) {   // the slot was taken: by an equal key (then this partition is the ranked kernel's), or not
+                    if (lds64(sb + o * 16 + 8) == v[k]) dup = 1;
+                    hs = (hs + 1) & (kSlots - 1);
+                    o = cas32_shared(sl + (hs << 2), kSlotEmpty, i0 + k * T) & 0xFFFFu;
+                }
+            }
+        }
+        if (tid == 0) s_posbase = posres;
+        dup = __syncthreads_or(dup);
+        const u64 base = s_posbase;
+        // one capacity check per item: when an item's slots do not all fit, the cursor ends beyond the capacity and the host
+        // redoes the join with the ranked emitter, so nothing of such an item needs to be written
+        const bool fits = base + n <= a.capacity;
+        Pair *const outp = a.out + base;
+        if (dup) {
+            // duplicate build keys: the reserved slots stay holes, the ranked kernel reserves its own
+            if (fits)
+                for (u32 i = tid; i < n; i += T) st_stream(outp + i, RHJ_HOLE, RHJ_HOLE);
+            if (tid == 0) {
+                miss_items += n;
+                left[atomicAdd(nleft, 1u)] = it;
+            }
+            __syncthreads();
+            continue;
+        }
+
+        // ---- probe + positional emit: tuple i of the item writes slot base + i ----
+        // One round: load the NEXT round's tuples into tn (in flight while this round is probed), probe the tuples in tc.
+        // Two tuple sets that swap roles from round to round (no register copies).
+        auto round = [&](Tup (&tc)[ITEMS], Tup (&tn)[ITEMS], const u32 r0) {
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) {
+                const u32 o = r0 + (PF ? ROUND : 0) + j * T + tid;
+                if (PF) {
+                    if (o < n) tn[j] = ld_stream(inp + o);
+                } else {
+                    if (o < n && r0) tc[j] = ld_stream(inp + o);
+                }
+            }
+            const u32 o0 = r0 + tid;
+            u32 pk[ITEMS];
+            u64 bw[ITEMS];
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) pk[j] = slot_of(tc[j].val) << 16;
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) pk[j] |= (o0 + j * T < n ? lds32(sl + (pk[j] >> 14)) : kSlotEmpty) & 0xFFFFu;
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) {
+                const u32 c = pk[j] & 0xFFFFu;
+                bw[j] = c != 0xFFFFu ? lds64(sb + c * 16 + 8) : 0;
+            }
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) {
+                // the low half becomes the matching build tuple or 0xFFFF; a first slot holding another key is the rare case
+                u32 c = pk[j] & 0xFFFFu;
+                if (c != 0xFFFFu && bw[j] != tc[j].val) {
+                    u32 hs = pk[j] >> 16;
+                    do {
+                        hs = (hs + 1) & (kSlots - 1);
+                        c = lds32(sl + (hs << 2)) & 0xFFFFu;
+                    } while (c != 0xFFFFu && lds64(sb + c * 16 + 8) != tc[j].val);
+                    pk[j] = c;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) {
+                const u32 c = pk[j] & 0xFFFFu;
+                bw[j] = c != 0xFFFFu ? lds64(sb + c * 16) : RHJ_HOLE;
+            }
+            Pair *const q = outp + o0;
+            if (fits) {
+                if (a.build_is_S) {
+#pragma unroll
+                    for (int j = 0; j < ITEMS; ++j)
+                        if (o0 + j * T < n) st_stream(q + j * T, (pk[j] & 0xFFFFu) != 0xFFFFu ? tc[j].key : RHJ_HOLE, bw[j]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < ITEMS; ++j)
+                        if (o0 + j * T < n) st_stream(q + j * T, bw[j], (pk[j] & 0xFFFFu) != 0xFFFFu ? tc[j].key : RHJ_HOLE);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) miss += (o0 + j * T < n) && (pk[j] & 0xFFFFu) == 0xFFFFu;
+        };
+        if (PF) {
+            Tup t2[ITEMS];
+            for (u32 r0 = 0; r0 < n; r0 += 2 * ROUND) {
+                round(t, t2, r0);
+                if (r0 + ROUND >= n) break;
+                round(t2, t, r0 + ROUND);
+            }
+        } else {
+            for (u32 r0 = 0; r0 < n; r0 += ROUND) round(t, t, r0);
+        }
+        __syncthreads();  // everyone is done with this table before it is overwritten
+    }
+    const u64 w = warp_sum64((u64) miss + miss_items);
+    if ((tid & 31) == 0 && w) atomicAdd(a.holes, w);
+}
+
 
 }  // namespace rhj

@@ -400,7 +400,7 @@ int rhj_pipe_join_device(rhj_ctx *ctx, rhj_pair *d_out, uint64_t capacity, uint6
     // positional emit (rhj_join.cuh): one slot per probe tuple, no ranking and no reservation latency in the probe loop
     bool pos = ctx->positional && ctx->pos_skip == 0;
     if (!pos && ctx->pos_skip > 0) ctx->pos_skip--;
-    if (pos) rc = launch_join<kJoinFused, true>(ctx, st, j, item_cap);
+    if (pos) rc = launch_join_positional(ctx, st, j, item_cap);
     else rc = launch_join<kJoinFused>(ctx, st, j, item_cap);
     if (rc) return rc;
     PipeCollectArgs ca{};

@@ -877,3 +877,63 @@ def test_sample_free_shortcut_after_agreeing_joins_and_its_overflow(monkeypatch)
         assert len(set(ls)) == 1
     finally:
         e.close()
+
+
+# ---- the positional emitter: k_join_pos<3, prefetch> (default), k_join_pos<4>, and the r02 kernel k_join<FUSED, POS> ----
+@pytest.mark.parametrize("env", [{}, {"RHJ_JOIN_POS_ITEMS": "4"}, {"RHJ_JOIN_LEAN": "0"}])
+def test_positional_emitter_kernels(env, monkeypatch):
+    """The fused emitter takes the positional path whenever the output buffer has a slot per probe tuple.  Shapes that
+    reach every branch of k_join_pos and of the leftover launch behind it: every probe tuple matches (no holes), some do
+    not (holes closed on the host side), duplicate build keys in a few / in all partitions (items handed to the ranked
+    kernel, their reserved slots become holes), a build partition of several chunks, probe partitions of many rounds,
+    either side as the build side, a result larger than the buffer (redone by the ranked emitter, which reports the
+    need).  Sorted pairs == oracle for all three kernels."""
+    from radixhashjoin_b200 import RadixHashJoin
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    e = RadixHashJoin(0)
+    rng = np.random.default_rng(2024)
+
+    def run(R, S, cap=None):
+        exp = O.oracle_join(R, S)
+        cap = max(len(R), len(S), len(exp), 1) if cap is None else cap
+        out, n = e.join_device(to_dev(R), to_dev(S), capacity=cap, emit=EMIT_FUSED)
+        assert n == len(exp)
+        if n <= 300000:
+            assert np.array_equal(O.sort_pairs(pairs_np(out)), O.sort_pairs(exp))
+        else:                                            # large results: count + multiset digest (sum and xor of mixed pairs)
+            assert O.pairs_digest(pairs_np(out)) == O.pairs_digest(exp)
+        return len(exp)
+
+    def uniq(n, id_base=0):
+        return O.as_tuples(rng.permutation(n).astype(np.uint64) + np.uint64(id_base), rng.permutation(1 << 22)[:n].astype(np.uint64))
+
+    try:
+        for nB, nP in ((1, 1), (5, 3000), (2000, 2000), (2560, 70000), (2561, 70000), (40000, 40000), (1 << 19, 1 << 21)):
+            B = uniq(nB)
+            # (a) foreign-key style: every probe tuple has exactly one partner
+            P = O.as_tuples(np.arange(nP, dtype=np.uint64) + np.uint64(1 << 40), B["payload"][rng.integers(0, nB, nP)])
+            assert run(B, P) == nP
+            assert run(P, B) == nP                       # the probe side given as R: pairs still come out R-first
+            # (b) a third of the probe tuples have no partner: holes
+            Pm = P.copy()
+            Pm["payload"][::3] += np.uint64(1 << 50)
+            run(B, Pm)
+            # (c) duplicate build keys in a few partitions: those items go to the ranked kernel
+            Bd = B.copy()
+            Bd["payload"][: max(1, nB // 50)] = Bd["payload"][-max(1, nB // 50):]
+            run(Bd, P)
+        # (d) duplicate build keys everywhere (every item is handed over), and one build key repeated beyond a table's capacity
+        R, S = rand_rel(rng, 60000, 9000), rand_rel(rng, 50000, 9000, 1 << 33)
+        run(R, S)
+        hot = O.as_tuples(np.arange(9000, dtype=np.uint64), np.concatenate([np.full(6000, 77, dtype=np.uint64),
+                                                                            np.arange(1000, 4000, dtype=np.uint64)]))
+        probe = O.as_tuples(np.arange(20000, dtype=np.uint64) + np.uint64(1 << 36), rng.integers(0, 4000, 20000, dtype=np.uint64))
+        run(hot, probe)
+        # (e) a buffer with a slot per probe tuple but too small for the result: the error carries the need
+        exp = O.oracle_join(R, S)
+        with pytest.raises(RhjError) as ei:
+            e.join_device(to_dev(R), to_dev(S), capacity=max(len(R), len(S)), emit=EMIT_FUSED)
+        assert ei.value.code == 4 and ei.value.needed == len(exp)
+    finally:
+        e.close()
