@@ -252,12 +252,20 @@ int launch_join_positional(rhj_ctx *ctx, cudaStream_t st, const JoinArgs &a, u32
     Item *left = (Item *) ctx->items_left.p;
     u32 *nleft = (u32 *) (sc + kScLeft);
     const u32 grid = std::min<u32>(std::max<u32>(item_cap, 1), (u32) ctx->num_sms * RHJ_JOIN_MINBLOCKS);
-    if (ctx->join_pos_items == 4) {   // four tuples per thread and round, no prefetch (the second tuple set would spill)
-        CK(set_smem(k_join_pos<4, false>, kJoinSmem));
-        k_join_pos<4, false><<<grid, kJoinThreads, kJoinSmem, st>>>(a, left, nleft);
-    } else {                          // three tuples per thread and round, the next round's in flight
-        CK(set_smem(k_join_pos<3, true>, kJoinSmem));
-        k_join_pos<3, true><<<grid, kJoinThreads, kJoinSmem, st>>>(a, left, nleft);
+    // three probe tuples per thread and round, the next round's in flight (four without prefetch: measured slower, 1.77 vs
+    // 1.55 ms); RHJ_JOIN_POS_V selects the variant of the kernel (see k_join_pos)
+    switch (ctx->join_pos_v) {
+    case 1:
+        CK(set_smem(k_join_pos<3, true, 1>, kJoinSmem));
+        k_join_pos<3, true, 1><<<grid, kJoinThreads, kJoinSmem, st>>>(a, left, nleft);
+        break;
+    case 3:
+        CK(set_smem(k_join_pos<3, true, 3>, kJoinSmem));
+        k_join_pos<3, true, 3><<<grid, kJoinThreads, kJoinSmem, st>>>(a, left, nleft);
+        break;
+    default:
+        CK(set_smem(k_join_pos<3, true, 0>, kJoinSmem));
+        k_join_pos<3, true, 0><<<grid, kJoinThreads, kJoinSmem, st>>>(a, left, nleft);
     }
     CK(cudaGetLastError());
     ctx->info.kernel_launches++;
@@ -1090,7 +1098,7 @@ int rhj_create(int device, rhj_ctx **out) {
     if ((e = getenv("RHJ_NO_TRUST"))) ctx->trust_sample = atoi(e) == 0;
     if ((e = getenv("RHJ_NO_POS"))) ctx->positional = atoi(e) == 0;
     if ((e = getenv("RHJ_JOIN_LEAN"))) ctx->join_lean = atoi(e) != 0;
-    if ((e = getenv("RHJ_JOIN_POS_ITEMS"))) ctx->join_pos_items = atoi(e);
+    if ((e = getenv("RHJ_JOIN_POS_V"))) ctx->join_pos_v = atoi(e);
     if ((e = getenv("RHJ_NO_SHARD_OPT2"))) ctx->shard_optimistic2 = atoi(e) == 0;
     if ((e = getenv("RHJ_SHARD_OPT2_WORLD"))) ctx->shard_opt2_world = (u32) std::max(0, atoi(e));
     if ((e = getenv("RHJ_HOST_CHUNK"))) ctx->host_chunk = std::max<long long>(1, atoll(e));

@@ -397,7 +397,19 @@ __device__ __forceinline__ u32 cas32_shared(u32 addr, u32 cmp, u32 val) {
 }
 
 // PF: prefetch the next round's probe tuples (a second tuple set: 4 registers per tuple); without it a round loads its own.
-template <int ITEMS, bool PF>
+// V, what the per-instruction counts of the first build showed (profiles/r02_ncu/k_join_pos3_source_sass.csv):
+//   bit 0: nvcc re-derives the 12-instruction hash wherever pk's slot half is used (once more per probe tuple, and at the
+//          head of every walk) instead of keeping it in a register; an empty asm makes the value opaque, so it is kept;
+//   bit 1: thread 0 claims the NEXT work item while the current one is probed and publishes it in front of the barrier
+//          that ends the item, which then also starts the next one: one CTA barrier and one exposed global round trip
+//          (the claiming atomic) less per item.
+template <int V>
+__device__ __forceinline__ u32 slot_hi16(u64 v) {
+    u32 h = slot_of(v) << 16;
+    if (V & 1) asm volatile("" : "+r"(h));
+    return h;
+}
+template <int ITEMS, bool PF, int V = 0>
 __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join_pos(JoinArgs a, Item *left, u32 *nleft) {
     constexpr u32 T = kJoinThreads, ROUND = T * ITEMS;
     extern __shared__ __align__(128) unsigned char dyn_smem[];   // [kBuildCap] staged build tuples | [kSlots] u32 slots
@@ -414,10 +426,17 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join_pos(J
     __syncthreads();
     const u32 nitems = *a.nitems;
     u32 phase = 0;
-
-    while (true) {
+    u32 nxt = 0;   // V & 2, thread 0: the next item, claimed while the current one is probed
+    if (V & 2) {
         if (tid == 0) s_item = atomicAdd(a.work_counter, 1u);
         __syncthreads();
+    }
+
+    while (true) {
+        if (!(V & 2)) {
+            if (tid == 0) s_item = atomicAdd(a.work_counter, 1u);
+            __syncthreads();
+        }
         const u32 item = s_item;
         if (item >= nitems) break;
         const Item it = a.items[item];
@@ -425,6 +444,15 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join_pos(J
         const u64 p0 = a.offP[it.part] + (u64) it.chunk * kProbeChunk;
         const u64 p1 = min(a.endP[it.part], p0 + (u64) kProbeChunk);
         if (b1 - b0 > kBuildCap) {   // several build chunks (duplicate-heavy keys no radix bit can split)
+            if (V & 2) {
+                __syncthreads();     // everybody has read s_item
+                if (tid == 0) {
+                    left[atomicAdd(nleft, 1u)] = it;
+                    s_item = atomicAdd(a.work_counter, 1u);
+                }
+                __syncthreads();
+                continue;
+            }
             if (tid == 0) left[atomicAdd(nleft, 1u)] = it;
             __syncthreads();         // nobody is still reading s_item when thread 0 overwrites it
             continue;
@@ -463,7 +491,7 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join_pos(J
                 v[k] = i < nb ? lds64(sb + i * 16 + 8) : 0;
             }
 #pragma unroll
-            for (int k = 0; k < ITEMS; ++k) pk[k] = slot_of(v[k]) << 16;
+            for (int k = 0; k < ITEMS; ++k) pk[k] = slot_hi16<V>(v[k]);
 #pragma unroll
             for (int k = 0; k < ITEMS; ++k) {
                 const u32 i = i0 + k * T;
@@ -480,7 +508,11 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join_pos(J
                 }
             }
         }
-        if (tid == 0) s_posbase = posres;
+        if (tid == 0) {
+            s_posbase = posres;
+            // everybody read s_item in front of the barrier behind the table load: the claim's latency hides behind the probe
+            if (V & 2) nxt = atomicAdd(a.work_counter, 1u);
+        }
         dup = __syncthreads_or(dup);
         const u64 base = s_posbase;
         // one capacity check per item: when an item's slots do not all fit, the cursor ends beyond the capacity and the host
@@ -494,6 +526,7 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join_pos(J
             if (tid == 0) {
                 miss_items += n;
                 left[atomicAdd(nleft, 1u)] = it;
+                if (V & 2) s_item = nxt;
             }
             __syncthreads();
             continue;
@@ -516,7 +549,7 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join_pos(J
             u32 pk[ITEMS];
             u64 bw[ITEMS];
 #pragma unroll
-            for (int j = 0; j < ITEMS; ++j) pk[j] = slot_of(tc[j].val) << 16;
+            for (int j = 0; j < ITEMS; ++j) pk[j] = slot_hi16<V>(tc[j].val);
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j) pk[j] |= (o0 + j * T < n ? lds32(sl + (pk[j] >> 14)) : kSlotEmpty) & 0xFFFFu;
 #pragma unroll
@@ -567,7 +600,8 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join_pos(J
         } else {
             for (u32 r0 = 0; r0 < n; r0 += ROUND) round(t, t, r0);
         }
-        __syncthreads();  // everyone is done with this table before it is overwritten
+        if ((V & 2) && tid == 0) s_item = nxt;
+        __syncthreads();  // everyone is done with this table before it is overwritten (V & 2: ... and sees the next item)
     }
     const u64 w = warp_sum64((u64) miss + miss_items);
     if ((tid & 31) == 0 && w) atomicAdd(a.holes, w);

@@ -879,15 +879,15 @@ def test_sample_free_shortcut_after_agreeing_joins_and_its_overflow(monkeypatch)
         e.close()
 
 
-# ---- the positional emitter: k_join_pos<3, prefetch> (default), k_join_pos<4>, and the r02 kernel k_join<FUSED, POS> ----
-@pytest.mark.parametrize("env", [{}, {"RHJ_JOIN_POS_ITEMS": "4"}, {"RHJ_JOIN_LEAN": "0"}])
+# ---- the positional emitter: the variants of k_join_pos (RHJ_JOIN_POS_V) and the r02 kernel k_join<FUSED, POS> ----
+@pytest.mark.parametrize("env", [{"RHJ_JOIN_POS_V": "0"}, {"RHJ_JOIN_POS_V": "1"}, {"RHJ_JOIN_POS_V": "3"}, {"RHJ_JOIN_LEAN": "0"}])
 def test_positional_emitter_kernels(env, monkeypatch):
     """The fused emitter takes the positional path whenever the output buffer has a slot per probe tuple.  Shapes that
     reach every branch of k_join_pos and of the leftover launch behind it: every probe tuple matches (no holes), some do
     not (holes closed on the host side), duplicate build keys in a few / in all partitions (items handed to the ranked
     kernel, their reserved slots become holes), a build partition of several chunks, probe partitions of many rounds,
     either side as the build side, a result larger than the buffer (redone by the ranked emitter, which reports the
-    need).  Sorted pairs == oracle for all three kernels."""
+    need).  Sorted pairs == oracle for every kernel."""
     from radixhashjoin_b200 import RadixHashJoin
     for k, v in env.items():
         monkeypatch.setenv(k, v)
