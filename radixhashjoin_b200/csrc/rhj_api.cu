@@ -256,16 +256,16 @@ int launch_join_positional(rhj_ctx *ctx, cudaStream_t st, const JoinArgs &a, u32
     // 1.55 ms); RHJ_JOIN_POS_V selects the variant of the kernel (see k_join_pos)
     switch (ctx->join_pos_v) {
     case 1:
-        CK(set_smem(k_join_pos<3, true, 1>, kJoinSmem));
-        k_join_pos<3, true, 1><<<grid, kJoinThreads, kJoinSmem, st>>>(a, left, nleft);
+        CK(set_smem(k_join_pos<3, 1>, kJoinSmem));
+        k_join_pos<3, 1><<<grid, kJoinThreads, kJoinSmem, st>>>(a, left, nleft);
         break;
     case 3:
-        CK(set_smem(k_join_pos<3, true, 3>, kJoinSmem));
-        k_join_pos<3, true, 3><<<grid, kJoinThreads, kJoinSmem, st>>>(a, left, nleft);
+        CK(set_smem(k_join_pos<3, 3>, kJoinSmem));
+        k_join_pos<3, 3><<<grid, kJoinThreads, kJoinSmem, st>>>(a, left, nleft);
         break;
     default:
-        CK(set_smem(k_join_pos<3, true, 0>, kJoinSmem));
-        k_join_pos<3, true, 0><<<grid, kJoinThreads, kJoinSmem, st>>>(a, left, nleft);
+        CK(set_smem(k_join_pos<3, 0>, kJoinSmem));
+        k_join_pos<3, 0><<<grid, kJoinThreads, kJoinSmem, st>>>(a, left, nleft);
     }
     CK(cudaGetLastError());
     ctx->info.kernel_launches++;

@@ -63,7 +63,7 @@ struct rhj_ctx {
     // probe tuple matches (foreign-key style joins); a join that left more than 1/64 holes switches it off for the next 16.
     bool positional = true;    // RHJ_NO_POS=1 disables
     int pos_skip = 0;
-    int join_pos_v = 0;        // variant of k_join_pos (RHJ_JOIN_POS_V): 0, 1 = hash kept in a register, 3 = 1 + next item claimed early
+    int join_pos_v = 3;        // variant of k_join_pos (RHJ_JOIN_POS_V): 3 (default) = hash kept in a register + next item claimed early; 1, 0 = without
     bool join_lean = true;     // positional emitter = k_join_pos + leftover launch (RHJ_JOIN_LEAN=0: the r02 kernel k_join<FUSED, POS>)
     DevBuf sample;            // sampled pass-1 histogram
     int scatter_mode = 0;     // 0 staged per-thread stores, 1 TMA bulk stores (RHJ_SCATTER_MODE)

@@ -396,7 +396,8 @@ __device__ __forceinline__ u32 cas32_shared(u32 addr, u32 cmp, u32 val) {
     return old;
 }
 
-// PF: prefetch the next round's probe tuples (a second tuple set: 4 registers per tuple); without it a round loads its own.
+// Four tuples per thread and round without the prefetch (the second tuple set would spill) were measured slower: 1.77 ms
+// against 1.55 ms (profiles/r02_call95_*).
 // V, what the per-instruction counts of the first build showed (profiles/r02_ncu/k_join_pos3_source_sass.csv):
 //   bit 0: nvcc re-derives the 12-instruction hash wherever pk's slot half is used (once more per probe tuple, and at the
 //          head of every walk) instead of keeping it in a register; an empty asm makes the value opaque, so it is kept;
@@ -409,7 +410,7 @@ __device__ __forceinline__ u32 slot_hi16(u64 v) {
     if (V & 1) asm volatile("" : "+r"(h));
     return h;
 }
-template <int ITEMS, bool PF, int V = 0>
+template <int ITEMS, int V>
 __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join_pos(JoinArgs a, Item *left, u32 *nleft) {
     constexpr u32 T = kJoinThreads, ROUND = T * ITEMS;
     extern __shared__ __align__(128) unsigned char dyn_smem[];   // [kBuildCap] staged build tuples | [kSlots] u32 slots
@@ -538,12 +539,8 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join_pos(J
         auto round = [&](Tup (&tc)[ITEMS], Tup (&tn)[ITEMS], const u32 r0) {
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j) {
-                const u32 o = r0 + (PF ? ROUND : 0) + j * T + tid;
-                if (PF) {
-                    if (o < n) tn[j] = ld_stream(inp + o);
-                } else {
-                    if (o < n && r0) tc[j] = ld_stream(inp + o);
-                }
+                const u32 o = r0 + ROUND + j * T + tid;
+                if (o < n) tn[j] = ld_stream(inp + o);
             }
             const u32 o0 = r0 + tid;
             u32 pk[ITEMS];
@@ -590,15 +587,11 @@ __global__ void __launch_bounds__(kJoinThreads, RHJ_JOIN_MINBLOCKS) k_join_pos(J
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j) miss += (o0 + j * T < n) && (pk[j] & 0xFFFFu) == 0xFFFFu;
         };
-        if (PF) {
-            Tup t2[ITEMS];
-            for (u32 r0 = 0; r0 < n; r0 += 2 * ROUND) {
-                round(t, t2, r0);
-                if (r0 + ROUND >= n) break;
-                round(t2, t, r0 + ROUND);
-            }
-        } else {
-            for (u32 r0 = 0; r0 < n; r0 += ROUND) round(t, t, r0);
+        Tup t2[ITEMS];
+        for (u32 r0 = 0; r0 < n; r0 += 2 * ROUND) {
+            round(t, t2, r0);
+            if (r0 + ROUND >= n) break;
+            round(t2, t, r0 + ROUND);
         }
         if ((V & 2) && tid == 0) s_item = nxt;
         __syncthreads();  // everyone is done with this table before it is overwritten (V & 2: ... and sees the next item)
