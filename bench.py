@@ -585,28 +585,31 @@ def run_b200(args, rank, world, local_rank):
         del dres, pR, pS
         e2e["pageable"] = {"value": n_in_local / dtp, "unit": UNIT, "ms_per_step": dtp * 1e3, "steps": kp, "verified": ok_p,
                            "note": "inputs in pageable (malloc'd) host arrays, as host/Result.cpp passes them"}
-    elif world > 1 and args.no_e2e:
-        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "--no-e2e"}
     elif world > 1:
-        # the shards live in pinned HOST memory: every step copies this rank's R and S to the device, runs the sharded join
-        # and copies the pairs back (radixhashjoin_b200/distributed.py: HostResidentSteps); wall clock, max over ranks
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": "--no-e2e"}
+
+    def sharded_e2e():
+        """e2e at N > 1: the shards live in pinned HOST memory; every step copies this rank's R and S to the device, runs the
+        sharded join and copies the pairs back (radixhashjoin_b200/distributed.py: HostResidentSteps); wall clock, max over ranks."""
         from radixhashjoin_b200.distributed import HostResidentSteps
-        hs = HostResidentSteps(step, R, S, out, world, dist=dist, local_world=env_int("LOCAL_WORLD_SIZE", world))
-        if hs.ok:
+        none = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+        try:
+            hs = HostResidentSteps(step, R, S, out, world, dist=dist, local_world=env_int("LOCAL_WORLD_SIZE", world))
+            if not hs.ok:   # agreed between the ranks before the first step: nobody is left waiting
+                return dict(none, note=hs.why)
             k = max(1, min(args.steps, args.e2e_steps))
             dt, cnt, d2h = hs.run(k, warmup=1)
             out[:cnt].copy_(hs.hout[:cnt])   # the HOST copy of the last result is what gets checked
             e2e_ok = verify(eng.pairs_digest(out[:cnt]))
             by = torch.tensor([hs.h2d_bytes, d2h], dtype=torch.int64, device=dev)
             dist.all_reduce(by, op=dist.ReduceOp.SUM)
-            e2e = {"value": n_in_local * world / dt, "unit": UNIT, "h2d_bytes_per_step": int(by[0].item()),
-                   "d2h_bytes_per_step": int(by[1].item()), "ms_per_step": dt * 1e3, "steps": k, "verified": e2e_ok,
-                   "api": f"{strategy} sharded join with host-resident shards: per step and rank H2D of both shards from pinned "
-                          "host memory -> exchange + join -> D2H of the pairs into pinned host memory, read by the host; "
-                          "bytes are summed over the ranks, the time is the slowest rank's wall clock"}
-        else:
-            e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "note": hs.why}
-        del hs
+            return {"value": n_in_local * world / dt, "unit": UNIT, "h2d_bytes_per_step": int(by[0].item()),
+                    "d2h_bytes_per_step": int(by[1].item()), "ms_per_step": dt * 1e3, "steps": k, "verified": e2e_ok,
+                    "api": f"{strategy} sharded join with host-resident shards: per step and rank H2D of both shards from "
+                           "pinned host memory -> exchange + join -> D2H of the pairs into pinned host memory, read by the "
+                           "host; bytes are summed over the ranks, the time is the slowest rank's wall clock"}
+        except Exception as ex:  # an error every rank hits alike must not cost the headline line
+            return dict(none, note="e2e failed: " + repr(ex)[:160])
 
     # ---- CPU baseline on this box's host cores (rank 0, N = 1 only, bounded sample) ----
     cpu = None
@@ -625,7 +628,7 @@ def run_b200(args, rank, world, local_rank):
         except Exception as ex:  # never lose the headline line to the extra block
             target = {"unavailable": repr(ex)[:200]}
 
-    if rank == 0:
+    def make_line(e2e_v):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "strong" if world > 1 and args.workload == "fk" else "weak",
@@ -656,7 +659,7 @@ def run_b200(args, rank, world, local_rank):
                                   "frac_moved_of_measured_hbm": moved_step / (ms_step * 1e-3) / 1e9 / peak if moved_step else None,
                                   "note": "canonical bytes credit the histograms the histogram-free passes skip; bytes_moved "
                                           "counts only what ran (plan optimistic mask %d)" % plan["optimistic_pass1"]},
-                "e2e": e2e, "cpu_baseline": cpu}
+                "e2e": e2e_v, "cpu_baseline": cpu}
         if target:
             line["target_2p28"] = target
         if shard_timeline:
@@ -665,9 +668,35 @@ def run_b200(args, rank, world, local_rank):
             line["nvlink"] = nvlink
         if world == 1 and not args.no_small_work:
             line["small_work"] = small_work_wall(args.small_work_ref)
-        print(json.dumps(line), flush=True)
+        return line
+
+    if world > 1 and not args.no_e2e:
+        # The host-resident e2e runs LAST and under a watchdog: whatever happens to it (a rank that dies in the pinned
+        # allocation, an exchange left waiting), rank 0 still prints the line of the measurements above.
+        done = threading.Lock()
+
+        def bail():
+            if done.acquire(blocking=False):
+                if rank == 0:
+                    print(json.dumps(make_line({"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                                "note": f"e2e did not finish within {args.e2e_timeout_s} s"})), flush=True)
+                os._exit(0)
+        wd = threading.Timer(args.e2e_timeout_s, bail)
+        wd.daemon = True
+        wd.start()
+        e2e = sharded_e2e()
+        wd.cancel()
+        if not done.acquire(blocking=False):
+            time.sleep(600)   # the watchdog is printing the line and ends the process
+    if rank == 0:
+        print(json.dumps(make_line(e2e)), flush=True)
     if world > 1:
+        # the line is out; a teardown that waits for a rank that is gone must not keep the job alive
+        td = threading.Timer(60.0, lambda: os._exit(0))
+        td.daemon = True
+        td.start()
         dist.destroy_process_group()
+        td.cancel()
 
 
 def main():
@@ -682,6 +711,7 @@ def main():
     ap.add_argument("--fk-probe-log2", type=int, default=0, help="fk: GLOBAL probe size (default: 2^log2n per GPU)")
     ap.add_argument("--emit", default="fused", choices=["fused", "count_then_write"])
     ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-timeout-s", type=float, default=240.0, help="N > 1: give up on the host-resident e2e after this long")
     ap.add_argument("--cpu-log2n", type=int, default=26, help="cpu_baseline sample size (2^k x 2^k)")
     ap.add_argument("--ref-log2n", type=int, default=0, help="--impl reference: 2^k x 2^k per step (default: --log2n, the stated config)")
     ap.add_argument("--ref-budget-s", type=float, default=150.0, help="--impl reference: stop timing after this many seconds of joins")
