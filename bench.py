@@ -308,6 +308,12 @@ def run_reference(args, rank):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
+def _device(local_rank):
+    """The rank's device.  (tests/test_bench_flow.py replaces this, the engine and the exchange classes to walk through
+    the orchestration below -- verification, line assembly, the N > 1 e2e and its watchdog -- without a GPU.)"""
+    return f"cuda:{local_rank}"
+
+
 def run_b200(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -316,7 +322,7 @@ def run_b200(args, rank, world, local_rank):
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
-    dev = f"cuda:{local_rank}"
+    dev = _device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     emit = EMIT_FUSED if args.emit == "fused" else EMIT_COUNT_THEN_WRITE
