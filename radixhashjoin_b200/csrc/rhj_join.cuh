@@ -25,6 +25,8 @@
 // A double-buffered, register-prefetching variant was measured and was not faster
 // (profiles/r01_tuning_notes.md).
 // Algorithmic bytes: 16 per input tuple read + 16 per result pair written.
+// The fused emitter's default, k_join_pos (bottom of this file), takes the common case -- one table load, unique build keys --
+// with instruction-level-parallel loops and leaves everything else to k_join<FUSED>.
 #pragma once
 #include "rhj_device.cuh"
 

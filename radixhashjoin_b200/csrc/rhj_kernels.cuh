@@ -5,7 +5,8 @@
 //  (2) prefix sum            PartitionJob::run 163-169, Result.cpp:100-107    k_scan_digits, k_scan_parts_plan
 //  (3) partition scatter     PartitionJob::run 170-174 + structs.cpp:183-194  k_scatter
 //  (4) per-bucket build/probe Result::join_buckets, Result.cpp:43-76           k_join            (rhj_join.cuh)
-//  (5) emitter               add_result/addAll, Result.cpp:21-35,78-84,111-121 k_join<COUNT|WRITE|FUSED>, k_scan_items
+//  (5) emitter               add_result/addAll, Result.cpp:21-35,78-84,111-121 k_join<COUNT|WRITE|FUSED>, k_scan_items;
+//                                                                             k_join_pos + k_holes_* (positional emit)
 //  filters / gathers         Query.cpp:94-146, structs.cpp:217-226, Query.cpp:66-74   k_filter_*, k_gather_*
 //
 // Data layout in HBM: relations stay 16-byte AoS tuples {rowid, value} end to end (the caller's
