@@ -29,6 +29,19 @@ def test_every_declared_symbol_is_exported_and_bound():
     assert sorted(_lib.SIGNATURES) == names
 
 
+def test_ctypes_signatures_have_the_arity_of_the_prototypes():
+    """every prototype of include/rhj.h and its ctypes binding (radixhashjoin_b200/_lib.py) take the same number of
+    arguments -- an argument added on one side only would shift every later one silently"""
+    src = open(os.path.join(ROOT, "include", "rhj.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = dict(re.findall(r"\b(rhj_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", src))
+    assert sorted(protos) == sorted(_lib.SIGNATURES)
+    for name, args in protos.items():
+        args = args.strip()
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        assert n == len(_lib.SIGNATURES[name][1]), f"{name}: {n} arguments in rhj.h, {len(_lib.SIGNATURES[name][1])} in _lib.SIGNATURES"
+
+
 def test_pod_layouts_match_reference():
     # tuple {u64 key; u64 payload} structs.h:33-36 ; key_tuple {u64 keyR; u64 keyS} Result.h:9-12
     assert api.TUPLE_DTYPE.itemsize == 16 and api.TUPLE_DTYPE.fields["payload"][1] == 8
