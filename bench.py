@@ -543,7 +543,11 @@ def run_b200(args, rank, world, local_rank):
         roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                     "traffic": traffic, "traffic_source": traffic_src,
                     "peak_source": peak_src, "kernel_ms": acc[dom],
-                    "algorithmic_bytes_per_launch": alg_bytes[dom]}
+                    "algorithmic_bytes_per_launch": alg_bytes[dom],
+                    # the same figure for every bandwidth kernel of the step (the dominant one is the headline above)
+                    "by_kernel": {k: {"kernel_ms": round(acc[k], 4), "algorithmic_bytes_per_launch": alg_bytes[k],
+                                      "frac": alg_bytes[k] / (acc[k] * 1e-3) / 1e9 / peak}
+                                  for k in alg_bytes if acc.get(k, 0) > 0}}
     b_alg_step = 96 * n_join + 16 * m_local     # canonical 2-pass plan
     step_gbs = b_alg_step / (ms_step * 1e-3) / 1e9
     moved_step = bytes_moved(nR, nS, m_local, plan) if world == 1 else None

@@ -176,6 +176,8 @@ def test_single_gpu_flow_prints_the_contract_line():
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["verified"] is True and d["gpu_launches"] == 33
     assert d["config"]["workload"] == "uniform_unique_2^12x2^12" and d["scaling"] == "weak"
     assert d["roofline"]["kernel"] == "scatter2" and d["roofline"]["bound"] == "hbm" and 0 < d["roofline"]["frac"]
+    assert set(d["roofline"]["by_kernel"]) == {"scatter1", "scatter2", "join"}
+    assert d["roofline"]["by_kernel"]["scatter2"]["frac"] == d["roofline"]["frac"]
     assert d["step_roofline"]["bytes_moved"] == 80 * (2 << 12) + 16 * (1 << 12)     # both histogram-free passes ran (mask 7)
 
 
