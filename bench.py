@@ -489,6 +489,14 @@ def run_b200(args, rank, world, local_rank):
 
     verified = verify(eng.pairs_digest(pairs))
     m_local = count
+    # how evenly the result (= the work of the local joins) is spread over the ranks: equal values meet on one rank, so skewed
+    # probe keys load their owner more ("accept imbalance and report it"; no hot-key replication here)
+    shard_balance = None
+    if world > 1:
+        cs = [None] * world
+        dist.all_gather_object(cs, int(count))
+        mean = sum(cs) / world
+        shard_balance = {"pairs_per_rank": cs, "max_over_mean": (max(cs) / mean) if mean else None}
 
     shard_timeline = None
     if world > 1 and strategy in ("dma", "pipe"):
@@ -672,6 +680,8 @@ def run_b200(args, rank, world, local_rank):
                 "e2e": e2e_v, "cpu_baseline": cpu}
         if target:
             line["target_2p28"] = target
+        if shard_balance:
+            line["shard_balance"] = shard_balance
         if shard_timeline:
             line["shard_timeline_ms"] = shard_timeline
         if nvlink:

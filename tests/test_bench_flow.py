@@ -192,6 +192,7 @@ def test_two_rank_flow_verifies_across_ranks_and_agrees_on_the_e2e():
     assert "no collective in the step" in d["config"]["parallelism"]
     assert d["e2e"]["value"] is None and "pinned host allocation failed" in d["e2e"]["note"] or "another rank" in d["e2e"]["note"]
     assert d["shard_timeline_ms"][0][0] == "start" and d["nvlink"]["bytes_out_per_gpu"] > 0
+    assert sum(d["shard_balance"]["pairs_per_rank"]) == 1 << 12 and 1.0 <= d["shard_balance"]["max_over_mean"] < 1.2
     assert d["roofline"]["kernel"] in ("scatter1", "join")
 
 
