@@ -6,7 +6,7 @@
 // oracle/_ref/libref_rhj.so.  No reference source is copied into the repo.
 //
 // It fills two `relation`s (structs.h:38-49), runs
-// Result::multiRadixHashJoin (Result.cpp:90-124) on a JobScheduler with
+// Result::multiRadixHashJoin (Result.cpp:90-124) on a process-wide JobScheduler with
 // NUM_OF_THREADS workers (JobScheduler.h:11) and flattens the page list in the
 // order a consumer walks it (intermediate.cpp:151-160).
 #include <cstdint>
@@ -35,8 +35,18 @@ int ref_multi_radix_hash_join(const uint64_t *R, uint64_t nR, const uint64_t *S,
     memcpy(relR.tuples, R, nR * sizeof(tuple));
     memcpy(relS.tuples, S, nS * sizeof(tuple));
 
-    JobScheduler js;
-    js.init(NUM_OF_THREADS);
+    // ONE scheduler for the life of the process, as in the reference program (a query thread keeps its JobScheduler across
+    // all its joins, MainScheduler.cpp:6-14) -- and never stopped: JobScheduler::stop() sets `done` and broadcasts WITHOUT
+    // holding queueLock (JobScheduler.cpp:139-145), so a worker that has just tested the flag and not yet reached
+    // pthread_cond_wait (JobScheduler.cpp:29-31) misses the wake-up and stop() joins it forever.  A harness that created
+    // and stopped a scheduler per call hit that window right behind tiny joins (observed: one hung run of the CPU suite).
+    // The idle workers end with the process.
+    static JobScheduler *const jsp = [] {
+        JobScheduler *p = new JobScheduler;
+        p->init(NUM_OF_THREADS);
+        return p;
+    }();
+    JobScheduler &js = *jsp;
     uint64_t n = 0;
     uint64_t *flat = nullptr;
     {
@@ -58,8 +68,6 @@ int ref_multi_radix_hash_join(const uint64_t *R, uint64_t nR, const uint64_t *S,
             }
         }
     }
-    js.stop();
-    js.destroy();
     *out = flat;
     *count = n;
     return 0;
