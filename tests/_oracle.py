@@ -16,6 +16,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORC_SO = os.path.join(ROOT, "oracle", "_build", "liborc.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_rhj.so")
+REF_T16_SO = os.path.join(ROOT, "oracle", "_ref", "libref_rhj_t16.so")      # the same sources with NUM_OF_THREADS = 16
 REF_DIR = os.path.join(ROOT, "oracle", "_ref")
 
 TUPLE = np.dtype([("key", "<u8"), ("payload", "<u8")])      # structs.h:33-36
@@ -59,25 +60,27 @@ def liborc():
     return _orc
 
 
-_ref = None
+_ref = {}
 
 
-def have_ref():
-    return os.path.exists(REF_SO)
+def have_ref(threads=8):
+    return os.path.exists(REF_SO if threads == 8 else REF_T16_SO)
 
 
-def libref():
-    global _ref
-    if _ref is None:
-        lib = ctypes.CDLL(REF_SO)
+def libref(threads=8):
+    """the reference as shipped (8 workers per JobScheduler), or its 16-worker build (oracle/Makefile)"""
+    assert threads in (8, 16)
+    if threads not in _ref:
+        lib = ctypes.CDLL(REF_SO if threads == 8 else REF_T16_SO)
         lib.ref_num_threads.restype = ctypes.c_int
         lib.ref_multi_radix_hash_join.restype = ctypes.c_int
         lib.ref_multi_radix_hash_join.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64,
                                                   ctypes.POINTER(ctypes.c_void_p), _u64p,
                                                   ctypes.POINTER(ctypes.c_double), ctypes.c_int]
         lib.ref_free.argtypes = [ctypes.c_void_p]
-        _ref = lib
-    return _ref
+        assert lib.ref_num_threads() == threads
+        _ref[threads] = lib
+    return _ref[threads]
 
 
 def as_tuples(keys, payloads):
@@ -108,19 +111,19 @@ def oracle_join(R, S):
     return _take(out, cnt.value, liborc().orc_free)
 
 
-def reference_join(R, S, want_pairs=True):
+def reference_join(R, S, want_pairs=True, threads=8):
     """The real reference (oracle/_ref).  Returns (pairs, seconds); pairs is None if not wanted."""
     R = np.ascontiguousarray(R, dtype=TUPLE)
     S = np.ascontiguousarray(S, dtype=TUPLE)
     out = ctypes.c_void_p()
     cnt = ctypes.c_uint64()
     sec = ctypes.c_double()
-    rc = libref().ref_multi_radix_hash_join(R.ctypes.data, len(R), S.ctypes.data, len(S), ctypes.byref(out),
+    rc = libref(threads).ref_multi_radix_hash_join(R.ctypes.data, len(R), S.ctypes.data, len(S), ctypes.byref(out),
                                             ctypes.byref(cnt), ctypes.byref(sec), 1 if want_pairs else 0)
     assert rc == 0
     if not want_pairs:
         return cnt.value, sec.value
-    return _take(out, cnt.value, libref().ref_free), sec.value
+    return _take(out, cnt.value, libref(threads).ref_free), sec.value
 
 
 def oracle_partition(T, fanout=256):

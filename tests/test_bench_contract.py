@@ -30,6 +30,21 @@ def test_reference_arm_prints_the_contract_line():
     assert d["config"]["workload"] == "uniform_unique_2^27x2^27"
 
 
+def test_reference_arm_reports_the_faster_of_its_builds():
+    """on a host with more than 8 CPUs (forced here) the 16-worker build of the same sources is timed too and the faster one
+    is the value; both figures are in the line"""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "libref_rhj_t16.so")):
+        return
+    env = dict(os.environ, RHJ_REF_ALL_BUILDS="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                          "--ref-log2n", "18"], cwd=ROOT, capture_output=True, timeout=600, env=env)
+    assert out.returncode == 0, out.stderr.decode()[-2000:]
+    d = json.loads([l for l in out.stdout.decode().splitlines() if l.startswith("{")][0])
+    b = d["cpu_baseline"]["builds_tuples_per_s"]
+    assert set(b) == {"NUM_OF_THREADS=8", "NUM_OF_THREADS=16"}
+    assert d["cpu_baseline"]["cores"] in (8, 16) and d["value"] == max(b.values()) == b[f"NUM_OF_THREADS={d['cpu_baseline']['cores']}"]
+
+
 def test_b200_arm_needs_a_gpu():
     import torch
     if torch.cuda.is_available():

@@ -52,6 +52,19 @@ def test_oracle_equals_reference_u64_extremes():
     assert np.array_equal(a, b)
 
 
+@pytest.mark.skipif(not O.have_ref(16), reason="oracle/_ref/libref_rhj_t16.so not built")
+def test_sixteen_worker_build_of_the_reference_joins_like_the_shipped_one():
+    """bench.py's reference arm may report the 16-worker build (NUM_OF_THREADS overridden at build time, oracle/Makefile): same
+    sources, same multiset of pairs as the 8-worker build the oracle is pinned against."""
+    rng = np.random.default_rng(16)
+    for nR, nS, dom in ((0, 7, 3), (1, 1, 1), (300, 5000, 40), (70000, 90000, 30000), (1 << 19, 1 << 19, 1 << 18)):
+        R = O.as_tuples(rng.permutation(nR).astype(np.uint64), rng.integers(0, dom, nR, dtype=np.uint64))
+        S = O.as_tuples(rng.permutation(nS).astype(np.uint64) + np.uint64(1 << 35), rng.integers(0, dom, nS, dtype=np.uint64))
+        a, _ = O.reference_join(R, S, threads=8)
+        b, _ = O.reference_join(R, S, threads=16)
+        assert len(a) == len(b) and np.array_equal(O.sort_pairs(a), O.sort_pairs(b))
+
+
 def test_next_prime_known_answers():
     """auxFun.cpp:4-22 incl. its special cases (2 -> 5 because 3 is skipped by the %3 test)."""
     got = [O.liborc().orc_next_prime(i) for i in range(0, 20)]
